@@ -1,0 +1,218 @@
+/*
+ * lorikeet_b200.h — C ABI of the B200-native read<->haplotype likelihood hot path.
+ *
+ * This is the drop-in boundary for rhysnewell/Lorikeet's two vector entry points
+ * (reference paths relative to the Lorikeet checkout @ 3fbbdec):
+ *
+ *   gkl::pairhmm::forward()        used at src/pair_hmm/pair_hmm.rs:348-366
+ *   gkl::smithwaterman::align()    used at src/smith_waterman/smith_waterman_aligner.rs:56-61
+ *
+ * plus batch forms of both (one FFI call per active region / per batch of regions),
+ * and the engine-level pre/post-ops of
+ * src/pair_hmm/pair_hmm_likelihood_calculation_engine.rs:195-242.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every buffer passed in; the
+ *     library keeps no caller pointer after a call returns.
+ *   - every entry point returns an lk_status (0 = OK); nothing unwinds or aborts
+ *     across the ABI.  lk_last_error(ctx) gives a message for the last failure on ctx.
+ *   - an lk_ctx is bound to one CUDA device and is thread-safe (calls serialise on an
+ *     internal lock; use one ctx per host thread for concurrency).
+ *   - all compute happens on the GPU.  There is no CPU fallback: without a CUDA
+ *     device lk_create fails with LK_ERR_CUDA.
+ */
+#ifndef LORIKEET_B200_H
+#define LORIKEET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lk_ctx lk_ctx;
+
+typedef enum lk_status {
+    LK_OK = 0,
+    LK_ERR_INVALID = 1,   /* bad argument: null pointer, length mismatch, empty sequence ... */
+    LK_ERR_CUDA = 2,      /* CUDA runtime failure (message in lk_last_error)                  */
+    LK_ERR_NOMEM = 3,     /* host or device allocation failed                                 */
+    LK_ERR_CAPACITY = 4   /* output buffer too small (e.g. max_ops for a CIGAR)               */
+} lk_status;
+
+/* Replaces gkl::smithwaterman::OverhangStrategy (smith_waterman_aligner.rs:71-72,146-148;
+ * shape mirrored at src/smith_waterman/bindings.rs:5-32). */
+typedef enum lk_sw_overhang {
+    LK_SW_SOFTCLIP = 0,
+    LK_SW_INDEL = 1,
+    LK_SW_LEADING_INDEL = 2,
+    LK_SW_IGNORE = 3
+} lk_sw_overhang;
+
+/* Replaces gkl::smithwaterman::Parameters (smith_waterman_aligner.rs:12-25, bindings.rs:34-66). */
+typedef struct lk_sw_params {
+    int32_t match_value;
+    int32_t mismatch_penalty;
+    int32_t gap_open_penalty;
+    int32_t gap_extend_penalty;
+} lk_sw_params;
+
+/* per-pair result flags of the PairHMM entry points */
+enum {
+    LK_FLAG_RESCUED = 1,   /* fp32 pass under-flowed or was out of its safe domain; value is from the f64 pass */
+    LK_FLAG_NEG_INF = 2    /* even f64 under-flowed: value is -inf (the reference returns log10(0) here too)  */
+};
+
+/* ---------------------------------------------------------------- context */
+
+/* device < 0 selects the current CUDA device. */
+lk_status lk_create(int device, lk_ctx **out_ctx);
+void lk_destroy(lk_ctx *ctx);
+const char *lk_last_error(const lk_ctx *ctx);
+const char *lk_version(void);
+/* Mirrors PairHMM::do_not_use_tristate_correction (pair_hmm.rs:189-191): mismatch prior err/1 instead of err/3. */
+lk_status lk_set_tristate_correction(lk_ctx *ctx, int use_tristate);
+/* 0 (default): fp32 scaled-linear first, f64 only for flagged pairs (the gkl convention);
+ * 1: every pair in f64 with the reference's own operation order (slow; for validation). */
+lk_status lk_set_force_f64(lk_ctx *ctx, int force_f64);
+
+/* ---------------------------------------------------------------- PairHMM */
+
+/*
+ * A batch of active regions.  Region g owns reads [region_read_start[g], region_read_start[g+1])
+ * and haplotypes [region_hap_start[g], region_hap_start[g+1]).  Read r occupies bytes
+ * [read_off[r], read_off[r+1]) of each of the four read arenas; haplotype h occupies
+ * [hap_off[h], hap_off[h+1]) of hap_bases.  read_gcp may be NULL, in which case gcp_constant is
+ * the gap-continuation penalty of every base (PairHMMInputScoreImputator::gap_continuation_penalties,
+ * pair_hmm_likelihood_calculation_engine.rs:649-651).
+ */
+typedef struct lk_pairhmm_batch {
+    int64_t n_regions;
+    const int64_t *region_read_start; /* n_regions + 1 */
+    const int64_t *region_hap_start;  /* n_regions + 1 */
+    const int64_t *read_off;          /* n_reads + 1   */
+    const uint8_t *read_bases;
+    const uint8_t *read_qual;
+    const uint8_t *read_ins;
+    const uint8_t *read_del;
+    const uint8_t *read_gcp;          /* per-base, or NULL */
+    uint8_t gcp_constant;
+    const int64_t *hap_off;           /* n_haps + 1    */
+    const uint8_t *hap_bases;
+} lk_pairhmm_batch;
+
+/* Number of (read, haplotype) pairs = sum_g reads_g * haps_g, and sum of R*H over them. */
+lk_status lk_pairhmm_batch_dims(const lk_pairhmm_batch *batch, int64_t *n_pairs, int64_t *n_cells);
+
+/*
+ * Batch form of PairHMM::compute_likelihoods (pair_hmm.rs:345-375): for every region, for every
+ * read r, for every haplotype h: out[base_g + r*A_g + h] = log10 P(read | hap), the layout of
+ * m_log_likelihood_array (pair_hmm.rs:262-263,349-369); base_g is the running sum of
+ * reads*haps over earlier regions.  All pointers are HOST pointers; the call stages, runs and
+ * copies back (chunked, overlapped) and returns when out is complete.
+ * flags may be NULL; otherwise one LK_FLAG_* byte per pair.
+ */
+lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags);
+
+/*
+ * Device-resident variant used for kernel-only timing: lk_pairhmm_upload stages a batch into
+ * HBM once; lk_pairhmm_run_resident launches the kernels on the resident copy (no H2D/D2H) and
+ * returns after the stream has drained; lk_pairhmm_download copies results back.
+ */
+typedef struct lk_resident lk_resident;
+lk_status lk_pairhmm_upload(lk_ctx *ctx, const lk_pairhmm_batch *batch, lk_resident **out_res);
+lk_status lk_pairhmm_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms /* may be NULL */);
+lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *out, uint8_t *flags);
+void lk_resident_free(lk_ctx *ctx, lk_resident *res);
+
+/*
+ * Single-pair convenience wrapper with exactly the argument list of the function pointer
+ * returned by gkl::pairhmm::forward() (pair_hmm.rs:358-365,
+ * tests/vector_pair_hmm_unit_tests.rs:51-59): (hap, read, qual, ins, del, gcp) -> log10 lk.
+ * All five read arrays have read_len entries.
+ */
+lk_status lk_pairhmm_forward(lk_ctx *ctx, const uint8_t *hap, int64_t hap_len, const uint8_t *read,
+                             const uint8_t *qual, const uint8_t *ins, const uint8_t *del, const uint8_t *gcp,
+                             int64_t read_len, double *out_log10);
+
+/* ---------------------------------------------------------------- Smith-Waterman */
+
+/*
+ * Batch form of SmithWatermanAligner::align (smith_waterman_aligner.rs:47-113) for n_pairs
+ * independent (reference, alternate) pairs sharing one parameter set and overhang strategy.
+ * Pair p: ref bytes [ref_off[p], ref_off[p+1]) of refs, alt likewise.
+ * Results, per pair: n_ops[p] CIGAR operations in forward order in cigar_ops[p*max_ops ..],
+ * BAM-encoded (len << 4 | op; M=0 I=1 D=2 S=4), and alignment_offset[p]
+ * (SmithWatermanAlignmentResult, smith_waterman_aligner.rs:455-458).
+ * n_ops[p] = -1: empty sequence (the reference asserts, :65-68); -2: more than max_ops operations.
+ */
+lk_status lk_sw_batch_host(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                           const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                           lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops,
+                           int32_t *alignment_offset);
+
+/* Resident variant for kernel-only timing (same contract as the PairHMM one). */
+lk_status lk_sw_upload(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                       const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                       lk_sw_overhang strategy, int32_t max_ops, lk_resident **out_res);
+lk_status lk_sw_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms);
+lk_status lk_sw_download(lk_ctx *ctx, lk_resident *res, uint32_t *cigar_ops, int32_t *n_ops,
+                         int32_t *alignment_offset);
+
+/*
+ * Single-pair wrapper with the argument list of the function pointer returned by
+ * gkl::smithwaterman::align() (smith_waterman_aligner.rs:56-61): the CIGAR is returned as ASCII
+ * text ("31M20S") in cigar_text (NUL-terminated, capacity cigar_cap) exactly as the reference
+ * parses it with CigarString::try_from, plus the alignment offset.
+ */
+lk_status lk_sw_align(lk_ctx *ctx, const uint8_t *ref, int64_t ref_len, const uint8_t *alt, int64_t alt_len,
+                      const lk_sw_params *params, lk_sw_overhang strategy, char *cigar_text, size_t cigar_cap,
+                      int32_t *alignment_offset);
+
+/* ---------------------------------------------------------------- engine pre/post-ops (host side) */
+
+/* PCRErrorModel (pair_hmm_likelihood_calculation_engine.rs:60-70) */
+typedef enum lk_pcr_model { LK_PCR_NONE = 0, LK_PCR_HOSTILE = 1, LK_PCR_AGGRESSIVE = 2, LK_PCR_CONSERVATIVE = 3 } lk_pcr_model;
+
+/* Arguments of PairHMMLikelihoodCalculationEngine::new (:129-167), in the same order. */
+typedef struct lk_engine_args {
+    uint8_t constant_gcp;
+    double log10_global_read_mismapping_rate;
+    int32_t pcr_error_model;                 /* lk_pcr_model */
+    uint8_t base_quality_score_threshold;
+    int32_t dynamic_read_disqualification;
+    double read_disqualification_scale;
+    double expected_error_rate_per_base;
+    int32_t symmetrically_normalize_alleles_to_reference;
+    int32_t disable_cap_read_qualities_to_mapq;
+    int32_t modify_soft_clipped_bases;       /* accepted for signature parity; clipping itself is the caller's */
+} lk_engine_args;
+
+/*
+ * modify_read_qualities (:352-426) on packed arenas, in place: apply_pcr_error_model (:502-526),
+ * cap_minimum_read_qualities (:428-458).  read_mapq has one entry per read.  Host-side, threaded.
+ */
+lk_status lk_engine_modify_read_qualities(const lk_engine_args *args, int64_t n_reads, const int64_t *read_off,
+                                          const uint8_t *read_bases, uint8_t *read_qual, uint8_t *read_ins,
+                                          uint8_t *read_del, const uint8_t *read_mapq, int n_threads);
+
+/*
+ * Region driver = compute_read_likelihoods (:195-242) for a batch of single-sample regions:
+ * modify_read_qualities on copies -> PairHMM on the GPU -> transpose into the reference's
+ * [allele][read] matrices -> normalize_likelihoods (allele_likelihoods.rs:378-444) ->
+ * filter_poorly_modeled_evidence (:925-1018, thresholds :244-319 computed from the ORIGINAL
+ * qualities and lengths, reproducing the "HMMQuals" key quirk).
+ * values: per region an [A_g x R_g] row-major f64 block at the same base offsets as
+ * lk_pairhmm_batch_host; removed reads' columns are compacted away and the tail set to NaN as the
+ * reference does.  keep[r] (per read, may be NULL) = 1 if the read survived the filter.
+ * ref_allele_index[g] (may be NULL = 0 for all) is the index of the reference haplotype in region g.
+ */
+lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_engine_args *args, const lk_pairhmm_batch *batch,
+                                             const uint8_t *read_mapq, const int32_t *ref_allele_index,
+                                             double *values, uint8_t *keep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LORIKEET_B200_H */

@@ -1,0 +1,138 @@
+"""ctypes binding of liblorikeet_b200.so (the C ABI of include/lorikeet_b200.h).
+
+The library is the product; this module only loads it and declares signatures.  There is no
+Python or CPU fallback: if the shared object is missing or no CUDA device is present, calls fail
+loudly (LorikeetError).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "liblorikeet_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+u32p = C.POINTER(C.c_uint32)
+i64p = C.POINTER(C.c_int64)
+f64p = C.POINTER(C.c_double)
+f32p = C.POINTER(C.c_float)
+
+LK_OK, LK_ERR_INVALID, LK_ERR_CUDA, LK_ERR_NOMEM, LK_ERR_CAPACITY = 0, 1, 2, 3, 4
+STATUS_NAMES = {0: "LK_OK", 1: "LK_ERR_INVALID", 2: "LK_ERR_CUDA", 3: "LK_ERR_NOMEM", 4: "LK_ERR_CAPACITY"}
+
+# the 29 entry points include/lorikeet_b200.h declares
+EXPORTED_SYMBOLS = [
+    "lk_create", "lk_destroy", "lk_last_error", "lk_version", "lk_set_tristate_correction", "lk_set_force_f64",
+    "lk_pairhmm_batch_dims", "lk_pairhmm_batch_host", "lk_pairhmm_upload", "lk_pairhmm_run_resident",
+    "lk_pairhmm_download", "lk_resident_free", "lk_pairhmm_forward",
+    "lk_sw_batch_host", "lk_sw_upload", "lk_sw_run_resident", "lk_sw_download", "lk_sw_align",
+    "lk_engine_modify_read_qualities", "lk_engine_compute_read_likelihoods",
+]
+
+
+class LorikeetError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), message))
+        self.status = status
+
+
+class PairHmmBatchStruct(C.Structure):
+    _fields_ = [
+        ("n_regions", C.c_int64),
+        ("region_read_start", i64p),
+        ("region_hap_start", i64p),
+        ("read_off", i64p),
+        ("read_bases", u8p),
+        ("read_qual", u8p),
+        ("read_ins", u8p),
+        ("read_del", u8p),
+        ("read_gcp", u8p),
+        ("gcp_constant", C.c_uint8),
+        ("hap_off", i64p),
+        ("hap_bases", u8p),
+    ]
+
+
+class SwParams(C.Structure):
+    _fields_ = [("match_value", C.c_int32), ("mismatch_penalty", C.c_int32),
+                ("gap_open_penalty", C.c_int32), ("gap_extend_penalty", C.c_int32)]
+
+
+class EngineArgs(C.Structure):
+    _fields_ = [
+        ("constant_gcp", C.c_uint8),
+        ("log10_global_read_mismapping_rate", C.c_double),
+        ("pcr_error_model", C.c_int32),
+        ("base_quality_score_threshold", C.c_uint8),
+        ("dynamic_read_disqualification", C.c_int32),
+        ("read_disqualification_scale", C.c_double),
+        ("expected_error_rate_per_base", C.c_double),
+        ("symmetrically_normalize_alleles_to_reference", C.c_int32),
+        ("disable_cap_read_qualities_to_mapq", C.c_int32),
+        ("modify_soft_clipped_bases", C.c_int32),
+    ]
+
+
+_LIB = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built: run __graft_entry__.build()."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        raise LorikeetError(LK_ERR_CUDA, "liblorikeet_b200.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`" % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    vp = C.c_void_p
+    L.lk_create.restype = C.c_int
+    L.lk_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.lk_destroy.restype = None
+    L.lk_destroy.argtypes = [vp]
+    L.lk_last_error.restype = C.c_char_p
+    L.lk_last_error.argtypes = [vp]
+    L.lk_version.restype = C.c_char_p
+    L.lk_set_tristate_correction.restype = C.c_int
+    L.lk_set_tristate_correction.argtypes = [vp, C.c_int]
+    L.lk_set_force_f64.restype = C.c_int
+    L.lk_set_force_f64.argtypes = [vp, C.c_int]
+    bp = C.POINTER(PairHmmBatchStruct)
+    L.lk_pairhmm_batch_dims.restype = C.c_int
+    L.lk_pairhmm_batch_dims.argtypes = [bp, i64p, i64p]
+    L.lk_pairhmm_batch_host.restype = C.c_int
+    L.lk_pairhmm_batch_host.argtypes = [vp, bp, f64p, u8p]
+    L.lk_pairhmm_upload.restype = C.c_int
+    L.lk_pairhmm_upload.argtypes = [vp, bp, C.POINTER(vp)]
+    L.lk_pairhmm_run_resident.restype = C.c_int
+    L.lk_pairhmm_run_resident.argtypes = [vp, vp, f32p]
+    L.lk_pairhmm_download.restype = C.c_int
+    L.lk_pairhmm_download.argtypes = [vp, vp, f64p, u8p]
+    L.lk_resident_free.restype = None
+    L.lk_resident_free.argtypes = [vp, vp]
+    L.lk_pairhmm_forward.restype = C.c_int
+    L.lk_pairhmm_forward.argtypes = [vp, u8p, C.c_int64, u8p, u8p, u8p, u8p, u8p, C.c_int64, f64p]
+    sp = C.POINTER(SwParams)
+    L.lk_sw_batch_host.restype = C.c_int
+    L.lk_sw_batch_host.argtypes = [vp, C.c_int64, i64p, u8p, i64p, u8p, sp, C.c_int, C.c_int32, u32p, i32p, i32p]
+    L.lk_sw_upload.restype = C.c_int
+    L.lk_sw_upload.argtypes = [vp, C.c_int64, i64p, u8p, i64p, u8p, sp, C.c_int, C.c_int32, C.POINTER(vp)]
+    L.lk_sw_run_resident.restype = C.c_int
+    L.lk_sw_run_resident.argtypes = [vp, vp, f32p]
+    L.lk_sw_download.restype = C.c_int
+    L.lk_sw_download.argtypes = [vp, vp, u32p, i32p, i32p]
+    L.lk_sw_align.restype = C.c_int
+    L.lk_sw_align.argtypes = [vp, u8p, C.c_int64, u8p, C.c_int64, sp, C.c_int, C.c_char_p, C.c_size_t, i32p]
+    ep = C.POINTER(EngineArgs)
+    L.lk_engine_modify_read_qualities.restype = C.c_int
+    L.lk_engine_modify_read_qualities.argtypes = [ep, C.c_int64, i64p, u8p, u8p, u8p, u8p, u8p, C.c_int]
+    L.lk_engine_compute_read_likelihoods.restype = C.c_int
+    L.lk_engine_compute_read_likelihoods.argtypes = [vp, ep, bp, u8p, i32p, f64p, u8p]
+    # introspection helpers (not part of the public header)
+    L.lk_resident_launch_count.restype = C.c_int32
+    L.lk_resident_launch_count.argtypes = [vp]
+    L.lk_resident_cells.restype = C.c_int64
+    L.lk_resident_cells.argtypes = [vp]
+    L.lk_resident_pairs.restype = C.c_int64
+    L.lk_resident_pairs.argtypes = [vp]
+    _LIB = L
+    return L

@@ -1,0 +1,193 @@
+"""Context = one lk_ctx (one CUDA device).  Thin, typed wrappers over the C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import LorikeetError
+
+SW_STRATEGY = {"SoftClip": 0, "InDel": 1, "LeadingInDel": 2, "Ignore": 3}
+CIGAR_CHARS = "MIDNSHP=X"
+
+
+def cigar_to_string(ops):
+    return "".join("%d%s" % (int(o) >> 4, CIGAR_CHARS[int(o) & 0xF]) for o in ops)
+
+
+class Context:
+    def __init__(self, device=-1):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        st = self._L.lk_create(int(device), C.byref(self._h))
+        if st != 0:
+            self._h = None
+            raise LorikeetError(st, "lk_create failed (a CUDA device is required; there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st):
+        if st != 0:
+            raise LorikeetError(st, (self._L.lk_last_error(self._h) or b"").decode())
+
+    def version(self):
+        return self._L.lk_version().decode()
+
+    def set_tristate_correction(self, on):
+        self._check(self._L.lk_set_tristate_correction(self._h, 1 if on else 0))
+
+    def set_force_f64(self, on):
+        self._check(self._L.lk_set_force_f64(self._h, 1 if on else 0))
+
+    # ---------------------------------------------------------------- PairHMM
+    def pairhmm_batch(self, batch, want_flags=False):
+        """lk_pairhmm_batch_host: host arrays in, log10 likelihoods out (layout r*A + h per region)."""
+        n = batch.n_pairs
+        out = np.empty(n, dtype=np.float64)
+        flags = np.zeros(n, dtype=np.uint8)
+        s = batch.as_struct()
+        self._check(self._L.lk_pairhmm_batch_host(self._h, C.byref(s), out.ctypes.data_as(_lib.f64p),
+                                                  flags.ctypes.data_as(_lib.u8p)))
+        return (out, flags) if want_flags else out
+
+    def pairhmm_forward(self, hap, read, qual, ins, dele, gcp):
+        """Single pair, gkl::pairhmm::forward()'s argument list (pair_hmm.rs:358-365)."""
+        from .batch import _u8
+        hap, read, qual, ins, dele, gcp = map(_u8, (hap, read, qual, ins, dele, gcp))
+        out = C.c_double(0.0)
+        p = lambda a: a.ctypes.data_as(_lib.u8p)
+        self._check(self._L.lk_pairhmm_forward(self._h, p(hap), hap.size, p(read), p(qual), p(ins), p(dele), p(gcp),
+                                               read.size, C.byref(out)))
+        return out.value
+
+    def pairhmm_upload(self, batch):
+        return ResidentPairHmm(self, batch)
+
+    # ---------------------------------------------------------------- Smith-Waterman
+    def sw_batch(self, ref_off, refs, alt_off, alts, params, strategy, max_ops=64):
+        from .batch import _u8, _i64
+        ref_off, alt_off, refs, alts = _i64(ref_off), _i64(alt_off), _u8(refs), _u8(alts)
+        n = len(ref_off) - 1
+        if isinstance(strategy, str):
+            strategy = SW_STRATEGY[strategy]
+        prm = _lib.SwParams(*[int(x) for x in params])
+        ops = np.zeros((n, max_ops), dtype=np.uint32)
+        n_ops = np.zeros(n, dtype=np.int32)
+        offs = np.zeros(n, dtype=np.int32)
+        self._check(self._L.lk_sw_batch_host(self._h, n, ref_off.ctypes.data_as(_lib.i64p), refs.ctypes.data_as(_lib.u8p),
+                                             alt_off.ctypes.data_as(_lib.i64p), alts.ctypes.data_as(_lib.u8p),
+                                             C.byref(prm), int(strategy), int(max_ops), ops.ctypes.data_as(_lib.u32p),
+                                             n_ops.ctypes.data_as(_lib.i32p), offs.ctypes.data_as(_lib.i32p)))
+        return ops, n_ops, offs
+
+    def sw_align(self, ref, alt, params, strategy, cigar_cap=4096):
+        """Single pair, gkl::smithwaterman::align()'s shape: returns (offset, "31M20S")."""
+        from .batch import _u8
+        ref, alt = _u8(ref), _u8(alt)
+        if isinstance(strategy, str):
+            strategy = SW_STRATEGY[strategy]
+        prm = _lib.SwParams(*[int(x) for x in params])
+        buf = C.create_string_buffer(cigar_cap)
+        off = C.c_int32(0)
+        self._check(self._L.lk_sw_align(self._h, ref.ctypes.data_as(_lib.u8p), ref.size, alt.ctypes.data_as(_lib.u8p),
+                                        alt.size, C.byref(prm), int(strategy), buf, cigar_cap, C.byref(off)))
+        return off.value, buf.value.decode()
+
+    def sw_upload(self, ref_off, refs, alt_off, alts, params, strategy, max_ops=64):
+        return ResidentSw(self, ref_off, refs, alt_off, alts, params, strategy, max_ops)
+
+
+class ResidentPairHmm:
+    """A batch staged in HBM (lk_pairhmm_upload) for kernel-only timing."""
+
+    def __init__(self, ctx, batch):
+        self.ctx, self.batch = ctx, batch
+        self._r = C.c_void_p()
+        s = batch.as_struct()
+        ctx._check(ctx._L.lk_pairhmm_upload(ctx._h, C.byref(s), C.byref(self._r)))
+        self.n_pairs = int(ctx._L.lk_resident_pairs(self._r))
+        self.n_cells = int(ctx._L.lk_resident_cells(self._r))
+
+    def run(self):
+        ms = C.c_float(0.0)
+        self.ctx._check(self.ctx._L.lk_pairhmm_run_resident(self.ctx._h, self._r, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launch_count(self):
+        return int(self.ctx._L.lk_resident_launch_count(self._r))
+
+    def download(self, want_flags=False):
+        out = np.empty(self.n_pairs, dtype=np.float64)
+        flags = np.zeros(self.n_pairs, dtype=np.uint8)
+        self.ctx._check(self.ctx._L.lk_pairhmm_download(self.ctx._h, self._r, out.ctypes.data_as(_lib.f64p),
+                                                        flags.ctypes.data_as(_lib.u8p)))
+        return (out, flags) if want_flags else out
+
+    def free(self):
+        if self._r:
+            self.ctx._L.lk_resident_free(self.ctx._h, self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass
+
+
+class ResidentSw:
+    def __init__(self, ctx, ref_off, refs, alt_off, alts, params, strategy, max_ops):
+        from .batch import _u8, _i64
+        self.ctx = ctx
+        ref_off, alt_off, refs, alts = _i64(ref_off), _i64(alt_off), _u8(refs), _u8(alts)
+        self.n = len(ref_off) - 1
+        self.max_ops = int(max_ops)
+        if isinstance(strategy, str):
+            strategy = SW_STRATEGY[strategy]
+        prm = _lib.SwParams(*[int(x) for x in params])
+        self._r = C.c_void_p()
+        ctx._check(ctx._L.lk_sw_upload(ctx._h, self.n, ref_off.ctypes.data_as(_lib.i64p), refs.ctypes.data_as(_lib.u8p),
+                                       alt_off.ctypes.data_as(_lib.i64p), alts.ctypes.data_as(_lib.u8p), C.byref(prm),
+                                       int(strategy), self.max_ops, C.byref(self._r)))
+        self.n_cells = int((np.diff(ref_off) * np.diff(alt_off)).sum())
+
+    def run(self):
+        ms = C.c_float(0.0)
+        self.ctx._check(self.ctx._L.lk_sw_run_resident(self.ctx._h, self._r, C.byref(ms)))
+        return ms.value
+
+    def download(self):
+        ops = np.zeros((self.n, self.max_ops), dtype=np.uint32)
+        n_ops = np.zeros(self.n, dtype=np.int32)
+        offs = np.zeros(self.n, dtype=np.int32)
+        self.ctx._check(self.ctx._L.lk_sw_download(self.ctx._h, self._r, ops.ctypes.data_as(_lib.u32p),
+                                                   n_ops.ctypes.data_as(_lib.i32p), offs.ctypes.data_as(_lib.i32p)))
+        return ops, n_ops, offs
+
+    def free(self):
+        if self._r:
+            self.ctx._L.lk_resident_free(self.ctx._h, self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass

@@ -1,0 +1,119 @@
+// host_prep.cpp — K selection and warp-task packing for the PairHMM fast path (host side).
+//
+// A warp task = reads of ONE region packed side by side into the 32 lanes (each read takes
+// ceil(R/K) lanes); the kernel then sweeps every haplotype of that region, i.e. the same
+// "for read { for haplotype }" order as the reference driver (src/pair_hmm/pair_hmm.rs:349-369).
+#include "host_prep.h"
+
+#include <algorithm>
+
+namespace lk {
+
+const int *fast_k_values(int *n) {
+    static const int ks[] = { LK_FAST_KS };
+    *n = (int)(sizeof(ks) / sizeof(ks[0]));
+    return ks;
+}
+
+// Pick rows-per-lane for a read of length R: maximise useful cell-updates per issue slot.
+//   lanes per read G = ceil(R/K); reads per warp p = floor(32/G);
+//   row efficiency = p*R / (32*K); skew efficiency ~ H/(H+G-1) with H ~ 2R;
+//   issue slots per cell ~ 8 + 9/K; a mild penalty for the lower occupancy of the big-K variants.
+int choose_k(int R, int force_k) {
+    int n = 0;
+    const int *ks = fast_k_values(&n);
+    if (force_k > 0) {
+        for (int i = 0; i < n; i++)
+            if (ks[i] == force_k && R <= 32 * force_k) return force_k;
+    }
+    double best = -1.0;
+    int best_k = 0;
+    for (int i = 0; i < n; i++) {
+        const int K = ks[i];
+        if (R > 32 * K) continue;
+        const int G = (R + K - 1) / K;
+        const int p = 32 / G;
+        const double row_eff = (double)(p * R) / (32.0 * K);
+        const double H = std::max(2.0 * R, 64.0);
+        const double skew = H / (H + G - 1);
+        const double occ = K <= 10 ? 1.0 : (K <= 12 ? 0.97 : 0.93);
+        const double score = row_eff * skew * occ / (8.0 + 9.0 / K);
+        if (score > best) { best = score; best_k = K; }
+    }
+    return best_k;  // 0: too long for the fast path
+}
+
+
+void build_prep(const lk_pairhmm_batch *b, int64_t n_reads, int64_t n_haps, int force_k, bool fast_enabled, HostPrep &P) {
+    P.read_region.resize((size_t)n_reads);
+    P.read_out_base.resize((size_t)n_reads);
+    P.henc_off.resize((size_t)n_haps);
+    int64_t w = 0;
+    for (int64_t h = 0; h < n_haps; h++) {
+        const int H = (int)(b->hap_off[h + 1] - b->hap_off[h]);
+        P.henc_off[(size_t)h] = w + HENC_PADL;
+        w += H + HENC_PADL + HENC_PADR;
+        P.h_max = std::max(P.h_max, H);
+    }
+    P.henc_words = w;
+    int nk = 0;
+    const int *ks = fast_k_values(&nk);
+    std::vector<int8_t> read_k((size_t)n_reads, 0);
+    std::vector<int> k_by_len;  // memo
+    int64_t base = 0;
+    for (int64_t g = 0; g < b->n_regions; g++) {
+        const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
+        const int64_t h0 = b->region_hap_start[g], h1 = b->region_hap_start[g + 1];
+        const int64_t A = h1 - h0;
+        for (int64_t r = r0; r < r1; r++) {
+            P.read_region[(size_t)r] = (int32_t)g;
+            P.read_out_base[(size_t)r] = base + (r - r0) * A;
+            const int R = (int)(b->read_off[r + 1] - b->read_off[r]);
+            int K = 0;
+            if (fast_enabled) {
+                if ((size_t)R >= k_by_len.size()) k_by_len.resize((size_t)R + 1, -1);
+                if (k_by_len[(size_t)R] < 0) k_by_len[(size_t)R] = choose_k(R, force_k);
+                K = k_by_len[(size_t)R];
+            }
+            read_k[(size_t)r] = (int8_t)K;
+            if (K == 0 && fast_enabled)
+                for (int64_t h = h0; h < h1; h++) P.direct.push_back(RescuePair{ (int32_t)r, (int32_t)h });
+        }
+        base += (r1 - r0) * A;
+        if (r1 > r0 && h1 > h0) P.n_cells += (b->read_off[r1] - b->read_off[r0]) * (b->hap_off[h1] - b->hap_off[h0]);
+    }
+    P.n_pairs = base;
+    if (!fast_enabled) return;
+    // one launch per K; inside a launch tasks follow region order so neighbouring warps share haplotypes
+    for (int ki = 0; ki < nk; ki++) {
+        const int K = ks[ki];
+        FastLaunch L;
+        L.K = K;
+        L.first_task = (int32_t)P.tasks.size();
+        for (int64_t g = 0; g < b->n_regions; g++) {
+            const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
+            if (b->region_hap_start[g + 1] == b->region_hap_start[g]) continue;
+            int lane = 0;
+            WarpTask t{ (int32_t)P.groups.size(), 0 };
+            for (int64_t r = r0; r < r1; r++) {
+                if (read_k[(size_t)r] != K) continue;
+                const int R = (int)(b->read_off[r + 1] - b->read_off[r]);
+                const int G = (R + K - 1) / K;
+                if (lane + G > 32) {
+                    P.tasks.push_back(t);
+                    t = WarpTask{ (int32_t)P.groups.size(), 0 };
+                    lane = 0;
+                }
+                P.groups.push_back(TaskGroup{ (int32_t)r, (int16_t)lane, (int16_t)G });
+                t.n_groups++;
+                lane += G;
+            }
+            if (t.n_groups > 0) P.tasks.push_back(t);
+        }
+        L.n_tasks = (int32_t)P.tasks.size() - L.first_task;
+        if (L.n_tasks > 0) P.launches.push_back(L);
+    }
+}
+
+
+}  // namespace lk

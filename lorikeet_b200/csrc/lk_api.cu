@@ -1,0 +1,405 @@
+// lk_api.cu — the C ABI declared in include/lorikeet_b200.h: context, staging, task building,
+// launches.  All compute is on the GPU; this file only moves bytes and builds work lists.
+//
+// Reference call sites this layer replaces:
+//   PairHMM::compute_likelihoods            src/pair_hmm/pair_hmm.rs:345-375  (gkl forward per pair)
+//   PairHMM::compute_log10_likelihoods      src/pair_hmm/pair_hmm.rs:217-341  (result layout r*A + h)
+//   SmithWatermanAligner::align             src/smith_waterman/smith_waterman_aligner.rs:47-113
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lorikeet_b200.h"
+#include "host_model.h"
+#include "host_prep.h"
+#include "lk_api_internal.h"
+#include "lk_internal.h"
+#include "pairhmm_core.cuh"
+
+using namespace lk;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+lk_status lk_fail(lk_ctx *ctx, lk_status st, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return st;
+}
+
+lk_status lk_cuda_fail(lk_ctx *ctx, cudaError_t e, const char *what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return lk_fail(ctx, e == cudaErrorMemoryAllocation ? LK_ERR_NOMEM : LK_ERR_CUDA, buf);
+}
+
+cudaError_t DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+}
+
+template <class T>
+static cudaError_t upload(DevBuf &b, const T *src, size_t n, cudaStream_t st) {
+    cudaError_t e = b.reserve(std::max<size_t>(n * sizeof(T), 16));
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *lk_version(void) { return "lorikeet_b200 0.1.0 (sm_100a)"; }
+
+extern "C" lk_status lk_create(int device, lk_ctx **out_ctx) {
+    if (!out_ctx) return LK_ERR_INVALID;
+    *out_ctx = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        (void)cudaGetLastError();
+        return LK_ERR_CUDA;  // no CPU fallback by design
+    }
+    if (device < 0) {
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return LK_ERR_CUDA;
+    }
+    if (device >= n_dev) return LK_ERR_INVALID;
+    lk_ctx *ctx = new (std::nothrow) lk_ctx();
+    if (!ctx) return LK_ERR_NOMEM;
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return LK_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return LK_ERR_CUDA; }
+    ctx->n_sm = prop.multiProcessorCount;
+    for (int i = 0; i < 3; i++)
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return LK_ERR_CUDA; }
+    ModelTables t;
+    build_model_tables(t);
+    cudaStream_t st = ctx->stream[0];
+    if ((e = upload(ctx->d_qerr_f, t.qerr_f.data(), t.qerr_f.size(), st)) != cudaSuccess ||
+        (e = upload(ctx->d_qerr_d, t.qerr_d.data(), t.qerr_d.size(), st)) != cudaSuccess ||
+        (e = upload(ctx->d_m2m, t.m2m.data(), t.m2m.size(), st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess) {
+        lk_destroy(ctx);
+        return LK_ERR_CUDA;
+    }
+    const char *fk = getenv("LK_FORCE_K");
+    ctx->force_k = fk ? atoi(fk) : 0;
+    *out_ctx = ctx;
+    return LK_OK;
+}
+
+extern "C" void lk_destroy(lk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < 3; i++)
+        if (ctx->stream[i]) { cudaStreamSynchronize(ctx->stream[i]); cudaStreamDestroy(ctx->stream[i]); }
+    ctx->d_qerr_f.release(); ctx->d_qerr_d.release(); ctx->d_m2m.release();
+    delete ctx;
+}
+
+extern "C" const char *lk_last_error(const lk_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" lk_status lk_set_tristate_correction(lk_ctx *ctx, int use_tristate) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->tristate = use_tristate != 0;
+    return LK_OK;
+}
+
+extern "C" lk_status lk_set_force_f64(lk_ctx *ctx, int force_f64) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->force_f64 = force_f64 != 0;
+    return LK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PairHMM: batch validation, K choice, task building
+// ------------------------------------------------------------------------------------------------
+static lk_status validate_batch(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t *n_reads, int64_t *n_haps) {
+    if (!b) return lk_fail(ctx, LK_ERR_INVALID, "null batch");
+    if (b->n_regions < 0) return lk_fail(ctx, LK_ERR_INVALID, "negative n_regions");
+    if (!b->region_read_start || !b->region_hap_start) return lk_fail(ctx, LK_ERR_INVALID, "null region offsets");
+    if (b->region_read_start[0] != 0 || b->region_hap_start[0] != 0)
+        return lk_fail(ctx, LK_ERR_INVALID, "region offsets must start at 0");
+    for (int64_t g = 0; g < b->n_regions; g++)
+        if (b->region_read_start[g + 1] < b->region_read_start[g] || b->region_hap_start[g + 1] < b->region_hap_start[g])
+            return lk_fail(ctx, LK_ERR_INVALID, "region offsets must be non-decreasing");
+    *n_reads = b->region_read_start[b->n_regions];
+    *n_haps = b->region_hap_start[b->n_regions];
+    if (*n_reads > 0x7fffffffLL || *n_haps > 0x7fffffffLL) return lk_fail(ctx, LK_ERR_INVALID, "batch too large (2^31 reads/haplotypes)");
+    if (*n_reads > 0) {
+        if (!b->read_off || !b->read_bases || !b->read_qual || !b->read_ins || !b->read_del)
+            return lk_fail(ctx, LK_ERR_INVALID, "null read arrays");
+        for (int64_t r = 0; r < *n_reads; r++)
+            if (b->read_off[r + 1] <= b->read_off[r])  // pair_hmm.rs:417-440 asserts equal, non-degenerate lengths
+                return lk_fail(ctx, LK_ERR_INVALID, "empty read or decreasing read_off");
+    }
+    if (*n_haps > 0) {
+        if (!b->hap_off || !b->hap_bases) return lk_fail(ctx, LK_ERR_INVALID, "null haplotype arrays");
+        for (int64_t h = 0; h < *n_haps; h++)
+            if (b->hap_off[h + 1] <= b->hap_off[h]) return lk_fail(ctx, LK_ERR_INVALID, "empty haplotype or decreasing hap_off");
+    }
+    return LK_OK;
+}
+
+extern "C" lk_status lk_pairhmm_batch_dims(const lk_pairhmm_batch *b, int64_t *n_pairs, int64_t *n_cells) {
+    int64_t nr, nh;
+    lk_status st = validate_batch(nullptr, b, &nr, &nh);
+    if (st != LK_OK) return st;
+    int64_t pairs = 0, cells = 0;
+    for (int64_t g = 0; g < b->n_regions; g++) {
+        const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
+        const int64_t h0 = b->region_hap_start[g], h1 = b->region_hap_start[g + 1];
+        pairs += (r1 - r0) * (h1 - h0);
+        if (r1 > r0 && h1 > h0) cells += (b->read_off[r1] - b->read_off[r0]) * (b->hap_off[h1] - b->hap_off[h0]);
+    }
+    if (n_pairs) *n_pairs = pairs;
+    if (n_cells) *n_cells = cells;
+    return LK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PairHMM: resident batches
+// ------------------------------------------------------------------------------------------------
+static bool gcp_is_uniform(const uint8_t *gcp, int64_t n, uint8_t *value) {
+    if (n == 0) { *value = 10; return true; }
+    const uint8_t v = gcp[0];
+    for (int64_t i = 1; i < n; i++)
+        if (gcp[i] != v) return false;
+    *value = v;
+    return true;
+}
+
+static lk_status upload_locked(lk_ctx *ctx, const lk_pairhmm_batch *b, lk_resident **out_res) {
+    int64_t n_reads = 0, n_haps = 0;
+    lk_status vs = validate_batch(ctx, b, &n_reads, &n_haps);
+    if (vs != LK_OK) return vs;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+
+    lk_resident *R = new (std::nothrow) lk_resident();
+    if (!R) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    R->kind = 0;
+    R->n_regions = b->n_regions; R->n_reads = n_reads; R->n_haps = n_haps;
+    const int64_t read_bytes = n_reads ? b->read_off[n_reads] : 0;
+    const int64_t hap_bytes = n_haps ? b->hap_off[n_haps] : 0;
+    R->gcp_constant = b->gcp_constant;
+    R->vargcp = false;
+    const uint8_t *gcp_arr = b->read_gcp;
+    if (gcp_arr) {
+        uint8_t v;
+        if (gcp_is_uniform(gcp_arr + (n_reads ? b->read_off[0] : 0), read_bytes - (n_reads ? b->read_off[0] : 0), &v)) {
+            R->gcp_constant = v; gcp_arr = nullptr;
+        } else R->vargcp = true;
+    }
+    HostPrep P;
+    build_prep(b, n_reads, n_haps, ctx->force_k, !ctx->force_f64, P);
+    R->n_pairs = P.n_pairs; R->n_cells = P.n_cells; R->h_max = P.h_max;
+    R->launches = P.launches;
+    R->n_direct = ctx->force_f64 ? (int32_t)0 : (int32_t)P.direct.size();
+    R->all_f64 = ctx->force_f64;
+    if (P.n_pairs > 0x7fffffffLL) { delete R; return lk_fail(ctx, LK_ERR_INVALID, "batch too large (2^31 pairs)"); }
+
+    cudaStream_t st = ctx->stream[0];
+#define UP(buf, ptr, n) if ((e = upload(R->buf, ptr, (size_t)(n), st)) != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "upload " #buf); }
+    UP(read_bases, b->read_bases, read_bytes);
+    UP(read_qual, b->read_qual, read_bytes);
+    UP(read_ins, b->read_ins, read_bytes);
+    UP(read_del, b->read_del, read_bytes);
+    if (R->vargcp) { UP(read_gcp, gcp_arr, read_bytes); }
+    UP(read_off, b->read_off, n_reads + 1);
+    UP(read_region, P.read_region.data(), n_reads);
+    UP(read_out_base, P.read_out_base.data(), n_reads);
+    UP(region_hap_start, b->region_hap_start, b->n_regions + 1);
+    UP(hap_off, b->hap_off, n_haps + 1);
+    UP(hap_bases, b->hap_bases, hap_bytes);
+    UP(henc_off, P.henc_off.data(), n_haps);
+    UP(tasks, P.tasks.data(), P.tasks.size());
+    UP(groups, P.groups.data(), P.groups.size());
+#undef UP
+#define RS(buf, bytes) if ((e = R->buf.reserve((size_t)std::max<int64_t>((bytes), 16))) != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "alloc " #buf); }
+    RS(read_flags, n_reads);
+    RS(hap_flags, n_haps);
+    RS(henc, P.henc_words * 4);
+    RS(out, P.n_pairs * 8);
+    RS(flags, P.n_pairs);
+    RS(counters, 64);
+    RS(rescue_pairs, P.n_pairs * (int64_t)sizeof(RescuePair));
+    R->plain_blocks = ctx->n_sm * 2;
+    R->scratch_stride = 6 * ((int64_t)P.h_max + 1);
+    RS(scratch, (int64_t)R->plain_blocks * (LK_PLAIN_THREADS / 32) * R->scratch_stride * 8);
+#undef RS
+    if (!P.direct.empty() && !ctx->force_f64) {
+        e = cudaMemcpyAsync(R->rescue_pairs.p, P.direct.data(), P.direct.size() * sizeof(RescuePair), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "upload direct pairs"); }
+    }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "upload sync"); }
+    *out_res = R;
+    return LK_OK;
+}
+
+static void fill_args(lk_ctx *ctx, lk_resident *R, PairHmmArgs &A) {
+    memset(&A, 0, sizeof A);
+    A.read_bases = (const uint8_t *)R->read_bases.p; A.read_qual = (const uint8_t *)R->read_qual.p;
+    A.read_ins = (const uint8_t *)R->read_ins.p; A.read_del = (const uint8_t *)R->read_del.p;
+    A.read_gcp = R->vargcp ? (const uint8_t *)R->read_gcp.p : nullptr;
+    A.read_off = (const int64_t *)R->read_off.p; A.read_region = (const int32_t *)R->read_region.p;
+    A.read_out_base = (const int64_t *)R->read_out_base.p; A.read_flags = (const uint8_t *)R->read_flags.p;
+    A.region_hap_start = (const int64_t *)R->region_hap_start.p; A.hap_off = (const int64_t *)R->hap_off.p;
+    A.hap_bases = (const uint8_t *)R->hap_bases.p; A.henc = (const uint32_t *)R->henc.p;
+    A.henc_off = (const int64_t *)R->henc_off.p; A.hap_flags = (const uint8_t *)R->hap_flags.p;
+    A.qerr_f = (const float *)ctx->d_qerr_f.p; A.qerr_d = (const double *)ctx->d_qerr_d.p; A.m2m = (const double *)ctx->d_m2m.p;
+    A.groups = (const TaskGroup *)R->groups.p;
+    A.out = (double *)R->out.p; A.flags = (uint8_t *)R->flags.p;
+    A.rescue_count = (int32_t *)R->counters.p; A.rescue_cursor = (int32_t *)R->counters.p + 1;
+    A.rescue_pairs = (RescuePair *)R->rescue_pairs.p; A.rescue_capacity = (int32_t)R->n_pairs;
+    A.scratch = (double *)R->scratch.p; A.scratch_stride = R->scratch_stride;
+    A.gcp_constant = R->gcp_constant;
+    A.mismatch_div = ctx->tristate ? 3.0f : 1.0f;
+}
+
+static lk_status run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
+    if (!R || R->kind != 0) return lk_fail(ctx, LK_ERR_INVALID, "not a PairHMM resident batch");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    cudaStream_t st = ctx->stream[0];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (kernel_ms) {
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, st);
+    }
+    PairHmmArgs A;
+    fill_args(ctx, R, A);
+    R->counter_init[0] = R->all_f64 ? (int32_t)R->n_pairs : R->n_direct;
+    R->counter_init[1] = 0;
+    e = cudaMemcpyAsync(R->counters.p, R->counter_init, 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "reset counters");
+    R->launch_count = 0;
+    if (R->n_pairs > 0) {
+        if (R->all_f64) {
+            if ((e = launch_list_all_pairs(A, R->n_reads, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "list_all_pairs");
+            R->launch_count++;
+        } else {
+            if ((e = launch_encode_haps(A.hap_bases, A.hap_off, A.henc_off, R->n_haps, (uint32_t *)R->henc.p, (uint8_t *)R->hap_flags.p, st)) != cudaSuccess)
+                return lk_cuda_fail(ctx, e, "encode_haps");
+            if ((e = launch_scan_reads(A.read_bases, A.read_qual, A.read_ins, A.read_off, R->n_reads, (uint8_t *)R->read_flags.p, st)) != cudaSuccess)
+                return lk_cuda_fail(ctx, e, "scan_reads");
+            R->launch_count += 2;
+            for (const auto &L : R->launches) {
+                PairHmmArgs AL = A;
+                AL.tasks = (const WarpTask *)R->tasks.p + L.first_task;
+                AL.n_tasks = L.n_tasks;
+                if ((e = launch_fast(L.K, AL, R->vargcp, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_fast");
+                R->launch_count++;
+            }
+        }
+        if ((e = launch_plain(A, R->plain_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_plain");
+        R->launch_count++;
+    }
+    if (kernel_ms) cudaEventRecord(ev1, st);
+    e = cudaStreamSynchronize(st);
+    if (kernel_ms) {
+        if (e == cudaSuccess) cudaEventElapsedTime(kernel_ms, ev0, ev1);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    }
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm kernels");
+    return LK_OK;
+}
+
+static lk_status download_locked(lk_ctx *ctx, lk_resident *R, double *out, uint8_t *flags) {
+    if (!R || R->kind != 0) return lk_fail(ctx, LK_ERR_INVALID, "not a PairHMM resident batch");
+    if (R->n_pairs == 0) return LK_OK;
+    if (!out) return lk_fail(ctx, LK_ERR_INVALID, "null out");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    cudaStream_t st = ctx->stream[0];
+    e = cudaMemcpyAsync(out, R->out.p, (size_t)R->n_pairs * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && flags) e = cudaMemcpyAsync(flags, R->flags.p, (size_t)R->n_pairs, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "download");
+    return LK_OK;
+}
+
+extern "C" lk_status lk_pairhmm_upload(lk_ctx *ctx, const lk_pairhmm_batch *batch, lk_resident **out_res) {
+    if (!ctx || !out_res) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    *out_res = nullptr;
+    return upload_locked(ctx, batch, out_res);
+}
+
+extern "C" lk_status lk_pairhmm_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return run_locked(ctx, res, kernel_ms);
+}
+
+extern "C" lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *out, uint8_t *flags) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return download_locked(ctx, res, out, flags);
+}
+
+extern "C" void lk_resident_free(lk_ctx *ctx, lk_resident *R) {
+    if (!R) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
+                       &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
+                       &R->hap_bases, &R->henc, &R->henc_off, &R->hap_flags, &R->tasks, &R->groups, &R->out,
+                       &R->flags, &R->counters, &R->rescue_pairs, &R->scratch,
+                       &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,
+                       &R->sw_ops, &R->sw_nops, &R->sw_offsets, &R->sw_order };
+    for (DevBuf *b : bufs) b->release();
+    delete R;
+}
+
+extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    lk_resident *R = nullptr;
+    lk_status st = upload_locked(ctx, batch, &R);
+    if (st != LK_OK) return st;
+    st = run_locked(ctx, R, nullptr);
+    if (st == LK_OK) st = download_locked(ctx, R, out, flags);
+    ctx->last_launch_count = R->launch_count;
+    lk_resident_free(ctx, R);
+    return st;
+}
+
+extern "C" lk_status lk_pairhmm_forward(lk_ctx *ctx, const uint8_t *hap, int64_t hap_len, const uint8_t *read,
+                                        const uint8_t *qual, const uint8_t *ins, const uint8_t *del, const uint8_t *gcp,
+                                        int64_t read_len, double *out_log10) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (!hap || !read || !qual || !ins || !del || !gcp || !out_log10) return lk_fail(ctx, LK_ERR_INVALID, "null argument");
+    if (hap_len <= 0 || read_len <= 0) return lk_fail(ctx, LK_ERR_INVALID, "empty read or haplotype");
+    const int64_t rs[2] = { 0, 1 }, ro[2] = { 0, read_len }, ho[2] = { 0, hap_len };
+    lk_pairhmm_batch b;
+    memset(&b, 0, sizeof b);
+    b.n_regions = 1; b.region_read_start = rs; b.region_hap_start = rs; b.read_off = ro;
+    b.read_bases = read; b.read_qual = qual; b.read_ins = ins; b.read_del = del; b.read_gcp = gcp;
+    b.gcp_constant = gcp[0]; b.hap_off = ho; b.hap_bases = hap;
+    return lk_pairhmm_batch_host(ctx, &b, out_log10, nullptr);
+}
+
+extern "C" int32_t lk_debug_last_launch_count(const lk_ctx *ctx) { return ctx ? ctx->last_launch_count : -1; }
+extern "C" int32_t lk_resident_launch_count(const lk_resident *r) { return r ? r->launch_count : -1; }
+extern "C" int64_t lk_resident_cells(const lk_resident *r) { return r ? r->n_cells : -1; }
+extern "C" int64_t lk_resident_pairs(const lk_resident *r) { return r ? r->n_pairs : -1; }

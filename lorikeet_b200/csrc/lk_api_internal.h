@@ -1,0 +1,57 @@
+// lk_api_internal.h — host-side structures behind the opaque handles of include/lorikeet_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lorikeet_b200.h"
+#include "host_prep.h"
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes);
+    void release();
+};
+
+struct lk_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream[3] = { nullptr, nullptr, nullptr };
+    std::mutex mu;
+    std::string err;
+    bool tristate = true;
+    bool force_f64 = false;
+    int force_k = 0;
+    int32_t last_launch_count = 0;
+    DevBuf d_qerr_f, d_qerr_d, d_m2m;
+};
+
+struct lk_resident {
+    int kind = 0;  // 0 PairHMM, 1 Smith-Waterman
+    // ---- PairHMM ----
+    int64_t n_regions = 0, n_reads = 0, n_haps = 0, n_pairs = 0, n_cells = 0;
+    int h_max = 0;
+    bool vargcp = false, all_f64 = false;
+    uint8_t gcp_constant = 10;
+    int32_t n_direct = 0;
+    int32_t counter_init[2] = { 0, 0 };
+    int plain_blocks = 0;
+    int64_t scratch_stride = 0;
+    int32_t launch_count = 0;
+    std::vector<lk::FastLaunch> launches;
+    DevBuf read_bases, read_qual, read_ins, read_del, read_gcp, read_off, read_region, read_out_base, read_flags;
+    DevBuf region_hap_start, hap_off, hap_bases, henc, henc_off, hap_flags;
+    DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch;
+    // ---- Smith-Waterman ----
+    int64_t sw_n_pairs = 0, sw_cells = 0;
+    int32_t sw_max_ops = 0, sw_strategy = 0;
+    lk_sw_params sw_params = { 0, 0, 0, 0 };
+    DevBuf sw_refs, sw_alts, sw_ref_off, sw_alt_off, sw_bt, sw_bt_off, sw_ops, sw_nops, sw_offsets, sw_order;
+};
+
+lk_status lk_fail(lk_ctx *ctx, lk_status st, const std::string &msg);
+lk_status lk_cuda_fail(lk_ctx *ctx, cudaError_t e, const char *what);

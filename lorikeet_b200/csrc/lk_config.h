@@ -1,0 +1,12 @@
+// lk_config.h — compile-time configuration shared by host and device code.
+#pragma once
+
+#define LK_FAST_THREADS 128
+#define LK_PLAIN_THREADS 128
+#define LK_PLAIN_K 4
+
+// Rows per lane (K) the fp32 fast kernel is instantiated for, with the launch-bounds
+// "min blocks per SM" that sets its register budget (128 threads/block: 4 -> 128 regs, 3 -> 168,
+// 2 -> 255).  The host picks K per read from this list (host_prep.cpp: choose_k).
+#define LK_FAST_K_TABLE(X) X(4, 4) X(6, 4) X(8, 4) X(10, 4) X(12, 3) X(14, 2) X(16, 2) X(19, 2) X(20, 2)
+#define LK_FAST_KS 4, 6, 8, 10, 12, 14, 16, 19, 20

@@ -1,0 +1,430 @@
+// pairhmm_core.cuh — PairHMM forward wavefront, warp-level routines.
+//
+// Computes what the reference's forward recurrence computes
+// (src/pair_hmm/pair_hmm.rs:503-615 `sub_compute_read_likelihood_given_haplotype_log10`,
+//  priors :626-654, transitions src/pair_hmm/pair_hmm_model.rs:142-156), re-designed for a
+// 32-lane warp:
+//
+//   * each lane owns a strip of K consecutive READ rows in registers; the warp sweeps the
+//     haplotype columns as a skewed wavefront (lane l works on column s-l at step s), handing the
+//     strip's last row (M, I, D) to the next lane with one __shfl_up_sync per value;
+//   * per-row constants (transition x prior products) are built once per read and reused for every
+//     haplotype of the region;
+//   * "hat form" (fp32 fast path): I^ = I / tMI[i], D^ = D / tMD[i] turn the I and D updates into one
+//     FMA each and the match prior is folded into the row constants, so a cell costs 8 issue slots
+//     (3 for the M sum, compare, select, scale, I^, D^) for the 12 flops the reference spends
+//     (pair_hmm.rs:575-591);
+//   * "plain form" (f64 pass): the reference's own operation order, initial condition 2^1020,
+//     un-fused multiplies/adds, any read / haplotype length (row bands with power-of-two
+//     renormalisation between bands).
+//
+// The routines are templated on a Warp policy so that the identical code runs (a) on the GPU
+// (DevWarp: shuffles) and (b) in tests/emul, a 32-thread lock-step host emulator used to debug
+// index logic where no GPU is present.  (b) is test tooling only and is never linked into the product.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LK_DEV __device__ __forceinline__
+#else
+#define LK_DEV inline
+#endif
+
+namespace lk {
+
+// ---- encoded haplotypes ---------------------------------------------------------------------
+// One u32 per haplotype base: the base's one-hot byte replicated into all 4 bytes
+// (A=01 C=02 G=04 T=08, N=FF so that it matches anything; anything else = 0 and the sequence is
+// flagged SEQ_EXOTIC, which routes its pairs to the byte-exact f64 pass).
+// Each encoded haplotype is surrounded by zero words so lanes can read columns <1 and >H.
+constexpr int HENC_PADL = 36;
+constexpr int HENC_PADR = 44;
+
+LK_DEV uint32_t encode_base(uint8_t b, bool &exotic) {
+    uint32_t m;
+    switch (b) {
+        case 'A': m = 0x01u; break;
+        case 'C': m = 0x02u; break;
+        case 'G': m = 0x04u; break;
+        case 'T': m = 0x08u; break;
+        case 'N': m = 0xFFu; break;
+        default: m = 0u; exotic = true; break;
+    }
+    return m * 0x01010101u;
+}
+
+// fp32 fast path: linear space pre-scaled by 2^100 (the reference uses 2^1020 in f64, pair_hmm.rs:16);
+// 2^28 of headroom is left for the hat variables (bounded by the spread of insertion qualities).
+constexpr float FAST_INIT = 1.2676506002282294e30f;          // 2^100
+constexpr double FAST_INIT_LOG10 = 30.102999566398120;        // 100*log10(2)
+constexpr float FAST_MIN_ACCEPTED = 7.7037197775489434e-34f;  // 2^-110; smaller sums are redone in f64
+constexpr int FAST_MAX_INS_RANGE = 60;                        // phred spread of ins quals the hat form tolerates
+
+enum : uint8_t { SEQ_EXOTIC = 1, SEQ_QUAL_DOMAIN = 2 };
+// per-pair result flags (same values as LK_FLAG_* in include/lorikeet_b200.h)
+enum : uint8_t { PAIR_RESCUED = 1, PAIR_NEG_INF = 2 };
+
+struct TaskGroup {       // one read inside a warp task
+    int32_t read;        // batch-global read index
+    int16_t lane_start;  // first lane of the group
+    int16_t lanes;       // ceil(R / K)
+};
+struct WarpTask {        // all groups of a task belong to one region
+    int32_t first_group;
+    int32_t n_groups;
+};
+struct RescuePair {
+    int32_t read;
+    int32_t hap;         // batch-global haplotype index
+};
+
+struct PairHmmArgs {
+    // reads (arenas as given by the caller)
+    const uint8_t *read_bases, *read_qual, *read_ins, *read_del, *read_gcp;  // read_gcp may be null
+    const int64_t *read_off;
+    const int32_t *read_region;
+    const int64_t *read_out_base;  // index in out[] of (read, first haplotype of its region)
+    const uint8_t *read_flags;
+    // haplotypes
+    const int64_t *region_hap_start;
+    const int64_t *hap_off;
+    const uint8_t *hap_bases;
+    const uint32_t *henc;
+    const int64_t *henc_off;       // index of column 1 of haplotype h inside henc
+    const uint8_t *hap_flags;
+    // tables
+    const float *qerr_f;           // 10^(-q/10), q = 0..255
+    const double *qerr_d;
+    const double *m2m;             // triangular match->match table, (max*(max+1)/2 + min)
+    // fast-path tasks
+    const WarpTask *tasks;
+    const TaskGroup *groups;
+    int32_t n_tasks;
+    // results
+    double *out;
+    uint8_t *flags;
+    int32_t *rescue_count;
+    RescuePair *rescue_pairs;
+    int32_t rescue_capacity;
+    // f64 pass
+    double *scratch;               // per-warp band boundaries
+    int64_t scratch_stride;        // doubles per warp
+    int32_t *rescue_cursor;
+    uint8_t gcp_constant;
+    float mismatch_div;            // 3 (tristate, pair_hmm.rs:53) or 1
+};
+
+LK_DEV int lk_popc(unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+// match->match, pair_hmm_model.rs:442-461 (table) — quals are bytes so max <= 255; 255 > MAX_QUAL uses
+// the closed form of :453-458 which the host folded into row 255 of the table.
+LK_DEV double m2m_lookup(const double *m2m, int ins, int del) {
+    int mn = ins < del ? ins : del, mx = ins < del ? del : ins;
+    return m2m[((mx * (mx + 1)) >> 1) + mn];
+}
+
+// =============================================================================================
+// Fast path: fp32 hat form, one warp task = up to 32 lanes of read groups, every haplotype of the
+// region in turn.  Requires R <= 32*K for every read of the task.
+// =============================================================================================
+template <class W, int K, bool VARGCP>
+LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
+    const int lane = w.lane();
+    const WarpTask t = A.tasks[task_id];
+    TaskGroup g;
+    g.read = -1; g.lane_start = 0; g.lanes = 0;
+    if (lane < t.n_groups) g = A.groups[t.first_group + lane];
+    const unsigned start_mask = w.reduce_or(lane < t.n_groups ? (1u << g.lane_start) : 0u);
+    const int maxlanes = (int)w.reduce_max((unsigned)g.lanes);
+    const int my_g = lk_popc(start_mask & (0xFFFFFFFFu >> (31 - lane))) - 1;
+    const int read = w.shfl(g.read, my_g);
+    const int lstart = w.shfl((int)g.lane_start, my_g);
+    const int glanes = w.shfl((int)g.lanes, my_g);
+    const int lig = lane - lstart;            // lane in group; lanes >= glanes are idle padding
+    const bool is_start = (lig == 0);
+
+    const int64_t ro = A.read_off[read];
+    const int R = (int)(A.read_off[read + 1] - ro);
+    const uint8_t rflag = A.read_flags[read];
+
+    // ---- per-row constants (hat form), built in f64 and rounded once -------------------------
+    float ca[K], cb[K], cc[K], ce[K], cr[K];
+    float cf[VARGCP ? K : 1];
+    uint32_t rm[(K + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (K + 3) / 4; i++) rm[i] = 0u;
+    float kcoef = 0.f, wM = 0.f, wI = 0.f;
+    if (!VARGCP) cf[0] = A.qerr_f[A.gcp_constant];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int i = lig * K + k;  // 0-based read position of this row
+        float a = 0.f, b = 0.f, c = 0.f, e = (i > R) ? 1.f : 0.f, r = 1.f, f = 1.f;
+        uint32_t mask = 0u;
+        if (i < R) {
+            const int q = A.read_qual[ro + i], qi = A.read_ins[ro + i], qd = A.read_del[ro + i];
+            const int qg = A.read_gcp ? A.read_gcp[ro + i] : A.gcp_constant;
+            const double err = A.qerr_d[q];
+            const double pm = 1.0 - err;                         // pair_hmm.rs:644
+            const double px = err / (double)A.mismatch_div;       // :646-651
+            const double tMM = m2m_lookup(A.m2m, qi, qd);         // pair_hmm_model.rs:149
+            const double tGM = 1.0 - A.qerr_d[qg];                // :152
+            const double tII = A.qerr_d[qg];                      // :153-155
+            bool ex = false;
+            mask = encode_base(A.read_bases[ro + i], ex) & 0xFFu;
+            if (i == 0) {
+                kcoef = (float)(pm * tGM);  // row 1 sees only D[0][j-1] = init/H (pair_hmm.rs:515-529)
+            } else {
+                const double tMIp = A.qerr_d[A.read_ins[ro + i - 1]];
+                const double tMDp = A.qerr_d[A.read_del[ro + i - 1]];
+                a = (float)(pm * tMM);
+                b = (float)(pm * tGM * tMIp);
+                c = (float)(pm * tGM * tMDp);
+                e = (float)(tII * tMIp / A.qerr_d[qi]);
+            }
+            r = (pm > 0.0) ? (float)(px / pm) : 0.f;
+            f = (float)tII;  // tDD == tII
+        } else if (i == R) {
+            // first padding row under the read: I^ becomes the column's summand M[R][j] + I[R][j]
+            e = (R > 0) ? A.qerr_f[A.read_ins[ro + R - 1]] : 0.f;
+        }
+        ca[k] = a; cb[k] = b; cc[k] = c; ce[k] = e; cr[k] = r;
+        if (VARGCP) cf[k] = f;
+        rm[k >> 2] |= mask << (8 * (k & 3));
+    }
+    if (lig == glanes - 1) {
+        const int kstar = (R - 1) - lig * K;
+        if (kstar == K - 1) { wM = 1.f; wI = A.qerr_f[A.read_ins[ro + R - 1]]; }
+        else { wM = 0.f; wI = 1.f; }
+    }
+
+    const int32_t region = A.read_region[read];
+    const int64_t h0 = A.region_hap_start[region], h1 = A.region_hap_start[region + 1];
+    const int64_t out_base = A.read_out_base[read];
+
+    for (int64_t h = h0; h < h1; ++h) {
+        const int H = (int)(A.hap_off[h + 1] - A.hap_off[h]);
+        const uint32_t *hp = A.henc + A.henc_off[h] - 1 - lig;  // hp[s] = encoded column (s - lig)
+        const float kinit = kcoef * (FAST_INIT / (float)H);
+        float M[K], I[K], D[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) { M[k] = 0.f; I[k] = 0.f; D[k] = 0.f; }
+        float Mu = 0.f, Iu = 0.f, Du = 0.f, Md = 0.f, Id = 0.f, Dd = 0.f, acc = 0.f;
+        const int n_steps = H + maxlanes - 1;
+        const int s_last = H + lig;  // last step at which this lane's column is still <= H
+
+#pragma unroll 4
+        for (int s = 1; s <= n_steps; ++s) {
+            const uint32_t hrep = w.ldg(hp + s);
+            // ---- M and D^ (descending so that row k-1 still holds column c-1) ----
+#pragma unroll
+            for (int k = K - 1; k >= 0; k--) {
+                float mm;
+                if (k == 0) {
+                    mm = fmaf(Md, ca[0], kinit);
+                    mm = fmaf(Id, cb[0], mm);
+                    mm = fmaf(Dd, cc[0], mm);
+                } else {
+                    mm = M[k - 1] * ca[k];
+                    mm = fmaf(I[k - 1], cb[k], mm);
+                    mm = fmaf(D[k - 1], cc[k], mm);
+                }
+                D[k] = fmaf(D[k], VARGCP ? cf[k] : cf[0], M[k]);
+                const bool match = (rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3)))) != 0u;
+                M[k] = mm * (match ? 1.0f : cr[k]);
+            }
+            // ---- I^ (ascending: same column, row above) ----
+            I[0] = fmaf(Iu, ce[0], Mu);
+#pragma unroll
+            for (int k = 1; k < K; k++) I[k] = fmaf(I[k - 1], ce[k], M[k - 1]);
+            if (s <= s_last) {
+                acc = fmaf(M[K - 1], wM, acc);
+                acc = fmaf(I[K - 1], wI, acc);
+            }
+            Md = Mu; Id = Iu; Dd = Du;
+            Mu = w.shfl_up1(M[K - 1]);
+            Iu = w.shfl_up1(I[K - 1]);
+            Du = w.shfl_up1(D[K - 1]);
+            if (is_start) Mu = 0.f;  // a0 = b0 = c0 = e0 = 0 already mute the other inputs
+        }
+
+        if (lig == glanes - 1) {
+            const int64_t oi = out_base + (h - h0);
+            const bool redo = !(acc >= FAST_MIN_ACCEPTED) || rflag != 0 || A.hap_flags[h] != 0;
+            if (redo) {
+                const int slot = w.atomic_add(A.rescue_count, 1);
+                if (slot < A.rescue_capacity) { A.rescue_pairs[slot].read = read; A.rescue_pairs[slot].hap = (int32_t)h; }
+            } else {
+                A.out[oi] = log10((double)acc) - FAST_INIT_LOG10;
+                if (A.flags) A.flags[oi] = 0;
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// f64 pass ("plain form"): one warp per (read, haplotype) pair, any lengths.  Rows are processed
+// in bands of 32*K; the band's last row travels through per-warp scratch; between bands the row is
+// renormalised by a power of two (exponent carried in an int) so long reads cannot underflow.
+// The arithmetic order is the reference's (pair_hmm.rs:575-591) with explicit un-fused mul/add.
+// =============================================================================================
+LK_DEV double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+LK_DEV double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+constexpr double PLAIN_INIT_EXP = 1020.0;  // INITIAL_CONDITION = 2^1020, pair_hmm.rs:16
+
+template <class W, int K>
+LK_DEV void pairhmm_plain_pair(W &w, const PairHmmArgs &A, int read, int64_t h, double *scratch) {
+    const int lane = w.lane();
+    const int64_t ro = A.read_off[read];
+    const int R = (int)(A.read_off[read + 1] - ro);
+    const int64_t ho = A.hap_off[h];
+    const int H = (int)(A.hap_off[h + 1] - ho);
+    const int32_t region = A.read_region[read];
+    const int64_t oi = A.read_out_base[read] + (h - A.region_hap_start[region]);
+
+    const int BAND = 32 * K;
+    const int n_bands = (R + BAND - 1) / BAND;
+    const double initH = ldexp(1.0, (int)PLAIN_INIT_EXP) / (double)H;  // pair_hmm.rs:517
+
+    // scratch: two boundary rows, each 3 arrays of (H+1)
+    const int64_t W1 = (int64_t)H + 1;
+    double *bnd[2] = { scratch, scratch + 3 * W1 };
+
+    long shift_total = 0;     // power of two removed so far
+    double in_scale = 1.0;    // 2^shift applied to the incoming boundary row of this band
+    double result_sum = 0.0;
+    bool underflow = false;
+
+    for (int band = 0; band < n_bands; band++) {
+        const int row0 = band * BAND;                        // first 0-based read position of the band
+        const int rows = (R - row0 < BAND) ? (R - row0) : BAND;
+        const int lanes = (rows + K - 1) / K;                // lanes holding real rows
+        const bool last_band = (band == n_bands - 1);
+        const double *bin = bnd[band & 1];
+        double *bout = bnd[(band + 1) & 1];
+
+        // ---- row constants ----
+        double tMM[K], tGM[K], tMI[K], tII[K], tMD[K], tDD[K], pm[K], px[K];
+        uint32_t rb[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int i = row0 + lane * K + k;
+            tMM[k] = tGM[k] = tMD[k] = tDD[k] = pm[k] = px[k] = 0.0;
+            tMI[k] = tII[k] = 1.0;  // padding rows: I copies M+I of the row above (column summand)
+            rb[k] = 0x100u;         // never equals a byte
+            if (i < R) {
+                const int q = A.read_qual[ro + i], qi = A.read_ins[ro + i], qd = A.read_del[ro + i];
+                const int qg = A.read_gcp ? A.read_gcp[ro + i] : A.gcp_constant;
+                tMM[k] = m2m_lookup(A.m2m, qi, qd);
+                tGM[k] = 1.0 - A.qerr_d[qg];
+                tMI[k] = A.qerr_d[qi];
+                tII[k] = A.qerr_d[qg];
+                tMD[k] = A.qerr_d[qd];
+                tDD[k] = A.qerr_d[qg];
+                pm[k] = 1.0 - A.qerr_d[q];
+                px[k] = A.qerr_d[q] / (double)A.mismatch_div;
+                rb[k] = A.read_bases[ro + i];
+            }
+        }
+        // which lane/row carries the band's last real row
+        const int last_lane = lanes - 1;
+        const int kstar = (rows - 1) - last_lane * K;
+        const double wM = (lane == last_lane && kstar == K - 1) ? 1.0 : 0.0;
+        const bool is_out_lane = (lane == last_lane);
+
+        double M[K], I[K], D[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) { M[k] = 0.0; I[k] = 0.0; D[k] = 0.0; }
+        // column 0: row 0 has D = init (pair_hmm.rs:520), rows >= 1 are zero
+        double Mu = 0.0, Iu = 0.0, Du = 0.0, Md = 0.0, Id = 0.0, Dd = 0.0;
+        if (lane == 0 && band == 0) Dd = initH;
+        double band_max = 0.0;
+        const int n_steps = H + lanes - 1;
+        if (lane == 0) { bout[0] = 0.0; bout[W1] = 0.0; bout[2 * W1] = 0.0; }
+
+        for (int s = 1; s <= n_steps; s++) {
+            const int c = s - lane;  // this lane's column
+            if (lane == 0) {
+                if (band == 0) { Mu = 0.0; Iu = 0.0; Du = initH; }
+                else if (c <= H) { Mu = bin[c] * in_scale; Iu = bin[W1 + c] * in_scale; Du = bin[2 * W1 + c] * in_scale; }
+                else { Mu = 0.0; Iu = 0.0; Du = 0.0; }
+            }
+            const uint32_t hb = (c >= 1 && c <= H) ? (uint32_t)A.hap_bases[ho + c - 1] : 0x200u;
+            const bool hN = (hb == 'N');
+#pragma unroll
+            for (int k = K - 1; k >= 0; k--) {
+                const double md = (k == 0) ? Md : M[k - 1];
+                const double id = (k == 0) ? Id : I[k - 1];
+                const double dd = (k == 0) ? Dd : D[k - 1];
+                const bool match = (rb[k] == hb) || (rb[k] == 'N') || hN;  // pair_hmm.rs:643
+                const double prior = match ? pm[k] : px[k];
+                const double sum = dadd(dadd(dmul(md, tMM[k]), dmul(id, tGM[k])), dmul(dd, tGM[k]));
+                const double dn = dadd(dmul(M[k], tMD[k]), dmul(D[k], tDD[k]));
+                M[k] = dmul(prior, sum);
+                D[k] = dn;
+            }
+            {
+                double mu = Mu, iu = Iu;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const double in = dadd(dmul(mu, tMI[k]), dmul(iu, tII[k]));
+                    mu = M[k];
+                    I[k] = in;
+                    iu = I[k];
+                }
+            }
+            if (is_out_lane && c >= 1 && c <= H) {
+                if (last_band) {
+                    result_sum = dadd(result_sum, dadd(dmul(M[K - 1], wM), I[K - 1]));  // pair_hmm.rs:600-603
+                } else {
+                    bout[c] = M[K - 1]; bout[W1 + c] = I[K - 1]; bout[2 * W1 + c] = D[K - 1];
+                    band_max = fmax(band_max, fmax(M[K - 1], fmax(I[K - 1], D[K - 1])));
+                }
+            }
+            Md = Mu; Id = Iu; Dd = Du;
+            Mu = w.shfl_up1(M[K - 1]);
+            Iu = w.shfl_up1(I[K - 1]);
+            Du = w.shfl_up1(D[K - 1]);
+        }
+        if (!last_band) {
+            band_max = w.shfl(band_max, last_lane);
+            w.sync();  // boundary row visible to lane 0 of the next band
+            if (!(band_max > 0.0)) { underflow = true; break; }
+            int e2;
+            (void)frexp(band_max, &e2);
+            const int k2 = 1000 - e2;  // bring the row maximum back near 2^1000
+            in_scale = ldexp(1.0, k2);
+            shift_total += k2;
+        }
+    }
+
+    if (lane == ((R - (n_bands - 1) * BAND) + K - 1) / K - 1) {
+        double v;
+        uint8_t fl = PAIR_RESCUED;
+        if (underflow || !(result_sum > 0.0)) { v = -INFINITY; fl |= PAIR_NEG_INF; }
+        else v = log10(result_sum) - log10(ldexp(1.0, (int)PLAIN_INIT_EXP)) - (double)shift_total * log10(2.0);
+        A.out[oi] = v;
+        if (A.flags) A.flags[oi] = fl;
+    }
+}
+
+}  // namespace lk

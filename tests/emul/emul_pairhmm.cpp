@@ -1,0 +1,163 @@
+// emul_pairhmm.cpp — TEST TOOLING ONLY (never linked into the product library).
+//
+// A 32-thread lock-step emulator of one CUDA warp: it runs the *same* templated warp routines the
+// GPU kernels run (lorikeet_b200/csrc/pairhmm_core.cuh) with shuffles implemented through a shared
+// slot array and barriers.  It exists because the build container has no GPU: it lets the CPU test
+// suite exercise the lane/strip/skew index logic of the kernels before a gpurun call.
+#include <atomic>
+#include <barrier>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../lorikeet_b200/csrc/host_model.h"
+#include "../../lorikeet_b200/csrc/host_prep.h"
+#include "../../lorikeet_b200/csrc/pairhmm_core.cuh"
+
+using namespace lk;
+
+struct WarpShared {
+    std::barrier<> bar{32};
+    uint64_t slot[32];
+};
+
+struct EmulWarp {
+    int lane_;
+    WarpShared *sh;
+    int lane() const { return lane_; }
+    template <class T> T exchange(T v, int src) {
+        uint64_t bits = 0;
+        memcpy(&bits, &v, sizeof(T));
+        sh->slot[lane_] = bits;
+        sh->bar.arrive_and_wait();
+        T r = v;
+        if (src >= 0 && src < 32) memcpy(&r, &sh->slot[src], sizeof(T));
+        sh->bar.arrive_and_wait();
+        return r;
+    }
+    template <class T> T shfl_up1(T v) { return exchange(v, lane_ - 1); }
+    template <class T> T shfl(T v, int src) { return exchange(v, src & 31); }
+    unsigned reduce_or(unsigned v) {
+        sh->slot[lane_] = v;
+        sh->bar.arrive_and_wait();
+        unsigned r = 0;
+        for (int i = 0; i < 32; i++) r |= (unsigned)sh->slot[i];
+        sh->bar.arrive_and_wait();
+        return r;
+    }
+    unsigned reduce_max(unsigned v) {
+        sh->slot[lane_] = v;
+        sh->bar.arrive_and_wait();
+        unsigned r = 0;
+        for (int i = 0; i < 32; i++) r = std::max(r, (unsigned)sh->slot[i]);
+        sh->bar.arrive_and_wait();
+        return r;
+    }
+    template <class T> T ldg(const T *p) const { return *p; }
+    int atomic_add(int32_t *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+    void sync() { sh->bar.arrive_and_wait(); }
+};
+
+template <int K>
+static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *tasks, int n_tasks) {
+    PairHmmArgs AL = A;
+    AL.tasks = tasks;
+    AL.n_tasks = n_tasks;
+    WarpShared sh;
+    std::vector<std::thread> th;
+    for (int l = 0; l < 32; l++)
+        th.emplace_back([&, l]() {
+            EmulWarp w{ l, &sh };
+            for (int t = 0; t < n_tasks; t++) {
+                if (vargcp) pairhmm_fast_task<EmulWarp, K, true>(w, AL, t);
+                else pairhmm_fast_task<EmulWarp, K, false>(w, AL, t);
+            }
+        });
+    for (auto &t : th) t.join();
+}
+
+static void run_plain(const PairHmmArgs &A, int n) {
+    WarpShared sh;
+    std::vector<std::thread> th;
+    for (int l = 0; l < 32; l++)
+        th.emplace_back([&, l]() {
+            EmulWarp w{ l, &sh };
+            for (int i = 0; i < n; i++)
+                pairhmm_plain_pair<EmulWarp, LK_PLAIN_K>(w, A, A.rescue_pairs[i].read, (int64_t)A.rescue_pairs[i].hap, A.scratch);
+        });
+    for (auto &t : th) t.join();
+}
+
+// Same contract as lk_pairhmm_batch_host, executed by the emulator.  force_k > 0 pins K; force_f64 sends
+// every pair through the plain-form pass.  n_rescued (may be null) receives the f64-pass pair count.
+extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, int force_k, int force_f64,
+                                  double *out, uint8_t *flags, int32_t *n_rescued) {
+    const int64_t n_reads = b->region_read_start[b->n_regions], n_haps = b->region_hap_start[b->n_regions];
+    HostPrep P;
+    build_prep(b, n_reads, n_haps, force_k, !force_f64, P);
+    ModelTables T;
+    build_model_tables(T);
+    std::vector<uint32_t> henc((size_t)P.henc_words, 0u);
+    std::vector<uint8_t> hap_flags((size_t)n_haps, 0), read_flags((size_t)n_reads, 0);
+    for (int64_t h = 0; h < n_haps; h++) {  // = encode_haps_kernel
+        bool ex = false;
+        for (int64_t j = b->hap_off[h]; j < b->hap_off[h + 1]; j++)
+            henc[(size_t)(P.henc_off[(size_t)h] + (j - b->hap_off[h]))] = encode_base(b->hap_bases[j], ex);
+        hap_flags[(size_t)h] = ex ? SEQ_EXOTIC : 0;
+    }
+    bool vargcp = false;
+    uint8_t gcp_const = b->gcp_constant;
+    if (b->read_gcp) {
+        gcp_const = b->read_gcp[0];
+        for (int64_t i = 0; i < b->read_off[n_reads]; i++) if (b->read_gcp[i] != gcp_const) vargcp = true;
+    }
+    for (int64_t r = 0; r < n_reads; r++) {  // = scan_reads_kernel
+        bool ex = false, qz = false;
+        int imin = 255, imax = 0;
+        for (int64_t i = b->read_off[r]; i < b->read_off[r + 1]; i++) {
+            (void)encode_base(b->read_bases[i], ex);
+            qz |= b->read_qual[i] == 0;
+            imin = std::min<int>(imin, b->read_ins[i]);
+            imax = std::max<int>(imax, b->read_ins[i]);
+        }
+        read_flags[(size_t)r] = (ex ? SEQ_EXOTIC : 0) | ((qz || imax - imin > FAST_MAX_INS_RANGE) ? SEQ_QUAL_DOMAIN : 0);
+    }
+    std::vector<RescuePair> rescue((size_t)std::max<int64_t>(P.n_pairs, 1));
+    int32_t counters[2] = { 0, 0 };
+    std::vector<double> scratch((size_t)(6 * (P.h_max + 1)));
+    PairHmmArgs A;
+    memset(&A, 0, sizeof A);
+    A.read_bases = b->read_bases; A.read_qual = b->read_qual; A.read_ins = b->read_ins; A.read_del = b->read_del;
+    A.read_gcp = vargcp ? b->read_gcp : nullptr;
+    A.read_off = b->read_off; A.read_region = P.read_region.data(); A.read_out_base = P.read_out_base.data();
+    A.read_flags = read_flags.data(); A.region_hap_start = b->region_hap_start; A.hap_off = b->hap_off;
+    A.hap_bases = b->hap_bases; A.henc = henc.data(); A.henc_off = P.henc_off.data(); A.hap_flags = hap_flags.data();
+    A.qerr_f = T.qerr_f.data(); A.qerr_d = T.qerr_d.data(); A.m2m = T.m2m.data();
+    A.groups = P.groups.data(); A.out = out; A.flags = flags;
+    A.rescue_count = &counters[0]; A.rescue_cursor = &counters[1];
+    A.rescue_pairs = rescue.data(); A.rescue_capacity = (int32_t)P.n_pairs;
+    A.scratch = scratch.data(); A.scratch_stride = (int64_t)scratch.size();
+    A.gcp_constant = gcp_const;
+    A.mismatch_div = use_tristate ? 3.0f : 1.0f;
+    if (force_f64) {
+        for (int64_t r = 0; r < n_reads; r++) {
+            const int32_t g = P.read_region[(size_t)r];
+            for (int64_t h = b->region_hap_start[g]; h < b->region_hap_start[g + 1]; h++)
+                rescue[(size_t)counters[0]++] = RescuePair{ (int32_t)r, (int32_t)h };
+        }
+    } else {
+        for (const auto &d : P.direct) rescue[(size_t)counters[0]++] = d;
+        for (const auto &L : P.launches) {
+            const WarpTask *t = P.tasks.data() + L.first_task;
+            switch (L.K) {
+#define LK_CASE(KV, MINB) case KV: run_fast_tasks<KV>(A, vargcp, t, L.n_tasks); break;
+                LK_FAST_K_TABLE(LK_CASE)
+#undef LK_CASE
+                default: return -1;
+            }
+        }
+    }
+    if (n_rescued) *n_rescued = counters[0];
+    run_plain(A, counters[0]);
+    return 0;
+}

@@ -1,0 +1,120 @@
+"""CPU tests of the CUDA kernels' warp routines through the lock-step emulator (tests/emul).
+
+These run the same templated code the GPU runs (pairhmm_core.cuh) so lane/strip/skew index bugs
+are caught without a GPU.  The authoritative parity tests are the -m gpu ones."""
+import numpy as np
+import pytest
+
+import emul_runner as E
+import pairhmm_cases as PC
+from conftest import load_pairhmm_golden
+from oracle import lk_oracle as O
+
+
+def _golden_batch(rows):
+    cases = [dict(hap=r["hap"], read=r["read"], qual=r["qual"], ins=r["ins"], dele=r["dele"], gcp=r["gcp"]) for r in rows]
+    return PC.pack_cases(cases)
+
+
+@pytest.mark.parametrize("force_k", [0, 4, 10, 19])
+def test_golden_rows_fast_path(force_k):
+    rows = load_pairhmm_golden()[::4]
+    got, flags, n_resc = E.pairhmm_batch(_golden_batch(rows), force_k=force_k)
+    exp = np.array([r["expected"] for r in rows])
+    assert n_resc == 0 and np.all(flags == 0)
+    assert np.max(np.abs(got - exp)) < 1e-5  # tests/vector_pair_hmm_unit_tests.rs:63
+
+
+def test_golden_rows_f64_pass():
+    rows = load_pairhmm_golden()[::8]
+    batch = _golden_batch(rows)
+    got, flags, n_resc = E.pairhmm_batch(batch, force_f64=True)
+    exp = O.pairhmm_batch(batch)
+    assert n_resc == len(rows) and np.all(flags == 1)
+    assert np.max(np.abs(got - exp)) < 1e-11
+
+
+def test_region_layout_and_packing():
+    # 3 regions with ragged read lengths / haplotype counts: out[r*A + h], several reads per warp
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    rrs, rhs, roff, hoff = [0], [0], [0], [0]
+    rb, rq, ri, rd, hb = [], [], [], [], []
+    for g in range(3):
+        base = rng.choice(acgt, 120 + 20 * g)
+        for _ in range(2 + g):
+            h = base.copy()
+            h[rng.integers(0, len(h), 2)] = rng.choice(acgt, 2)
+            hb.append(h); hoff.append(hoff[-1] + len(h))
+        rhs.append(rhs[-1] + 2 + g)
+        for _ in range(7):
+            n = int(rng.integers(5, 100))
+            s = int(rng.integers(0, len(base) - n))
+            r = base[s:s + n].copy()
+            if n > 10:
+                r[rng.integers(0, n)] = ord("N")
+            rb.append(r); rq.append(rng.integers(6, 41, n).astype(np.uint8))
+            ri.append(rng.integers(30, 46, n).astype(np.uint8)); rd.append(rng.integers(30, 46, n).astype(np.uint8))
+            roff.append(roff[-1] + n)
+        rrs.append(rrs[-1] + 7)
+    batch = dict(region_read_start=np.array(rrs), region_hap_start=np.array(rhs), read_off=np.array(roff),
+                 hap_off=np.array(hoff), read_bases=np.concatenate(rb), read_qual=np.concatenate(rq),
+                 read_ins=np.concatenate(ri), read_del=np.concatenate(rd),
+                 read_gcp=np.full(roff[-1], 10, np.uint8), hap_bases=np.concatenate(hb))
+    exp = O.pairhmm_batch(batch)
+    for fk in (0, 6, 12):
+        got, flags, n_resc = E.pairhmm_batch(batch, force_k=fk)
+        assert n_resc == 0
+        assert np.max(np.abs(got - exp) / np.abs(exp)) < 1e-4
+
+
+def test_analytic_families_subset():
+    cases = PC.basic_likelihood_cases(extensive=True)[::97] + PC.mismatch_sweep_cases()[::5] + PC.all_matching_cases()
+    batch = PC.pack_cases(cases)
+    exp = O.pairhmm_batch(batch, use_tristate=False)
+    got, flags, n_resc = E.pairhmm_batch(batch, use_tristate=False)
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - exp) / np.maximum(1e-3, np.abs(exp))) < 1e-4
+
+
+def test_variable_gcp_and_exotic_bases():
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    hap = rng.choice(acgt, 90)
+    read = hap[10:70].copy()
+    n = len(read)
+    gcp = rng.integers(5, 20, n).astype(np.uint8)
+    c1 = dict(hap=hap, read=read, qual=np.full(n, 30, np.uint8), ins=np.full(n, 40, np.uint8),
+              dele=np.full(n, 42, np.uint8), gcp=gcp)
+    hap2 = hap.copy(); hap2[30] = ord("X"); read2 = read.copy(); read2[20] = ord("X")
+    c2 = dict(c1, hap=hap2, read=read2)
+    batch = PC.pack_cases([c1, c2])
+    exp = O.pairhmm_batch(batch)
+    got, flags, n_resc = E.pairhmm_batch(batch)
+    assert n_resc == 1 and flags[0] == 0 and flags[1] == 1  # exotic bytes go to the byte-exact f64 pass
+    assert abs(got[0] - exp[0]) / abs(exp[0]) < 1e-4
+    assert abs(got[1] - exp[1]) < 1e-10
+
+
+def test_underflow_is_rescued_and_long_read_bands():
+    rng = np.random.default_rng(2)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    # (a) unrelated read: fp32 underflows -> f64 pass
+    hap = rng.choice(acgt, 200)
+    read = rng.choice(acgt, 150)
+    n = len(read)
+    c1 = dict(hap=hap, read=read, qual=np.full(n, 40, np.uint8), ins=np.full(n, 45, np.uint8),
+              dele=np.full(n, 45, np.uint8), gcp=np.full(n, 10, np.uint8))
+    # (b) read longer than the fast path's 32*20 rows -> f64 pass with several row bands
+    hap_l = rng.choice(acgt, 900)
+    read_l = hap_l[50:50 + 700].copy()
+    m = len(read_l)
+    c2 = dict(hap=hap_l, read=read_l, qual=rng.integers(10, 30, m).astype(np.uint8), ins=np.full(m, 45, np.uint8),
+              dele=np.full(m, 45, np.uint8), gcp=np.full(m, 10, np.uint8))
+    batch = PC.pack_cases([c1, c2])
+    exp = O.pairhmm_batch(batch)
+    exp_resc = O.pairhmm_batch(batch, rescaled=True)
+    got, flags, n_resc = E.pairhmm_batch(batch)
+    assert n_resc == 2 and np.all(flags == 1)
+    assert abs(got[0] - exp[0]) < 1e-9
+    assert abs(got[1] - exp_resc[1]) < 1e-8
