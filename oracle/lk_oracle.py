@@ -147,7 +147,7 @@ def pairhmm_batch(batch, use_tristate=True, rescaled=False, n_threads=None, lib_
     L = lib(lib_path)
     if lib_path is not None:
         L.lko_init()
-    g = (lambda k: batch[k]) if isinstance(batch, dict) else (lambda k: getattr(batch, k))
+    g = (lambda k: batch[k]) if hasattr(batch, "__getitem__") else (lambda k: getattr(batch, k))
     rrs = np.ascontiguousarray(g("region_read_start"), dtype=np.int64)
     rhs = np.ascontiguousarray(g("region_hap_start"), dtype=np.int64)
     roff = np.ascontiguousarray(g("read_off"), dtype=np.int64)
