@@ -134,5 +134,11 @@ def load():
     L.lk_resident_cells.argtypes = [vp]
     L.lk_resident_pairs.restype = C.c_int64
     L.lk_resident_pairs.argtypes = [vp]
+    L.lk_resident_last_fast_ms.restype = C.c_float
+    L.lk_resident_last_fast_ms.argtypes = [vp]
+    L.lk_resident_out_device_ptr.restype = C.c_void_p
+    L.lk_resident_out_device_ptr.argtypes = [vp]
+    L.lk_measure_fp32_fma_tflops.restype = C.c_int
+    L.lk_measure_fp32_fma_tflops.argtypes = [vp, C.c_double, f64p]
     _LIB = L
     return L

@@ -53,6 +53,12 @@ class Context:
     def set_force_f64(self, on):
         self._check(self._L.lk_set_force_f64(self._h, 1 if on else 0))
 
+    def measure_fp32_fma_tflops(self, duration_ms=300.0):
+        """FFMA-only microbenchmark: the fp32 roofline denominator measured on this device."""
+        v = C.c_double(0.0)
+        self._check(self._L.lk_measure_fp32_fma_tflops(self._h, float(duration_ms), C.byref(v)))
+        return v.value
+
     # ---------------------------------------------------------------- PairHMM
     def pairhmm_batch(self, batch, want_flags=False):
         """lk_pairhmm_batch_host: host arrays in, log10 likelihoods out (layout r*A + h per region)."""
@@ -130,6 +136,15 @@ class ResidentPairHmm:
     @property
     def launch_count(self):
         return int(self.ctx._L.lk_resident_launch_count(self._r))
+
+    @property
+    def last_fast_ms(self):
+        """Device time of the dominant (fp32 wavefront) kernel launches inside the last run()."""
+        return float(self.ctx._L.lk_resident_last_fast_ms(self._r))
+
+    @property
+    def out_device_ptr(self):
+        return int(self.ctx._L.lk_resident_out_device_ptr(self._r))
 
     def download(self, want_flags=False):
         out = np.empty(self.n_pairs, dtype=np.float64)

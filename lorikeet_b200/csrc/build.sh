@@ -7,7 +7,7 @@ NVCC=${NVCC:-nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function"
 mkdir -p ../_build
 pids=()
-for f in pairhmm_kernels.cu sw_kernels.cu lk_api.cu lk_sw_api.cu; do
+for f in pairhmm_kernels.cu sw_kernels.cu lk_api.cu lk_sw_api.cu tools_kernels.cu; do
   [ -f "$f" ] || continue
   o=../_build/${f%.cu}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$o" -print -quit)" ] || [ ../../include/lorikeet_b200.h -nt "$o" ]; then

@@ -304,6 +304,7 @@ static lk_status run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
             if ((e = launch_scan_reads(A.read_bases, A.read_qual, A.read_ins, A.read_off, R->n_reads, (uint8_t *)R->read_flags.p, st)) != cudaSuccess)
                 return lk_cuda_fail(ctx, e, "scan_reads");
             R->launch_count += 2;
+            if (kernel_ms) { cudaEventCreate(&R->ev_fast0); cudaEventCreate(&R->ev_fast1); cudaEventRecord(R->ev_fast0, st); }
             for (const auto &L : R->launches) {
                 PairHmmArgs AL = A;
                 AL.tasks = (const WarpTask *)R->tasks.p + L.first_task;
@@ -311,6 +312,7 @@ static lk_status run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
                 if ((e = launch_fast(L.K, AL, R->vargcp, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_fast");
                 R->launch_count++;
             }
+            if (kernel_ms) cudaEventRecord(R->ev_fast1, st);
         }
         if ((e = launch_plain(A, R->plain_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_plain");
         R->launch_count++;
@@ -320,6 +322,12 @@ static lk_status run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
     if (kernel_ms) {
         if (e == cudaSuccess) cudaEventElapsedTime(kernel_ms, ev0, ev1);
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        R->last_fast_ms = 0.f;
+        if (R->ev_fast0) {
+            if (e == cudaSuccess) cudaEventElapsedTime(&R->last_fast_ms, R->ev_fast0, R->ev_fast1);
+            cudaEventDestroy(R->ev_fast0); cudaEventDestroy(R->ev_fast1);
+            R->ev_fast0 = R->ev_fast1 = nullptr;
+        }
     }
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm kernels");
     return LK_OK;
@@ -403,3 +411,8 @@ extern "C" int32_t lk_debug_last_launch_count(const lk_ctx *ctx) { return ctx ? 
 extern "C" int32_t lk_resident_launch_count(const lk_resident *r) { return r ? r->launch_count : -1; }
 extern "C" int64_t lk_resident_cells(const lk_resident *r) { return r ? r->n_cells : -1; }
 extern "C" int64_t lk_resident_pairs(const lk_resident *r) { return r ? r->n_pairs : -1; }
+
+// device pointer of the resident result block (f64, n_pairs) so a caller can hand it to a collective
+extern "C" void *lk_resident_out_device_ptr(const lk_resident *r) { return r ? r->out.p : nullptr; }
+// duration of the fast-path (dominant) kernel launches inside the last timed lk_pairhmm_run_resident
+extern "C" float lk_resident_last_fast_ms(const lk_resident *r) { return r ? r->last_fast_ms : -1.f; }

@@ -42,6 +42,8 @@ struct lk_resident {
     int plain_blocks = 0;
     int64_t scratch_stride = 0;
     int32_t launch_count = 0;
+    float last_fast_ms = 0.f;
+    cudaEvent_t ev_fast0 = nullptr, ev_fast1 = nullptr;
     std::vector<lk::FastLaunch> launches;
     DevBuf read_bases, read_qual, read_ins, read_del, read_gcp, read_off, read_region, read_out_base, read_flags;
     DevBuf region_hap_start, hap_off, hap_bases, henc, henc_off, hap_flags;
