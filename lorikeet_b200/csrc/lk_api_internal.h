@@ -49,6 +49,10 @@ struct lk_resident {
     DevBuf region_hap_start, hap_off, hap_bases, henc, henc_off, hap_flags;
     DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch;
     // ---- Smith-Waterman ----
+    struct SwLaunch { int K; int32_t first; int32_t count; };
+    std::vector<SwLaunch> sw_launches;
+    int sw_blocks = 0;
+    int64_t sw_scratch_words = 0;
     int64_t sw_n_pairs = 0, sw_cells = 0;
     int32_t sw_max_ops = 0, sw_strategy = 0;
     lk_sw_params sw_params = { 0, 0, 0, 0 };

@@ -1,15 +1,214 @@
-// lk_sw_api.cu — Smith-Waterman entry points of the C ABI (placeholder until sw_kernels.cu lands).
-#include "lk_api_internal.h"
+// lk_sw_api.cu — Smith-Waterman entry points of the C ABI (include/lorikeet_b200.h).
+//
+// Replaces gkl::smithwaterman::align() as called from SmithWatermanAligner::align
+// (src/smith_waterman/smith_waterman_aligner.rs:47-113); results are bit-identical to the reference's
+// in-tree scalar path (calculate_matrix :124-263 + calculate_cigar :273-442), which the reference's own
+// test_avx_mode asserts to equal the gkl path (tests/smith_waterman_aligner_unit_tests.rs:1001-1101).
+#include <cuda_runtime.h>
 
-extern "C" lk_status lk_sw_batch_host(lk_ctx *ctx, int64_t, const int64_t *, const uint8_t *, const int64_t *, const uint8_t *,
-                                      const lk_sw_params *, lk_sw_overhang, int32_t, uint32_t *, int32_t *, int32_t *) {
-    return lk_fail(ctx, LK_ERR_INVALID, "SW not built yet");
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lk_api_internal.h"
+#include "lk_internal.h"
+#include "sw_core.cuh"
+
+using namespace lk;
+
+namespace {
+
+const int kSwKs[] = { LK_SW_KS };
+constexpr int kNumSwKs = (int)(sizeof(kSwKs) / sizeof(kSwKs[0]));
+
+int sw_choose_k(int n) {
+    for (int i = 0; i < kNumSwKs; i++)
+        if (n <= 32 * kSwKs[i]) return kSwKs[i];
+    return kSwKs[kNumSwKs - 1];  // banded
 }
-extern "C" lk_status lk_sw_upload(lk_ctx *ctx, int64_t, const int64_t *, const uint8_t *, const int64_t *, const uint8_t *,
-                                  const lk_sw_params *, lk_sw_overhang, int32_t, lk_resident **) {
-    return lk_fail(ctx, LK_ERR_INVALID, "SW not built yet");
+
+template <class T>
+cudaError_t up(DevBuf &b, const T *src, size_t n, cudaStream_t st) {
+    cudaError_t e = b.reserve(std::max<size_t>(n * sizeof(T), 16));
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
 }
-extern "C" lk_status lk_sw_run_resident(lk_ctx *ctx, lk_resident *, float *) { return lk_fail(ctx, LK_ERR_INVALID, "SW not built yet"); }
-extern "C" lk_status lk_sw_download(lk_ctx *ctx, lk_resident *, uint32_t *, int32_t *, int32_t *) { return lk_fail(ctx, LK_ERR_INVALID, "SW not built yet"); }
-extern "C" lk_status lk_sw_align(lk_ctx *ctx, const uint8_t *, int64_t, const uint8_t *, int64_t, const lk_sw_params *,
-                                 lk_sw_overhang, char *, size_t, int32_t *) { return lk_fail(ctx, LK_ERR_INVALID, "SW not built yet"); }
+
+lk_status sw_upload_locked(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                           const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                           lk_sw_overhang strategy, int32_t max_ops, lk_resident **out_res) {
+    if (n_pairs < 0 || !params || max_ops < 1) return lk_fail(ctx, LK_ERR_INVALID, "bad SW arguments");
+    if ((int)strategy < 0 || (int)strategy > 3) return lk_fail(ctx, LK_ERR_INVALID, "bad overhang strategy");
+    if (n_pairs > 0 && (!ref_off || !refs || !alt_off || !alts)) return lk_fail(ctx, LK_ERR_INVALID, "null SW arrays");
+    if (n_pairs > 0x7fffffffLL / std::max(1, max_ops)) return lk_fail(ctx, LK_ERR_INVALID, "SW batch too large");
+    for (int64_t p = 0; p < n_pairs; p++)
+        if (ref_off[p + 1] < ref_off[p] || alt_off[p + 1] < alt_off[p]) return lk_fail(ctx, LK_ERR_INVALID, "decreasing SW offsets");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    lk_resident *R = new (std::nothrow) lk_resident();
+    if (!R) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    R->kind = 1;
+    R->sw_n_pairs = n_pairs; R->sw_max_ops = max_ops; R->sw_strategy = (int32_t)strategy; R->sw_params = *params;
+    // order arrays: one contiguous run per K class, longest pairs first inside a class (better tail balance)
+    std::vector<int32_t> order;
+    order.reserve((size_t)n_pairs);
+    int64_t max_words = 64;
+    R->sw_cells = 0;
+    for (int ki = 0; ki < kNumSwKs; ki++) {
+        const int K = kSwKs[ki];
+        const size_t first = order.size();
+        for (int64_t p = 0; p < n_pairs; p++) {
+            const int n = (int)(ref_off[p + 1] - ref_off[p]), m = (int)(alt_off[p + 1] - alt_off[p]);
+            if (sw_choose_k(n) != K) continue;
+            order.push_back((int32_t)p);
+            if (n > 0 && m > 0) max_words = std::max(max_words, sw_bt_words(n, m, K) + 2 * ((int64_t)m + 1) + 32);
+        }
+        std::stable_sort(order.begin() + (long)first, order.end(), [&](int32_t a, int32_t b) {
+            return (ref_off[a + 1] - ref_off[a]) * (alt_off[a + 1] - alt_off[a]) > (ref_off[b + 1] - ref_off[b]) * (alt_off[b + 1] - alt_off[b]);
+        });
+        if (order.size() > first) R->sw_launches.push_back(lk_resident::SwLaunch{ K, (int32_t)first, (int32_t)(order.size() - first) });
+    }
+    for (int64_t p = 0; p < n_pairs; p++) R->sw_cells += (ref_off[p + 1] - ref_off[p]) * (alt_off[p + 1] - alt_off[p]);
+    // persistent grid: up to 16 warps per SM, fewer if the per-warp backtrack scratch would exceed ~12 GB
+    const int warps_per_block = LK_SW_THREADS / 32;
+    int64_t warps = (int64_t)ctx->n_sm * 16;
+    const int64_t budget_words = (12LL << 30) / 4;
+    warps = std::max<int64_t>(warps_per_block, std::min(warps, budget_words / max_words));
+    warps = std::min<int64_t>(warps, std::max<int64_t>(warps_per_block, ((n_pairs + warps_per_block - 1) / warps_per_block) * warps_per_block));
+    R->sw_blocks = (int)(warps / warps_per_block);
+    R->sw_scratch_words = max_words;
+    cudaStream_t st = ctx->stream[0];
+    const int64_t ref_bytes = n_pairs ? ref_off[n_pairs] : 0, alt_bytes = n_pairs ? alt_off[n_pairs] : 0;
+    bool ok = (e = up(R->sw_refs, refs, (size_t)ref_bytes, st)) == cudaSuccess &&
+              (e = up(R->sw_alts, alts, (size_t)alt_bytes, st)) == cudaSuccess &&
+              (e = up(R->sw_ref_off, ref_off, (size_t)n_pairs + 1, st)) == cudaSuccess &&
+              (e = up(R->sw_alt_off, alt_off, (size_t)n_pairs + 1, st)) == cudaSuccess &&
+              (e = up(R->sw_order, order.data(), order.size(), st)) == cudaSuccess &&
+              (e = R->sw_ops.reserve((size_t)std::max<int64_t>(n_pairs * max_ops * 4, 16))) == cudaSuccess &&
+              (e = R->sw_nops.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
+              (e = R->sw_offsets.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
+              (e = R->counters.reserve(64)) == cudaSuccess &&
+              (e = R->sw_bt.reserve((size_t)((int64_t)R->sw_blocks * warps_per_block * max_words * 4))) == cudaSuccess &&
+              (e = cudaStreamSynchronize(st)) == cudaSuccess;
+    if (!ok) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "SW upload"); }
+    *out_res = R;
+    return LK_OK;
+}
+
+lk_status sw_run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
+    if (!R || R->kind != 1) return lk_fail(ctx, LK_ERR_INVALID, "not a Smith-Waterman resident batch");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    cudaStream_t st = ctx->stream[0];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (kernel_ms) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+    R->launch_count = 0;
+    SwArgs A;
+    memset(&A, 0, sizeof A);
+    A.refs = (const uint8_t *)R->sw_refs.p; A.alts = (const uint8_t *)R->sw_alts.p;
+    A.ref_off = (const int64_t *)R->sw_ref_off.p; A.alt_off = (const int64_t *)R->sw_alt_off.p;
+    A.w_match = R->sw_params.match_value; A.w_mismatch = R->sw_params.mismatch_penalty;
+    A.w_open = R->sw_params.gap_open_penalty; A.w_extend = R->sw_params.gap_extend_penalty;
+    A.strategy = R->sw_strategy; A.max_ops = R->sw_max_ops;
+    A.cigar_ops = (uint32_t *)R->sw_ops.p; A.n_ops = (int32_t *)R->sw_nops.p; A.offsets = (int32_t *)R->sw_offsets.p;
+    A.scratch = (uint32_t *)R->sw_bt.p; A.scratch_words = R->sw_scratch_words;
+    if ((e = cudaMemsetAsync(R->counters.p, 0, 64, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "memset");
+    int li = 0;
+    for (const auto &L : R->sw_launches) {
+        A.order = (const int32_t *)R->sw_order.p + L.first;
+        A.n_order = L.count;
+        A.cursor = (int32_t *)R->counters.p + li++;
+        if ((e = launch_sw(L.K, A, R->sw_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
+        R->launch_count++;
+    }
+    if (kernel_ms) cudaEventRecord(ev1, st);
+    e = cudaStreamSynchronize(st);
+    if (kernel_ms) {
+        if (e == cudaSuccess) cudaEventElapsedTime(kernel_ms, ev0, ev1);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    }
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "sw kernels");
+    return LK_OK;
+}
+
+lk_status sw_download_locked(lk_ctx *ctx, lk_resident *R, uint32_t *cigar_ops, int32_t *n_ops, int32_t *offsets) {
+    if (!R || R->kind != 1) return lk_fail(ctx, LK_ERR_INVALID, "not a Smith-Waterman resident batch");
+    if (R->sw_n_pairs == 0) return LK_OK;
+    if (!cigar_ops || !n_ops || !offsets) return lk_fail(ctx, LK_ERR_INVALID, "null SW outputs");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream[0];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cigar_ops, R->sw_ops.p, (size_t)R->sw_n_pairs * R->sw_max_ops * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_ops, R->sw_nops.p, (size_t)R->sw_n_pairs * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(offsets, R->sw_offsets.p, (size_t)R->sw_n_pairs * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "SW download");
+    return LK_OK;
+}
+
+}  // namespace
+
+extern "C" lk_status lk_sw_upload(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                                  const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                                  lk_sw_overhang strategy, int32_t max_ops, lk_resident **out_res) {
+    if (!ctx || !out_res) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    *out_res = nullptr;
+    return sw_upload_locked(ctx, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops, out_res);
+}
+
+extern "C" lk_status lk_sw_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return sw_run_locked(ctx, res, kernel_ms);
+}
+
+extern "C" lk_status lk_sw_download(lk_ctx *ctx, lk_resident *res, uint32_t *cigar_ops, int32_t *n_ops, int32_t *offsets) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    return sw_download_locked(ctx, res, cigar_ops, n_ops, offsets);
+}
+
+extern "C" lk_status lk_sw_batch_host(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                                      const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                                      lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops,
+                                      int32_t *alignment_offset) {
+    if (!ctx) return LK_ERR_INVALID;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    lk_resident *R = nullptr;
+    lk_status st = sw_upload_locked(ctx, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops, &R);
+    if (st != LK_OK) return st;
+    st = sw_run_locked(ctx, R, nullptr);
+    if (st == LK_OK) st = sw_download_locked(ctx, R, cigar_ops, n_ops, alignment_offset);
+    ctx->last_launch_count = R->launch_count;
+    lk_resident_free(ctx, R);
+    return st;
+}
+
+extern "C" lk_status lk_sw_align(lk_ctx *ctx, const uint8_t *ref, int64_t ref_len, const uint8_t *alt, int64_t alt_len,
+                                 const lk_sw_params *params, lk_sw_overhang strategy, char *cigar_text, size_t cigar_cap,
+                                 int32_t *alignment_offset) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (!ref || !alt || !params || !cigar_text || !alignment_offset || cigar_cap < 2) return lk_fail(ctx, LK_ERR_INVALID, "null argument");
+    if (ref_len <= 0 || alt_len <= 0)  // smith_waterman_aligner.rs:65-68
+        return lk_fail(ctx, LK_ERR_INVALID, "non-empty sequences are required for the Smith-Waterman calculation");
+    const int64_t ro[2] = { 0, ref_len }, ao[2] = { 0, alt_len };
+    const int32_t max_ops = (int32_t)std::min<int64_t>(2 * (ref_len + alt_len) + 8, 1 << 20);
+    std::vector<uint32_t> ops((size_t)max_ops);
+    int32_t n_ops = 0;
+    lk_status st = lk_sw_batch_host(ctx, 1, ro, ref, ao, alt, params, strategy, max_ops, ops.data(), &n_ops, alignment_offset);
+    if (st != LK_OK) return st;
+    if (n_ops < 0) return lk_fail(ctx, n_ops == -2 ? LK_ERR_CAPACITY : LK_ERR_INVALID, "Smith-Waterman failed");
+    std::string text;
+    static const char codes[] = "MIDNSHP=X";
+    for (int i = 0; i < n_ops; i++) {
+        char buf[32];
+        snprintf(buf, sizeof buf, "%u%c", ops[(size_t)i] >> 4, codes[ops[(size_t)i] & 0xF]);
+        text += buf;
+    }
+    if (text.size() + 1 > cigar_cap) return lk_fail(ctx, LK_ERR_CAPACITY, "cigar_text too small");
+    memcpy(cigar_text, text.c_str(), text.size() + 1);
+    return LK_OK;
+}

@@ -1,0 +1,320 @@
+// sw_core.cuh — Smith-Waterman (GATK single-matrix affine-gap formulation) with CIGAR traceback,
+// one warp per (reference, alternate) pair.
+//
+// Bit-exact re-design of src/smith_waterman/smith_waterman_aligner.rs:
+//   align            :47-113   (exact-substring shortcut for SoftClip / Ignore, :70-80,102-107)
+//   calculate_matrix :124-263  (fill)
+//   calculate_cigar  :273-442  (start-cell search, traceback, overhang handling)
+//
+// Layout: rows = reference positions, columns = alternate positions, exactly as the reference.
+// Each lane owns K consecutive rows; the warp sweeps the columns as a skewed wavefront (lane l is
+// at column s-l at step s) and hands (H, F) of its last row to the next lane by shuffle.  Rows are
+// processed in bands of 32*K; a band's last row travels through per-warp scratch.
+//
+// The reference keeps two (n+1)x(m+1) i32 matrices (sw, btrack).  Here nothing of `sw` is stored
+// except the band boundary; `btrack` is compressed to 4 bits per cell
+//     bits 0-1  move: 0 diagonal, 1 horizontal ("step right", insertion), 2 vertical ("step down", deletion)
+//     bit  2    a horizontal gap was (re)opened at this cell  (gap_size_h[i] reset to 1, :235-239)
+//     bit  3    a vertical gap was (re)opened at this cell    (gap_size_v[j] reset to 1, :212-218)
+// from which the stored gap length k of the reference's btrack (-ki / +kd) is recovered during the
+// traceback by walking back to the cell where the gap was opened.  Nibbles of one lane's K rows are
+// packed into ceil(K/8) words and stored step-major ([step][word][lane]) so every store is a
+// coalesced 128-byte line.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LK_DEV __device__ __forceinline__
+#define LK_HD __host__ __device__ __forceinline__
+#else
+#define LK_DEV inline
+#define LK_HD inline
+#endif
+
+namespace lk {
+
+enum : int { SW_SOFTCLIP = 0, SW_INDEL = 1, SW_LEADING_INDEL = 2, SW_IGNORE = 3 };
+enum : uint32_t { CIG_M = 0, CIG_I = 1, CIG_D = 2, CIG_S = 4 };
+constexpr int32_t SW_MATRIX_MIN_CUTOFF = -100000000;            // smith_waterman_aligner.rs:31
+constexpr int32_t SW_LOW_INIT = (int32_t)(-2147483647 - 1) / 2;  // i32::MIN / 2, :139
+
+struct SwArgs {
+    const uint8_t *refs, *alts;
+    const int64_t *ref_off, *alt_off;
+    const int32_t *order;      // pair ids this launch works through (dynamic, via cursor)
+    int32_t n_order;
+    int32_t *cursor;
+    int32_t w_match, w_mismatch, w_open, w_extend;
+    int32_t strategy;
+    int32_t max_ops;
+    uint32_t *cigar_ops;       // [pair][max_ops]
+    int32_t *n_ops;            // [pair]
+    int32_t *offsets;          // [pair]
+    uint32_t *scratch;         // per-warp backtrack + band boundary
+    int64_t scratch_words;     // words per warp
+};
+
+LK_DEV uint32_t sw_cigar_el(uint32_t op, int32_t len) { return ((uint32_t)len << 4) | op; }
+
+// number of backtrack words one pair needs (host + device agree on this)
+LK_HD int64_t sw_bt_words(int n, int m, int K) {
+    const int band_rows = 32 * K;
+    const int n_bands = (n + band_rows - 1) / band_rows;
+    const int W = (K + 7) / 8;
+    return (int64_t)n_bands * (int64_t)(m + 32) * W * 32;
+}
+
+template <class Wp, int K>
+LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
+    const int lane = w.lane();
+    const uint8_t *ref = A.refs + A.ref_off[pair];
+    const uint8_t *alt = A.alts + A.alt_off[pair];
+    const int n = (int)(A.ref_off[pair + 1] - A.ref_off[pair]);
+    const int m = (int)(A.alt_off[pair + 1] - A.alt_off[pair]);
+    uint32_t *ops_out = A.cigar_ops + (int64_t)pair * A.max_ops;
+    if (n <= 0 || m <= 0) {  // :65-68 assert
+        if (lane == 0) { A.n_ops[pair] = -1; A.offsets[pair] = 0; }
+        return;
+    }
+    const int strategy = A.strategy;
+
+    // ---- exact-substring shortcut, AlignmentUtils::last_index_of (alignment_utils.rs:717-735) ----
+    if ((strategy == SW_SOFTCLIP || strategy == SW_IGNORE) && m <= n) {
+        int found = -1;
+        for (int base = n - m; base >= 0 && found < 0; base -= 32) {
+            const int r = base - lane;
+            bool ok = r >= 0;
+            if (ok) {
+                int q = 0;
+                while (q < m && ref[r + q] == alt[q]) q++;
+                ok = (q == m);
+            }
+            const unsigned b = w.ballot(ok);
+            if (b) found = base - (w.ffs(b) - 1);  // lowest lane = largest r
+        }
+        if (found >= 0) {
+            if (lane == 0) {
+                if (A.max_ops < 1) A.n_ops[pair] = -2;
+                else { ops_out[0] = sw_cigar_el(CIG_M, m); A.n_ops[pair] = 1; }
+                A.offsets[pair] = found;
+            }
+            return;
+        }
+    }
+
+    // ---- fill -----------------------------------------------------------------------------------
+    const int32_t wm = A.w_match, wx = A.w_mismatch, wo = A.w_open, we = A.w_extend;
+    const bool edge_gaps = (strategy == SW_INDEL || strategy == SW_LEADING_INDEL);  // :146-179
+    const int BAND = 32 * K;
+    const int n_bands = (n + BAND - 1) / BAND;
+    constexpr int W = (K + 7) / 8;
+    const int64_t band_words = (int64_t)(m + 32) * W * 32;
+    uint32_t *bt = scratch;                                         // [band][step][W][32]
+    int32_t *bndH = (int32_t *)(scratch + sw_bt_words(n, m, K));    // two boundary rows: H then F
+    int32_t *bndF = bndH + (m + 1);
+    // best cell of the last column (scan top->bottom with >=, :301-307) and bottom-row summary
+    int32_t col_max = (int32_t)(-2147483647 - 1);
+    int col_p1 = 0;
+    int32_t bot_max = (int32_t)(-2147483647 - 1);
+    int bot_j = 0;
+
+    for (int band = 0; band < n_bands; band++) {
+        const int row0 = band * BAND;  // rows row0+1 .. row0+rows (1-based)
+        const int rows = (n - row0 < BAND) ? (n - row0) : BAND;
+        const int lanes = (rows + K - 1) / K;
+        uint32_t rb[K];
+        int32_t H[K], E[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int i = row0 + lane * K + k + 1;  // 1-based matrix row
+            rb[k] = (i <= n) ? (uint32_t)ref[i - 1] : 0x100u;
+            H[k] = edge_gaps ? (wo + (i - 1) * we) : 0;  // sw[i][0]
+            E[k] = SW_LOW_INIT;                           // best_gap_h[i]
+        }
+        // column 0 of the row above this lane's strip
+        const int i_above = row0 + lane * K;  // matrix row index of the row above (0 = top row)
+        int32_t Hd = (i_above == 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
+        int32_t Hu = 0, Fu = SW_LOW_INIT;
+        uint32_t *btb = bt + (int64_t)band * band_words;
+        const bool has_bottom = (band == n_bands - 1);
+        const int bottom_lane = (rows - 1) / K, bottom_k = (rows - 1) % K;
+        const int n_steps = m + lanes - 1;
+
+        for (int s = 1; s <= n_steps; s++) {
+            const int c = s - lane;
+            if (lane == 0) {  // row above comes from the matrix top row or from the previous band
+                if (band == 0) { Hu = edge_gaps ? (wo + (c - 1) * we) : 0; Fu = SW_LOW_INIT; }
+                else if (c <= m) { Hu = bndH[c]; Fu = bndF[c]; }
+            }
+            const bool active = (c >= 1) && (c <= m) && (lane < lanes);
+            int32_t h_last = 0, f_last = SW_LOW_INIT;
+            if (active) {
+                const uint32_t ab = w.ldg(alt + c - 1);
+                int32_t hdiag = Hd, hup = Hu, fup = Fu;
+                uint32_t words[W];
+#pragma unroll
+                for (int i = 0; i < W; i++) words[i] = 0u;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const int32_t hold = H[k];
+                    const int32_t step_diag = hdiag + ((rb[k] == ab) ? wm : wx);     // :197-202
+                    const int32_t open_v = hup + wo, ext_v = fup + we;               // :210-222
+                    const bool vopen = open_v > ext_v;
+                    const int32_t step_down = vopen ? open_v : ext_v;
+                    const int32_t open_h = hold + wo, ext_h = E[k] + we;             // :232-245
+                    const bool hopen = open_h > ext_h;
+                    const int32_t step_right = hopen ? open_h : ext_h;
+                    uint32_t mv;
+                    int32_t best;
+                    if (step_diag >= step_down && step_diag >= step_right) { mv = 0u; best = step_diag; }  // :248-260
+                    else if (step_right >= step_down) { mv = 1u; best = step_right; }
+                    else { mv = 2u; best = step_down; }
+                    best = best > SW_MATRIX_MIN_CUTOFF ? best : SW_MATRIX_MIN_CUTOFF;
+                    const uint32_t nib = mv | (hopen ? 4u : 0u) | (vopen ? 8u : 0u);
+                    words[k >> 3] |= nib << (4 * (k & 7));
+                    E[k] = step_right;
+                    H[k] = best;
+                    hdiag = hold; hup = best; fup = step_down;
+                }
+                h_last = H[K - 1]; f_last = fup;
+#pragma unroll
+                for (int i = 0; i < W; i++) btb[((int64_t)s * W + i) * 32 + lane] = words[i];
+                if (c == m) {  // this lane's rows of the last column, top -> bottom with >=  (:301-307)
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        const int i = row0 + lane * K + k + 1;
+                        if (i <= n && H[k] >= col_max) { col_max = H[k]; col_p1 = i; }
+                    }
+                }
+                if (has_bottom && lane == bottom_lane) {  // bottom row summary (:316-329), see below
+                    int32_t cur = H[0];
+#pragma unroll
+                    for (int k = 1; k < K; k++) cur = (k == bottom_k) ? H[k] : cur;
+                    const int dj = (n > c) ? (n - c) : (c - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
+                    if (cur > bot_max || (cur == bot_max && dj < db)) { bot_max = cur; bot_j = c; }
+                }
+                if (!has_bottom && lane == lanes - 1) { bndH[c] = h_last; bndF[c] = f_last; }
+            }
+            // hand the strip's last row to the next lane; keep this step's "up" as next step's diagonal
+            Hd = Hu;
+            const int32_t hs = w.shfl_up1(h_last), fs = w.shfl_up1(f_last);
+            if (lane != 0) { Hu = hs; Fu = fs; }
+            // a lane that has not started yet must keep seeing column 0 of the row above as its diagonal
+            if (c < 1) Hd = (i_above == 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
+        }
+        w.sync();
+    }
+
+    // ---- start cell (:288-333) -------------------------------------------------------------------
+    // last column: every lane scanned its own rows with >=; combine so the LARGEST row among maxima wins
+    for (int d = 16; d >= 1; d >>= 1) {
+        const int32_t ov = w.shfl_xor(col_max, d);
+        const int op = w.shfl_xor(col_p1, d);
+        if (ov > col_max || (ov == col_max && op > col_p1)) { col_max = ov; col_p1 = op; }
+    }
+    {
+        const int bl = ((n - (n_bands - 1) * BAND) - 1) / K;
+        bot_max = w.shfl(bot_max, bl);
+        bot_j = w.shfl(bot_j, bl);
+    }
+    int p1, p2;
+    int32_t segment_length = 0;
+    if (strategy == SW_INDEL) { p1 = n; p2 = m; }
+    else {
+        p1 = col_p1; p2 = m;
+        if (strategy != SW_LEADING_INDEL) {
+            // The reference scans the bottom row left->right taking a cell if it is strictly better, or equal and
+            // closer to the diagonal than the current best.  Its outcome depends only on the row maximum and on the
+            // maximal cell closest to the diagonal (leftmost on ties), which is what (bot_max, bot_j) track.
+            const int d_best = (p1 > p2) ? (p1 - p2) : (p2 - p1);
+            const int d_bot = (n > bot_j) ? (n - bot_j) : (bot_j - n);
+            if (bot_max > col_max || (bot_max == col_max && d_bot < d_best)) {
+                p1 = n; p2 = bot_j;
+                segment_length = m - bot_j;
+            }
+        }
+    }
+
+    // ---- traceback (:335-442), warp-cooperative: 32 cells of a run are fetched per round trip -----
+    auto nibble = [&](int i, int j) -> uint32_t {  // backtrack nibble of matrix cell (i, j), 1-based
+        const int band = (i - 1) / BAND, r = (i - 1) % BAND, ln = r / K, k = r % K;
+        const uint32_t wd = bt[(int64_t)band * band_words + ((int64_t)(j + ln) * W + (k >> 3)) * 32 + ln];
+        return (wd >> (4 * (k & 7))) & 15u;
+    };
+    int n_out = 0;
+    bool overflow = false;
+    auto push = [&](uint32_t el) {
+        if (n_out < A.max_ops) { if (lane == 0) ops_out[n_out] = el; }
+        else overflow = true;
+        n_out++;
+    };
+    if (segment_length > 0 && strategy == SW_SOFTCLIP) { push(sw_cigar_el(CIG_S, segment_length)); segment_length = 0; }
+    int state = 0;  // 0 match, 1 insertion, 2 deletion
+    auto op_of = [](int st) -> uint32_t { return st == 0 ? CIG_M : (st == 1 ? CIG_I : CIG_D); };
+    for (;;) {
+        // how many consecutive diagonal moves start at (p1, p2)?
+        const int lim = (p1 < p2) ? p1 : p2;  // cells available along the diagonal
+        int run = 0;
+        uint32_t stop_nib = 0;
+        for (;;) {
+            const int t = run + lane;
+            uint32_t nb = 0xFFu;
+            if (t < lim) nb = nibble(p1 - t, p2 - t);
+            const unsigned nd = w.ballot(t >= lim || (nb & 3u) != 0u);
+            if (nd == 0) { run += 32; continue; }
+            const int f = w.ffs(nd) - 1;
+            run += f;
+            stop_nib = w.shfl(nb, f);
+            break;
+        }
+        if (run > 0) {  // `run` diagonal steps
+            if (state == 0) segment_length += run;
+            else { if (segment_length > 0) push(sw_cigar_el(op_of(state), segment_length)); segment_length = run; state = 0; }
+            p1 -= run; p2 -= run;
+            if (p1 <= 0 || p2 <= 0) break;
+        }
+        // (p1, p2) holds a gap move; recover its length = distance back to the cell where the gap was opened
+        const uint32_t mv = stop_nib & 3u;
+        int glen = 0;
+        for (;;) {
+            const int t = glen + lane;
+            bool opened;
+            if (mv == 1u) { opened = (p2 - t <= 1) ? true : ((nibble(p1, p2 - t) & 4u) != 0u); }
+            else { opened = (p1 - t <= 1) ? true : ((nibble(p1 - t, p2) & 8u) != 0u); }
+            const unsigned b = w.ballot(opened);
+            if (b == 0) { glen += 32; continue; }
+            glen += w.ffs(b);  // inclusive
+            break;
+        }
+        const int new_state = (mv == 1u) ? 1 : 2;
+        if (new_state == 1) p2 -= glen; else p1 -= glen;
+        if (new_state == state) segment_length += glen;
+        else { if (segment_length > 0) push(sw_cigar_el(op_of(state), segment_length)); segment_length = glen; state = new_state; }
+        if (p1 <= 0 || p2 <= 0) break;
+    }
+    int32_t alignment_offset;
+    if (strategy == SW_SOFTCLIP) {          // :413-419
+        push(sw_cigar_el(op_of(state), segment_length));
+        if (p2 > 0) push(sw_cigar_el(CIG_S, p2));
+        alignment_offset = p1;
+    } else if (strategy == SW_IGNORE) {     // :420-423
+        push(sw_cigar_el(op_of(state), segment_length + p2));
+        alignment_offset = p1 - p2;
+    } else {                                // :424-436
+        push(sw_cigar_el(op_of(state), segment_length));
+        if (p1 > 0) push(sw_cigar_el(CIG_D, p1));
+        else if (p2 > 0) push(sw_cigar_el(CIG_I, p2));
+        alignment_offset = 0;
+    }
+    w.sync();
+    if (lane == 0) {
+        if (overflow) A.n_ops[pair] = -2;
+        else {
+            for (int a = 0, b = n_out - 1; a < b; a++, b--) { const uint32_t t = ops_out[a]; ops_out[a] = ops_out[b]; ops_out[b] = t; }  // :440
+            A.n_ops[pair] = n_out;
+        }
+        A.offsets[pair] = alignment_offset;
+    }
+}
+
+}  // namespace lk

@@ -1,0 +1,47 @@
+// sw_kernels.cu — sm_100a Smith-Waterman kernel (fill + in-kernel traceback) and its launcher.
+// Persistent warps pull pair ids from a cursor; each warp owns a slice of scratch for the 4-bit backtrack.
+#include <cuda_runtime.h>
+
+#include "lk_internal.h"
+#include "sw_core.cuh"
+
+namespace lk {
+
+struct SwDevWarp {
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    template <class T> __device__ __forceinline__ T shfl_up1(T v) const { return __shfl_up_sync(0xffffffffu, v, 1); }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    __device__ __forceinline__ int ffs(unsigned v) const { return __ffs((int)v); }
+    template <class T> __device__ __forceinline__ T ldg(const T *p) const { return __ldg(p); }
+    __device__ __forceinline__ void sync() const { __threadfence_block(); __syncwarp(); }
+};
+
+template <int K>
+__global__ void __launch_bounds__(LK_SW_THREADS) sw_kernel(const SwArgs A) {
+    SwDevWarp w;
+    const int warp_in_grid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    uint32_t *scratch = A.scratch + (int64_t)warp_in_grid * A.scratch_words;
+    for (;;) {
+        int idx = 0;
+        if (w.lane() == 0) idx = atomicAdd(A.cursor, 1);
+        idx = w.shfl(idx, 0);
+        if (idx >= A.n_order) break;
+        sw_align_pair<SwDevWarp, K>(w, A, A.order[idx], scratch);
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_sw(int K, const SwArgs &A, int n_blocks, cudaStream_t st) {
+    if (A.n_order == 0) return cudaSuccess;
+    switch (K) {
+#define LK_CASE(KV) case KV: sw_kernel<KV><<<n_blocks, LK_SW_THREADS, 0, st>>>(A); break;
+        LK_SW_K_TABLE(LK_CASE)
+#undef LK_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace lk

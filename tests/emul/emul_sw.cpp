@@ -1,0 +1,82 @@
+// emul_sw.cpp — TEST TOOLING ONLY: runs the Smith-Waterman warp routine (lorikeet_b200/csrc/sw_core.cuh) in the
+// 32-thread lock-step emulator (see emul_pairhmm.cpp).
+#include <algorithm>
+#include <barrier>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../lorikeet_b200/csrc/lk_config.h"
+#include "../../lorikeet_b200/csrc/sw_core.cuh"
+
+using namespace lk;
+
+struct SwShared {
+    std::barrier<> bar{32};
+    uint64_t slot[32];
+};
+
+struct SwEmulWarp {
+    int lane_;
+    SwShared *sh;
+    int lane() const { return lane_; }
+    template <class T> T exchange(T v, int src) {
+        uint64_t bits = 0;
+        memcpy(&bits, &v, sizeof(T));
+        sh->slot[lane_] = bits;
+        sh->bar.arrive_and_wait();
+        T r = v;
+        if (src >= 0 && src < 32) memcpy(&r, &sh->slot[src], sizeof(T));
+        sh->bar.arrive_and_wait();
+        return r;
+    }
+    template <class T> T shfl_up1(T v) { return exchange(v, lane_ - 1); }
+    template <class T> T shfl(T v, int src) { return exchange(v, src & 31); }
+    template <class T> T shfl_xor(T v, int m) { return exchange(v, lane_ ^ m); }
+    unsigned ballot(bool p) {
+        sh->slot[lane_] = p ? 1 : 0;
+        sh->bar.arrive_and_wait();
+        unsigned r = 0;
+        for (int i = 0; i < 32; i++) r |= (unsigned)sh->slot[i] << i;
+        sh->bar.arrive_and_wait();
+        return r;
+    }
+    int ffs(unsigned v) const { return __builtin_ffs((int)v); }
+    template <class T> T ldg(const T *p) const { return *p; }
+    void sync() { sh->bar.arrive_and_wait(); }
+};
+
+static int choose_k(int n, int force_k) {
+    if (force_k > 0) return force_k;
+    static const int ks[] = { LK_SW_KS };
+    for (int k : ks) if (n <= 32 * k) return k;
+    return 17;
+}
+
+extern "C" int emul_sw_batch(int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs, const int64_t *alt_off,
+                             const uint8_t *alts, const int32_t *params, int strategy, int max_ops, int force_k,
+                             uint32_t *cigar_ops, int32_t *n_ops, int32_t *offsets) {
+    SwArgs A;
+    memset(&A, 0, sizeof A);
+    A.refs = refs; A.alts = alts; A.ref_off = ref_off; A.alt_off = alt_off;
+    A.w_match = params[0]; A.w_mismatch = params[1]; A.w_open = params[2]; A.w_extend = params[3];
+    A.strategy = strategy; A.max_ops = max_ops; A.cigar_ops = cigar_ops; A.n_ops = n_ops; A.offsets = offsets;
+    SwShared sh;
+    for (int64_t p = 0; p < n_pairs; p++) {
+        const int n = (int)(ref_off[p + 1] - ref_off[p]), m = (int)(alt_off[p + 1] - alt_off[p]);
+        const int K = choose_k(n, force_k);
+        std::vector<uint32_t> scratch((size_t)(n > 0 && m > 0 ? sw_bt_words(n, m, K) + 2 * (m + 1) + 32 : 64));
+        std::vector<std::thread> th;
+        for (int l = 0; l < 32; l++)
+            th.emplace_back([&, l]() {
+                SwEmulWarp w{ l, &sh };
+                switch (K) {
+#define LK_CASE(KV) case KV: sw_align_pair<SwEmulWarp, KV>(w, A, (int)p, scratch.data()); break;
+                    LK_SW_K_TABLE(LK_CASE)
+#undef LK_CASE
+                }
+            });
+        for (auto &t : th) t.join();
+    }
+    return 0;
+}

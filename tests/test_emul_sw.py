@@ -1,0 +1,56 @@
+"""CPU tests of the CUDA Smith-Waterman warp routine through the lock-step emulator (tests/emul), bit-exact
+against the oracle (= the reference's scalar path).  The authoritative parity tests are the -m gpu ones."""
+import numpy as np
+import pytest
+
+import emul_runner as E
+import sw_cases as SC
+from oracle import lk_oracle as O
+
+
+def _compare(pairs, params, strategy, max_ops=256, force_k=0):
+    ro, refs, ao, alts = SC.pack(pairs)
+    ops, n_ops, offs = E.sw_batch(ro, refs, ao, alts, params, strategy, max_ops=max_ops, force_k=force_k)
+    eops, en, eoffs = O.sw_batch(ro, refs, ao, alts, params, strategy, max_ops=max_ops)
+    for i in range(len(pairs)):
+        assert n_ops[i] == en[i], (i, strategy, params, O.cigar_to_string(ops[i, :max(n_ops[i], 0)]), O.cigar_to_string(eops[i, :en[i]]))
+        assert offs[i] == eoffs[i], (i, strategy, params)
+        assert np.array_equal(ops[i, :n_ops[i]], eops[i, :en[i]]), (i, strategy, params, O.cigar_to_string(ops[i, :n_ops[i]]), O.cigar_to_string(eops[i, :en[i]]))
+
+
+def test_known_answers():
+    for c in SC.KAT:
+        ro, refs, ao, alts = SC.pack([(c["ref"], c["alt"])])
+        ops, n_ops, offs = E.sw_batch(ro, refs, ao, alts, c["params"], c["strategy"])
+        assert (int(offs[0]), O.cigar_to_string(ops[0, :n_ops[0]])) == (c["offset"], c["cigar"]), c
+
+
+@pytest.mark.parametrize("strategy", SC.STRATEGIES)
+def test_random_pairs_all_params(strategy):
+    pairs = SC.random_pairs(60, seed=hash(strategy) % 1000)
+    for params in SC.ALL_PARAMS:
+        _compare(pairs, params, strategy)
+
+
+@pytest.mark.parametrize("force_k", [2, 4])
+def test_multi_band_small_k(force_k):
+    # forcing a small K makes references of 70..200 rows span several row bands
+    pairs = SC.random_pairs(16, seed=3, min_len=70, max_len=200)
+    for strategy in SC.STRATEGIES:
+        _compare(pairs, SC.NEW_SW_PARAMETERS, strategy, force_k=force_k)
+
+
+def test_long_pair_reference_fixture():
+    # one of the test_avx_mode pairs (ref 275+20 x alt 1154+20), 3 strategies as in the reference test
+    pair = SC.long_pairs_padded()[:1]
+    for strategy in ("InDel", "SoftClip", "LeadingInDel"):
+        _compare(pair, SC.NEW_SW_PARAMETERS, strategy, max_ops=512)
+
+
+def test_capacity_and_empty():
+    ro, refs, ao, alts = SC.pack([("ACGTACGTAAAA", "ACGAACGTTTTAAAA"), ("ACGT", "ACGT")])
+    ops, n_ops, offs = E.sw_batch(ro, refs, ao, alts, SC.ORIGINAL_DEFAULT, "InDel", max_ops=1)
+    assert n_ops[0] == -2 and n_ops[1] == 1
+    ro = np.array([0, 0, 4]); ao = np.array([0, 3, 3])
+    ops, n_ops, offs = E.sw_batch(ro, np.frombuffer(b"ACGT", np.uint8), ao, np.frombuffer(b"ACG", np.uint8), SC.ORIGINAL_DEFAULT, "SoftClip")
+    assert list(n_ops) == [-1, -1]

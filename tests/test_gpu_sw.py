@@ -1,0 +1,120 @@
+"""GPU parity tests (-m gpu): the CUDA Smith-Waterman path through the C ABI must reproduce the reference's
+(offset, CIGAR) bit for bit (BASELINE.json north_star: "SW CIGARs bit-exact").  Mirrors
+tests/smith_waterman_aligner_unit_tests.rs of the reference."""
+import numpy as np
+import pytest
+
+import sw_cases as SC
+from oracle import lk_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import lorikeet_b200 as lk
+    c = lk.Context(0)
+    yield c
+    c.close()
+
+
+def _compare(ctx, pairs, params, strategy, max_ops=256):
+    ro, refs, ao, alts = SC.pack(pairs)
+    ops, n_ops, offs = ctx.sw_batch(ro, refs, ao, alts, params, strategy, max_ops=max_ops)
+    eops, en, eoffs = O.sw_batch(ro, refs, ao, alts, params, strategy, max_ops=max_ops)
+    assert np.array_equal(n_ops, en)
+    assert np.array_equal(offs, eoffs)
+    for i in range(len(pairs)):
+        assert np.array_equal(ops[i, :max(n_ops[i], 0)], eops[i, :max(en[i], 0)]), (i, strategy, params)
+
+
+@pytest.mark.parametrize("case", SC.KAT, ids=[c["source"].split(":")[-1] + c["strategy"] for c in SC.KAT])
+def test_known_answers_single_pair_entry_point(ctx, case):
+    # the gkl::smithwaterman::align()-shaped wrapper: ASCII CIGAR + offset (smith_waterman_aligner.rs:56-61)
+    off, cigar = ctx.sw_align(case["ref"], case["alt"], case["params"], case["strategy"])
+    assert (off, cigar) == (case["offset"], case["cigar"])
+
+
+@pytest.mark.parametrize("strategy", SC.STRATEGIES)
+@pytest.mark.parametrize("params", SC.ALL_PARAMS, ids=["new", "ngs", "besthap", "orig"])
+def test_random_pairs(ctx, strategy, params):
+    _compare(ctx, SC.random_pairs(400, seed=len(strategy) * 7 + params[0], max_len=120), params, strategy)
+
+
+@pytest.mark.parametrize("strategy", ["InDel", "SoftClip", "LeadingInDel", "Ignore"])
+def test_avx_mode_long_pairs(ctx, strategy):
+    # test_avx_mode (:403-1101): 3 long pairs x {NEW_SW, STANDARD_NGS, ALIGNMENT_TO_BEST_HAPLOTYPE}, 10xN padded
+    for params in (SC.NEW_SW_PARAMETERS, SC.STANDARD_NGS, SC.ALIGNMENT_TO_BEST_HAPLOTYPE):
+        _compare(ctx, SC.long_pairs_padded(), params, strategy, max_ops=1024)
+
+
+def test_thread_safety_hammer(ctx):
+    # the reference hammers align() from 1000 parallel tasks (:1001); here 8 host threads share one context
+    import threading
+    pairs = SC.long_pairs_padded()
+    ro, refs, ao, alts = SC.pack(pairs)
+    exp = O.sw_batch(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, "SoftClip", max_ops=1024)
+    errs = []
+
+    def work():
+        try:
+            for _ in range(5):
+                got = ctx.sw_batch(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, "SoftClip", max_ops=1024)
+                assert np.array_equal(got[1], exp[1]) and np.array_equal(got[2], exp[2])
+                for i in range(len(pairs)):
+                    assert np.array_equal(got[0][i, :got[1][i]], exp[0][i, :exp[1][i]])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work) for _ in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:1]
+
+
+def test_cfg4_slice_all_strategies(ctx):
+    # cfg#4 generator (500 bp + 10xN pads, NEW_SW_PARAMETERS): SoftClip on 1500 pairs, the others on a 10 % slice
+    from lorikeet_b200 import synth
+    ro, refs, ao, alts = synth.sw_pairs(1500)
+    for strategy, n in (("SoftClip", 1500), ("InDel", 150), ("LeadingInDel", 150), ("Ignore", 150)):
+        r, a = ro[:n + 1], ao[:n + 1]
+        ops, n_ops, offs = ctx.sw_batch(r, refs[:r[-1]], a, alts[:a[-1]], SC.NEW_SW_PARAMETERS, strategy, max_ops=64)
+        eops, en, eoffs = O.sw_batch(r, refs[:r[-1]], a, alts[:a[-1]], SC.NEW_SW_PARAMETERS, strategy, max_ops=64)
+        assert np.array_equal(n_ops, en) and np.array_equal(offs, eoffs)
+        assert np.array_equal(ops, eops)
+    ops, n_ops, offs = ctx.sw_batch(ro[:151], refs[:ro[150]], ao[:151], alts[:ao[150]], SC.STANDARD_NGS, "LeadingInDel")
+    eops, en, eoffs = O.sw_batch(ro[:151], refs[:ro[150]], ao[:151], alts[:ao[150]], SC.STANDARD_NGS, "LeadingInDel")
+    assert np.array_equal(ops, eops) and np.array_equal(offs, eoffs)
+
+
+def test_multi_band_long_reference(ctx):
+    # references longer than 32*17 rows exercise the band boundary (H, F) hand-off
+    rng = np.random.default_rng(4)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    pairs = []
+    for n in (545, 700, 1300, 2000):
+        ref = rng.choice(acgt, n)
+        alt = np.concatenate([ref[30:n // 2], rng.choice(acgt, 17), ref[n // 2 + 40:n - 11]])
+        alt[::97] = rng.choice(acgt, len(alt[::97]))
+        pairs.append((ref, alt))
+    for strategy in SC.STRATEGIES:
+        _compare(ctx, pairs, SC.NEW_SW_PARAMETERS, strategy, max_ops=512)
+
+
+def test_resident_repeatable_and_edge_cases(ctx):
+    from lorikeet_b200 import synth
+    ro, refs, ao, alts = synth.sw_pairs(300, first_pair=5000)
+    res = ctx.sw_upload(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, "SoftClip", max_ops=64)
+    ms = res.run()
+    a = res.download()
+    res.run()
+    b = res.download()
+    res.free()
+    assert ms > 0 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    # empty sequences are per-pair errors (the reference asserts), a too-small max_ops is -2
+    ro = np.array([0, 0, 4, 16]); ao = np.array([0, 3, 3, 18])
+    ops, n_ops, offs = ctx.sw_batch(ro, np.frombuffer(b"ACGTACGTACGTAAAA", np.uint8), ao,
+                                    np.frombuffer(b"ACGACGAACGTTTTAAAA", np.uint8), SC.ORIGINAL_DEFAULT, "InDel", max_ops=1)
+    assert list(n_ops) == [-1, -1, -2]
+    import lorikeet_b200 as lk
+    with pytest.raises(lk.LorikeetError):
+        ctx.sw_align(b"", b"ACGT", SC.ORIGINAL_DEFAULT, "SoftClip")

@@ -1,0 +1,24 @@
+"""Developer check: kernel-only GCUPS of the Smith-Waterman path on the cfg#4 generator."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import lorikeet_b200 as lk
+from lorikeet_b200 import synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+ro, refs, ao, alts = synth.sw_pairs(n)
+with lk.Context(0) as ctx:
+    for strategy in ("SoftClip", "InDel"):
+        res = ctx.sw_upload(ro, refs, ao, alts, [200, -150, -260, -11], strategy, max_ops=64)
+        for _ in range(2):
+            res.run()
+        ms = min(res.run() for _ in range(5))
+        print("SW %s pairs=%d cells=%.3e best_ms=%.3f GCUPS=%.1f" % (strategy, n, res.n_cells, ms, res.n_cells / ms / 1e6), flush=True)
+        t = time.time()
+        ctx.sw_batch(ro, refs, ao, alts, [200, -150, -260, -11], strategy, max_ops=64)
+        print("   e2e host call %.1f ms" % ((time.time() - t) * 1e3))
+        res.free()
