@@ -44,13 +44,18 @@ int choose_k(int R, int force_k) {
 }
 
 
-void build_prep(const lk_pairhmm_batch *b, int64_t n_reads, int64_t n_haps, int force_k, bool fast_enabled, HostPrep &P) {
+void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, bool fast_enabled, HostPrep &P) {
+    // Everything produced here is LOCAL to the region range [g0, g1): read / haplotype / region indices and
+    // result offsets start at 0, so a chunk can be staged and run on its own.
+    const int64_t rbase = b->region_read_start[g0], hbase = b->region_hap_start[g0];
+    const int64_t n_reads = b->region_read_start[g1] - rbase, n_haps = b->region_hap_start[g1] - hbase;
+    P = HostPrep();
     P.read_region.resize((size_t)n_reads);
     P.read_out_base.resize((size_t)n_reads);
     P.henc_off.resize((size_t)n_haps);
     int64_t w = 0;
     for (int64_t h = 0; h < n_haps; h++) {
-        const int H = (int)(b->hap_off[h + 1] - b->hap_off[h]);
+        const int H = (int)(b->hap_off[hbase + h + 1] - b->hap_off[hbase + h]);
         P.henc_off[(size_t)h] = w + HENC_PADL;
         w += H + HENC_PADL + HENC_PADR;
         P.h_max = std::max(P.h_max, H);
@@ -59,15 +64,16 @@ void build_prep(const lk_pairhmm_batch *b, int64_t n_reads, int64_t n_haps, int 
     int nk = 0;
     const int *ks = fast_k_values(&nk);
     std::vector<int8_t> read_k((size_t)n_reads, 0);
-    std::vector<int> k_by_len;  // memo
+    std::vector<int> k_by_len;  // memo: read length -> K
+    bool k_present[64] = { false };
     int64_t base = 0;
-    for (int64_t g = 0; g < b->n_regions; g++) {
+    for (int64_t g = g0; g < g1; g++) {
         const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
         const int64_t h0 = b->region_hap_start[g], h1 = b->region_hap_start[g + 1];
         const int64_t A = h1 - h0;
         for (int64_t r = r0; r < r1; r++) {
-            P.read_region[(size_t)r] = (int32_t)g;
-            P.read_out_base[(size_t)r] = base + (r - r0) * A;
+            P.read_region[(size_t)(r - rbase)] = (int32_t)(g - g0);
+            P.read_out_base[(size_t)(r - rbase)] = base + (r - r0) * A;
             const int R = (int)(b->read_off[r + 1] - b->read_off[r]);
             int K = 0;
             if (fast_enabled) {
@@ -75,28 +81,31 @@ void build_prep(const lk_pairhmm_batch *b, int64_t n_reads, int64_t n_haps, int 
                 if (k_by_len[(size_t)R] < 0) k_by_len[(size_t)R] = choose_k(R, force_k);
                 K = k_by_len[(size_t)R];
             }
-            read_k[(size_t)r] = (int8_t)K;
+            read_k[(size_t)(r - rbase)] = (int8_t)K;
+            k_present[K] = true;
             if (K == 0 && fast_enabled)
-                for (int64_t h = h0; h < h1; h++) P.direct.push_back(RescuePair{ (int32_t)r, (int32_t)h });
+                for (int64_t h = h0; h < h1; h++) P.direct.push_back(RescuePair{ (int32_t)(r - rbase), (int32_t)(h - hbase) });
         }
         base += (r1 - r0) * A;
         if (r1 > r0 && h1 > h0) P.n_cells += (b->read_off[r1] - b->read_off[r0]) * (b->hap_off[h1] - b->hap_off[h0]);
     }
     P.n_pairs = base;
     if (!fast_enabled) return;
+    P.groups.reserve((size_t)n_reads);
     // one launch per K; inside a launch tasks follow region order so neighbouring warps share haplotypes
     for (int ki = 0; ki < nk; ki++) {
         const int K = ks[ki];
+        if (!k_present[K]) continue;
         FastLaunch L;
         L.K = K;
         L.first_task = (int32_t)P.tasks.size();
-        for (int64_t g = 0; g < b->n_regions; g++) {
+        for (int64_t g = g0; g < g1; g++) {
             const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
             if (b->region_hap_start[g + 1] == b->region_hap_start[g]) continue;
             int lane = 0;
             WarpTask t{ (int32_t)P.groups.size(), 0 };
             for (int64_t r = r0; r < r1; r++) {
-                if (read_k[(size_t)r] != K) continue;
+                if (read_k[(size_t)(r - rbase)] != K) continue;
                 const int R = (int)(b->read_off[r + 1] - b->read_off[r]);
                 const int G = (R + K - 1) / K;
                 if (lane + G > 32) {
@@ -104,7 +113,7 @@ void build_prep(const lk_pairhmm_batch *b, int64_t n_reads, int64_t n_haps, int 
                     t = WarpTask{ (int32_t)P.groups.size(), 0 };
                     lane = 0;
                 }
-                P.groups.push_back(TaskGroup{ (int32_t)r, (int16_t)lane, (int16_t)G });
+                P.groups.push_back(TaskGroup{ (int32_t)(r - rbase), (int16_t)lane, (int16_t)G });
                 t.n_groups++;
                 lane += G;
             }
@@ -114,6 +123,5 @@ void build_prep(const lk_pairhmm_batch *b, int64_t n_reads, int64_t n_haps, int 
         if (L.n_tasks > 0) P.launches.push_back(L);
     }
 }
-
 
 }  // namespace lk

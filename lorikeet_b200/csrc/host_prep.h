@@ -27,6 +27,7 @@ struct HostPrep {
 
 const int *fast_k_values(int *n);
 int choose_k(int R, int force_k);
-void build_prep(const lk_pairhmm_batch *b, int64_t n_reads, int64_t n_haps, int force_k, bool fast_enabled, HostPrep &P);
+// work lists for the region range [g0, g1) of b, with chunk-local indices
+void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, bool fast_enabled, HostPrep &P);
 
 }  // namespace lk

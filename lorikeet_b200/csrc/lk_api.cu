@@ -111,6 +111,8 @@ extern "C" void lk_destroy(lk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (int i = 0; i < 3; i++)
         if (ctx->stream[i]) { cudaStreamSynchronize(ctx->stream[i]); cudaStreamDestroy(ctx->stream[i]); }
+    for (int i = 0; i < 2; i++)
+        if (ctx->ws[i]) { lk_resident_free(nullptr, ctx->ws[i]); ctx->ws[i] = nullptr; }
     ctx->d_qerr_f.release(); ctx->d_qerr_d.release(); ctx->d_m2m.release();
     delete ctx;
 }
@@ -178,7 +180,7 @@ extern "C" lk_status lk_pairhmm_batch_dims(const lk_pairhmm_batch *b, int64_t *n
 }
 
 // ------------------------------------------------------------------------------------------------
-// PairHMM: resident batches
+// PairHMM: staging a region range into a workspace, launching, collecting
 // ------------------------------------------------------------------------------------------------
 static bool gcp_is_uniform(const uint8_t *gcp, int64_t n, uint8_t *value) {
     if (n == 0) { *value = 10; return true; }
@@ -189,83 +191,126 @@ static bool gcp_is_uniform(const uint8_t *gcp, int64_t n, uint8_t *value) {
     return true;
 }
 
-static lk_status upload_locked(lk_ctx *ctx, const lk_pairhmm_batch *b, lk_resident **out_res) {
-    int64_t n_reads = 0, n_haps = 0;
-    lk_status vs = validate_batch(ctx, b, &n_reads, &n_haps);
-    if (vs != LK_OK) return vs;
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+cudaError_t PinnedBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+}
+void PinnedBuf::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+}
 
-    lk_resident *R = new (std::nothrow) lk_resident();
-    if (!R) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
-    R->kind = 0;
-    R->n_regions = b->n_regions; R->n_reads = n_reads; R->n_haps = n_haps;
-    const int64_t read_bytes = n_reads ? b->read_off[n_reads] : 0;
-    const int64_t hap_bytes = n_haps ? b->hap_off[n_haps] : 0;
-    R->gcp_constant = b->gcp_constant;
-    R->vargcp = false;
-    const uint8_t *gcp_arr = b->read_gcp;
-    if (gcp_arr) {
+struct GcpMode { bool vargcp; uint8_t constant; const uint8_t *array; };
+
+static GcpMode resolve_gcp(const lk_pairhmm_batch *b, int64_t n_reads) {
+    GcpMode m{ false, b->gcp_constant, nullptr };
+    if (b->read_gcp && n_reads > 0) {
         uint8_t v;
-        if (gcp_is_uniform(gcp_arr + (n_reads ? b->read_off[0] : 0), read_bytes - (n_reads ? b->read_off[0] : 0), &v)) {
-            R->gcp_constant = v; gcp_arr = nullptr;
-        } else R->vargcp = true;
+        const int64_t lo = b->read_off[0], hi = b->read_off[n_reads];
+        if (gcp_is_uniform(b->read_gcp + lo, hi - lo, &v)) m.constant = v;
+        else { m.vargcp = true; m.array = b->read_gcp; }
     }
-    HostPrep P;
-    build_prep(b, n_reads, n_haps, ctx->force_k, !ctx->force_f64, P);
+    return m;
+}
+
+// Stage regions [g0, g1) of a validated batch into workspace R: build the work lists, copy the byte arenas and the
+// metadata to the device on stream st.  Asynchronous: returns once the copies are queued (metadata goes through
+// the workspace's pinned arena; `ev_staged` marks the point where that arena may be reused).
+static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0, int64_t g1, const GcpMode &gcp,
+                             lk_resident *R, cudaStream_t st) {
+    cudaError_t e;
+    if (R->ev_staged) {
+        if ((e = cudaEventSynchronize(R->ev_staged)) != cudaSuccess) return lk_cuda_fail(ctx, e, "wait staging");
+    } else if ((e = cudaEventCreateWithFlags(&R->ev_staged, cudaEventDisableTiming)) != cudaSuccess) {
+        return lk_cuda_fail(ctx, e, "event create");
+    }
+    HostPrep &P = R->prep;
+    build_prep(b, g0, g1, ctx->force_k, !ctx->force_f64, P);
+    const int64_t rbase = b->region_read_start[g0], hbase = b->region_hap_start[g0];
+    const int64_t n_reads = b->region_read_start[g1] - rbase, n_haps = b->region_hap_start[g1] - hbase;
+    const int64_t n_regions = g1 - g0;
+    if (P.n_pairs > 0x7fffffffLL) return lk_fail(ctx, LK_ERR_INVALID, "batch too large (2^31 pairs per chunk)");
+    R->kind = 0;
+    R->n_regions = n_regions; R->n_reads = n_reads; R->n_haps = n_haps;
     R->n_pairs = P.n_pairs; R->n_cells = P.n_cells; R->h_max = P.h_max;
     R->launches = P.launches;
-    R->n_direct = ctx->force_f64 ? (int32_t)0 : (int32_t)P.direct.size();
     R->all_f64 = ctx->force_f64;
-    if (P.n_pairs > 0x7fffffffLL) { delete R; return lk_fail(ctx, LK_ERR_INVALID, "batch too large (2^31 pairs)"); }
+    R->n_direct = ctx->force_f64 ? 0 : (int32_t)P.direct.size();
+    R->vargcp = gcp.vargcp; R->gcp_constant = gcp.constant;
+    R->read_byte0 = n_reads ? b->read_off[rbase] : 0;
+    R->hap_byte0 = n_haps ? b->hap_off[hbase] : 0;
+    const int64_t read_bytes = n_reads ? b->read_off[rbase + n_reads] - R->read_byte0 : 0;
+    const int64_t hap_bytes = n_haps ? b->hap_off[hbase + n_haps] - R->hap_byte0 : 0;
 
-    cudaStream_t st = ctx->stream[0];
-#define UP(buf, ptr, n) if ((e = upload(R->buf, ptr, (size_t)(n), st)) != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "upload " #buf); }
-    UP(read_bases, b->read_bases, read_bytes);
-    UP(read_qual, b->read_qual, read_bytes);
-    UP(read_ins, b->read_ins, read_bytes);
-    UP(read_del, b->read_del, read_bytes);
-    if (R->vargcp) { UP(read_gcp, gcp_arr, read_bytes); }
-    UP(read_off, b->read_off, n_reads + 1);
-    UP(read_region, P.read_region.data(), n_reads);
-    UP(read_out_base, P.read_out_base.data(), n_reads);
-    UP(region_hap_start, b->region_hap_start, b->n_regions + 1);
-    UP(hap_off, b->hap_off, n_haps + 1);
-    UP(hap_bases, b->hap_bases, hap_bytes);
-    UP(henc_off, P.henc_off.data(), n_haps);
-    UP(tasks, P.tasks.data(), P.tasks.size());
-    UP(groups, P.groups.data(), P.groups.size());
-#undef UP
-#define RS(buf, bytes) if ((e = R->buf.reserve((size_t)std::max<int64_t>((bytes), 16))) != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "alloc " #buf); }
-    RS(read_flags, n_reads);
-    RS(hap_flags, n_haps);
+    // ---- metadata through the pinned arena ----
+    struct Piece { DevBuf *dst; const void *src; size_t bytes; };
+    std::vector<int64_t> local_rhs((size_t)n_regions + 1);
+    for (int64_t g = 0; g <= n_regions; g++) local_rhs[(size_t)g] = b->region_hap_start[g0 + g] - hbase;
+    const Piece pieces[] = {
+        { &R->read_off, b->read_off + rbase, (size_t)(n_reads + 1) * 8 },
+        { &R->read_region, P.read_region.data(), (size_t)n_reads * 4 },
+        { &R->read_out_base, P.read_out_base.data(), (size_t)n_reads * 8 },
+        { &R->region_hap_start, local_rhs.data(), (size_t)(n_regions + 1) * 8 },
+        { &R->hap_off, b->hap_off + hbase, (size_t)(n_haps + 1) * 8 },
+        { &R->henc_off, P.henc_off.data(), (size_t)n_haps * 8 },
+        { &R->tasks, P.tasks.data(), P.tasks.size() * sizeof(WarpTask) },
+        { &R->groups, P.groups.data(), P.groups.size() * sizeof(TaskGroup) },
+        { &R->rescue_pairs, P.direct.data(), (size_t)R->n_direct * sizeof(RescuePair) },
+    };
+    size_t total = 0;
+    for (const Piece &pc : pieces) total += (pc.bytes + 255) & ~(size_t)255;
+    if ((e = R->pinned.reserve(total + 256)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pinned staging");
+    // device buffers (grow-only; reused across calls)
+#define RS(buf, bytes) if ((e = R->buf.reserve((size_t)std::max<int64_t>((int64_t)(bytes), 16))) != cudaSuccess) return lk_cuda_fail(ctx, e, "alloc " #buf);
+    RS(read_bases, read_bytes); RS(read_qual, read_bytes); RS(read_ins, read_bytes); RS(read_del, read_bytes);
+    if (gcp.vargcp) { RS(read_gcp, read_bytes); }
+    RS(hap_bases, hap_bytes);
+    RS(read_flags, n_reads); RS(hap_flags, n_haps);
     RS(henc, P.henc_words * 4);
-    RS(out, P.n_pairs * 8);
-    RS(flags, P.n_pairs);
+    RS(out, P.n_pairs * 8); RS(flags, P.n_pairs);
     RS(counters, 64);
-    RS(rescue_pairs, P.n_pairs * (int64_t)sizeof(RescuePair));
+    RS(rescue_pairs, std::max<int64_t>(P.n_pairs, 1) * (int64_t)sizeof(RescuePair));
     R->plain_blocks = ctx->n_sm * 2;
     R->scratch_stride = 6 * ((int64_t)P.h_max + 1);
     RS(scratch, (int64_t)R->plain_blocks * (LK_PLAIN_THREADS / 32) * R->scratch_stride * 8);
-#undef RS
-    if (!P.direct.empty() && !ctx->force_f64) {
-        e = cudaMemcpyAsync(R->rescue_pairs.p, P.direct.data(), P.direct.size() * sizeof(RescuePair), cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "upload direct pairs"); }
+    size_t off = 0;
+    for (const Piece &pc : pieces) {
+        if (pc.dst != &R->rescue_pairs && (e = pc.dst->reserve(std::max<size_t>(pc.bytes, 16))) != cudaSuccess)
+            return lk_cuda_fail(ctx, e, "alloc metadata");
+        if (pc.bytes) {
+            memcpy((char *)R->pinned.p + off, pc.src, pc.bytes);
+            if ((e = cudaMemcpyAsync(pc.dst->p, (char *)R->pinned.p + off, pc.bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+                return lk_cuda_fail(ctx, e, "metadata H2D");
+        }
+        off += (pc.bytes + 255) & ~(size_t)255;
     }
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "upload sync"); }
-    *out_res = R;
+#undef RS
+    if ((e = cudaEventRecord(R->ev_staged, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "event record");
+    // ---- byte arenas straight from the caller's memory ----
+#define CP(buf, src) if (read_bytes && (e = cudaMemcpyAsync(R->buf.p, (src) + R->read_byte0, (size_t)read_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "H2D " #buf);
+    CP(read_bases, b->read_bases); CP(read_qual, b->read_qual); CP(read_ins, b->read_ins); CP(read_del, b->read_del);
+    if (gcp.vargcp) { CP(read_gcp, gcp.array); }
+#undef CP
+    if (hap_bytes && (e = cudaMemcpyAsync(R->hap_bases.p, b->hap_bases + R->hap_byte0, (size_t)hap_bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return lk_cuda_fail(ctx, e, "H2D hap_bases");
     return LK_OK;
 }
 
 static void fill_args(lk_ctx *ctx, lk_resident *R, PairHmmArgs &A) {
     memset(&A, 0, sizeof A);
-    A.read_bases = (const uint8_t *)R->read_bases.p; A.read_qual = (const uint8_t *)R->read_qual.p;
-    A.read_ins = (const uint8_t *)R->read_ins.p; A.read_del = (const uint8_t *)R->read_del.p;
-    A.read_gcp = R->vargcp ? (const uint8_t *)R->read_gcp.p : nullptr;
+    // arenas are indexed with the caller's absolute byte offsets: bias the base pointers instead of rebasing offsets
+    A.read_bases = (const uint8_t *)R->read_bases.p - R->read_byte0; A.read_qual = (const uint8_t *)R->read_qual.p - R->read_byte0;
+    A.read_ins = (const uint8_t *)R->read_ins.p - R->read_byte0; A.read_del = (const uint8_t *)R->read_del.p - R->read_byte0;
+    A.read_gcp = R->vargcp ? (const uint8_t *)R->read_gcp.p - R->read_byte0 : nullptr;
     A.read_off = (const int64_t *)R->read_off.p; A.read_region = (const int32_t *)R->read_region.p;
     A.read_out_base = (const int64_t *)R->read_out_base.p; A.read_flags = (const uint8_t *)R->read_flags.p;
     A.region_hap_start = (const int64_t *)R->region_hap_start.p; A.hap_off = (const int64_t *)R->hap_off.p;
-    A.hap_bases = (const uint8_t *)R->hap_bases.p; A.henc = (const uint32_t *)R->henc.p;
+    A.hap_bases = (const uint8_t *)R->hap_bases.p - R->hap_byte0; A.henc = (const uint32_t *)R->henc.p;
     A.henc_off = (const int64_t *)R->henc_off.p; A.hap_flags = (const uint8_t *)R->hap_flags.p;
     A.qerr_f = (const float *)ctx->d_qerr_f.p; A.qerr_d = (const double *)ctx->d_qerr_d.p; A.m2m = (const double *)ctx->d_m2m.p;
     A.groups = (const TaskGroup *)R->groups.p;
@@ -275,6 +320,41 @@ static void fill_args(lk_ctx *ctx, lk_resident *R, PairHmmArgs &A) {
     A.scratch = (double *)R->scratch.p; A.scratch_stride = R->scratch_stride;
     A.gcp_constant = R->gcp_constant;
     A.mismatch_div = ctx->tristate ? 3.0f : 1.0f;
+}
+
+// Queue every kernel of one staged workspace on st (no synchronisation).
+static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, bool timed) {
+    cudaError_t e;
+    PairHmmArgs A;
+    fill_args(ctx, R, A);
+    R->counter_init[0] = R->all_f64 ? (int32_t)R->n_pairs : R->n_direct;
+    R->counter_init[1] = 0;
+    if ((e = cudaMemcpyAsync(R->counters.p, R->counter_init, 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return lk_cuda_fail(ctx, e, "reset counters");
+    R->launch_count = 0;
+    if (R->n_pairs == 0) return LK_OK;
+    if (R->all_f64) {
+        if ((e = launch_list_all_pairs(A, R->n_reads, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "list_all_pairs");
+        R->launch_count++;
+    } else {
+        if ((e = launch_encode_haps(A.hap_bases, A.hap_off, A.henc_off, R->n_haps, (uint32_t *)R->henc.p, (uint8_t *)R->hap_flags.p, st)) != cudaSuccess)
+            return lk_cuda_fail(ctx, e, "encode_haps");
+        if ((e = launch_scan_reads(A.read_bases, A.read_qual, A.read_ins, A.read_off, R->n_reads, (uint8_t *)R->read_flags.p, st)) != cudaSuccess)
+            return lk_cuda_fail(ctx, e, "scan_reads");
+        R->launch_count += 2;
+        if (timed) { cudaEventCreate(&R->ev_fast0); cudaEventCreate(&R->ev_fast1); cudaEventRecord(R->ev_fast0, st); }
+        for (const auto &L : R->launches) {
+            PairHmmArgs AL = A;
+            AL.tasks = (const WarpTask *)R->tasks.p + L.first_task;
+            AL.n_tasks = L.n_tasks;
+            if ((e = launch_fast(L.K, AL, R->vargcp, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_fast");
+            R->launch_count++;
+        }
+        if (timed) cudaEventRecord(R->ev_fast1, st);
+    }
+    if ((e = launch_plain(A, R->plain_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_plain");
+    R->launch_count++;
+    return LK_OK;
 }
 
 static lk_status run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
@@ -287,36 +367,7 @@ static lk_status run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, st);
     }
-    PairHmmArgs A;
-    fill_args(ctx, R, A);
-    R->counter_init[0] = R->all_f64 ? (int32_t)R->n_pairs : R->n_direct;
-    R->counter_init[1] = 0;
-    e = cudaMemcpyAsync(R->counters.p, R->counter_init, 8, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "reset counters");
-    R->launch_count = 0;
-    if (R->n_pairs > 0) {
-        if (R->all_f64) {
-            if ((e = launch_list_all_pairs(A, R->n_reads, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "list_all_pairs");
-            R->launch_count++;
-        } else {
-            if ((e = launch_encode_haps(A.hap_bases, A.hap_off, A.henc_off, R->n_haps, (uint32_t *)R->henc.p, (uint8_t *)R->hap_flags.p, st)) != cudaSuccess)
-                return lk_cuda_fail(ctx, e, "encode_haps");
-            if ((e = launch_scan_reads(A.read_bases, A.read_qual, A.read_ins, A.read_off, R->n_reads, (uint8_t *)R->read_flags.p, st)) != cudaSuccess)
-                return lk_cuda_fail(ctx, e, "scan_reads");
-            R->launch_count += 2;
-            if (kernel_ms) { cudaEventCreate(&R->ev_fast0); cudaEventCreate(&R->ev_fast1); cudaEventRecord(R->ev_fast0, st); }
-            for (const auto &L : R->launches) {
-                PairHmmArgs AL = A;
-                AL.tasks = (const WarpTask *)R->tasks.p + L.first_task;
-                AL.n_tasks = L.n_tasks;
-                if ((e = launch_fast(L.K, AL, R->vargcp, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_fast");
-                R->launch_count++;
-            }
-            if (kernel_ms) cudaEventRecord(R->ev_fast1, st);
-        }
-        if ((e = launch_plain(A, R->plain_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_plain");
-        R->launch_count++;
-    }
+    lk_status ls = enqueue_kernels(ctx, R, st, kernel_ms != nullptr);
     if (kernel_ms) cudaEventRecord(ev1, st);
     e = cudaStreamSynchronize(st);
     if (kernel_ms) {
@@ -329,6 +380,7 @@ static lk_status run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
             R->ev_fast0 = R->ev_fast1 = nullptr;
         }
     }
+    if (ls != LK_OK) return ls;
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm kernels");
     return LK_OK;
 }
@@ -351,7 +403,19 @@ extern "C" lk_status lk_pairhmm_upload(lk_ctx *ctx, const lk_pairhmm_batch *batc
     if (!ctx || !out_res) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
     *out_res = nullptr;
-    return upload_locked(ctx, batch, out_res);
+    int64_t n_reads = 0, n_haps = 0;
+    lk_status vs = validate_batch(ctx, batch, &n_reads, &n_haps);
+    if (vs != LK_OK) return vs;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    lk_resident *R = new (std::nothrow) lk_resident();
+    if (!R) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    const GcpMode gcp = resolve_gcp(batch, n_reads);
+    lk_status st = stage_range(ctx, batch, 0, batch->n_regions, gcp, R, ctx->stream[0]);
+    if (st == LK_OK && (e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess) st = lk_cuda_fail(ctx, e, "upload sync");
+    if (st != LK_OK) { lk_resident_free(ctx, R); return st; }
+    *out_res = R;
+    return LK_OK;
 }
 
 extern "C" lk_status lk_pairhmm_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms) {
@@ -366,9 +430,7 @@ extern "C" lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *
     return download_locked(ctx, res, out, flags);
 }
 
-extern "C" void lk_resident_free(lk_ctx *ctx, lk_resident *R) {
-    if (!R) return;
-    if (ctx) cudaSetDevice(ctx->device);
+static void release_buffers(lk_resident *R) {
     DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
                        &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
                        &R->hap_bases, &R->henc, &R->henc_off, &R->hap_flags, &R->tasks, &R->groups, &R->out,
@@ -376,19 +438,74 @@ extern "C" void lk_resident_free(lk_ctx *ctx, lk_resident *R) {
                        &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,
                        &R->sw_ops, &R->sw_nops, &R->sw_offsets, &R->sw_order };
     for (DevBuf *b : bufs) b->release();
+    R->pinned.release();
+    if (R->ev_staged) { cudaEventDestroy(R->ev_staged); R->ev_staged = nullptr; }
+}
+
+extern "C" void lk_resident_free(lk_ctx *ctx, lk_resident *R) {
+    if (!R) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    release_buffers(R);
     delete R;
 }
 
+// Host-buffer entry point: regions are cut into chunks that flow through two workspaces / two streams, so the
+// H2D copy and task building of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
 extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags) {
     if (!ctx) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
-    lk_resident *R = nullptr;
-    lk_status st = upload_locked(ctx, batch, &R);
-    if (st != LK_OK) return st;
-    st = run_locked(ctx, R, nullptr);
-    if (st == LK_OK) st = download_locked(ctx, R, out, flags);
-    ctx->last_launch_count = R->launch_count;
-    lk_resident_free(ctx, R);
+    int64_t n_reads = 0, n_haps = 0;
+    lk_status vs = validate_batch(ctx, batch, &n_reads, &n_haps);
+    if (vs != LK_OK) return vs;
+    int64_t n_pairs = 0;
+    for (int64_t r = 0; r < batch->n_regions; r++)
+        n_pairs += (batch->region_read_start[r + 1] - batch->region_read_start[r]) * (batch->region_hap_start[r + 1] - batch->region_hap_start[r]);
+    if (n_pairs == 0) { ctx->last_launch_count = 0; return LK_OK; }
+    if (!out) return lk_fail(ctx, LK_ERR_INVALID, "null out");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    const GcpMode gcp = resolve_gcp(batch, n_reads);
+    // chunk boundaries: ~equal pair counts, at most 8 chunks, at least ~1M pairs each
+    int n_chunks = (int)std::min<int64_t>(8, std::max<int64_t>(1, n_pairs / (1 << 20)));
+    n_chunks = (int)std::min<int64_t>(n_chunks, batch->n_regions);
+    std::vector<int64_t> cut(1, 0), pair_base(1, 0);
+    {
+        int64_t acc = 0, next = 1;
+        for (int64_t r = 0; r < batch->n_regions; r++) {
+            acc += (batch->region_read_start[r + 1] - batch->region_read_start[r]) * (batch->region_hap_start[r + 1] - batch->region_hap_start[r]);
+            if (r + 1 == batch->n_regions || (next < n_chunks && acc >= n_pairs * next / n_chunks)) {
+                cut.push_back(r + 1); pair_base.push_back(acc); next++;
+            }
+        }
+    }
+    const int C = (int)cut.size() - 1;
+    for (int i = 0; i < 2; i++)
+        if (!ctx->ws[i]) { ctx->ws[i] = new (std::nothrow) lk_resident(); if (!ctx->ws[i]) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"); }
+    lk_status st = LK_OK;
+    int32_t launches = 0;
+    auto collect = [&](int i) -> lk_status {  // D2H of chunk i (queued behind its kernels on the same stream)
+        lk_resident *R = ctx->ws[i & 1];
+        cudaStream_t s = ctx->stream[i & 1];
+        if (R->n_pairs == 0) return LK_OK;
+        cudaError_t ce = cudaMemcpyAsync(out + pair_base[(size_t)i], R->out.p, (size_t)R->n_pairs * 8, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && flags) ce = cudaMemcpyAsync(flags + pair_base[(size_t)i], R->flags.p, (size_t)R->n_pairs, cudaMemcpyDeviceToHost, s);
+        if (ce != cudaSuccess) return lk_cuda_fail(ctx, ce, "D2H");
+        return LK_OK;
+    };
+    for (int i = 0; i < C && st == LK_OK; i++) {
+        lk_resident *R = ctx->ws[i & 1];
+        cudaStream_t s = ctx->stream[i & 1];
+        st = stage_range(ctx, batch, cut[(size_t)i], cut[(size_t)i + 1], gcp, R, s);
+        if (st == LK_OK) st = enqueue_kernels(ctx, R, s, false);
+        launches += R->launch_count;
+        if (st == LK_OK && i >= 1) st = collect(i - 1);  // may block on a pageable destination: chunk i is already queued
+    }
+    if (st == LK_OK) st = collect(C - 1);
+    for (int i = 0; i < 2; i++) {
+        e = cudaStreamSynchronize(ctx->stream[i]);
+        if (e != cudaSuccess && st == LK_OK) st = lk_cuda_fail(ctx, e, "pairhmm pipeline");
+    }
+    ctx->last_launch_count = launches;
     return st;
 }
 

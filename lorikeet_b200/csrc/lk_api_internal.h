@@ -17,6 +17,15 @@ struct DevBuf {
     void release();
 };
 
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes);
+    void release();
+};
+
+struct lk_resident;
+
 struct lk_ctx {
     int device = 0;
     int n_sm = 148;
@@ -28,6 +37,7 @@ struct lk_ctx {
     int force_k = 0;
     int32_t last_launch_count = 0;
     DevBuf d_qerr_f, d_qerr_d, d_m2m;
+    lk_resident *ws[2] = { nullptr, nullptr };  // reusable workspaces of lk_pairhmm_batch_host's chunk pipeline
 };
 
 struct lk_resident {
@@ -45,6 +55,10 @@ struct lk_resident {
     float last_fast_ms = 0.f;
     cudaEvent_t ev_fast0 = nullptr, ev_fast1 = nullptr;
     std::vector<lk::FastLaunch> launches;
+    lk::HostPrep prep;
+    PinnedBuf pinned;                 // metadata staging (so its H2D copies are truly asynchronous)
+    cudaEvent_t ev_staged = nullptr;  // pinned arena may be rewritten once this has fired
+    int64_t read_byte0 = 0, hap_byte0 = 0;  // first arena byte staged: device pointers are biased by these
     DevBuf read_bases, read_qual, read_ins, read_del, read_gcp, read_off, read_region, read_out_base, read_flags;
     DevBuf region_hap_start, hap_off, hap_bases, henc, henc_off, hap_flags;
     DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch;

@@ -94,7 +94,7 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
                                   double *out, uint8_t *flags, int32_t *n_rescued) {
     const int64_t n_reads = b->region_read_start[b->n_regions], n_haps = b->region_hap_start[b->n_regions];
     HostPrep P;
-    build_prep(b, n_reads, n_haps, force_k, !force_f64, P);
+    build_prep(b, 0, b->n_regions, force_k, !force_f64, P);
     ModelTables T;
     build_model_tables(T);
     std::vector<uint32_t> henc((size_t)P.henc_words, 0u);

@@ -196,3 +196,22 @@ def test_invalid_inputs_are_rejected(ctx):
     empty = _batch(dict(region_read_start=np.array([0]), region_hap_start=np.array([0]), read_off=np.array([0]),
                         hap_off=np.array([0]), read_bases=b"", read_qual=b"", read_ins=b"", read_del=b"", hap_bases=b""))
     assert ctx.pairhmm_batch(empty).shape == (0,)
+
+
+def test_chunked_host_pipeline_matches_resident(ctx):
+    # > 2M pairs: lk_pairhmm_batch_host cuts the batch into chunks over two streams; the result must equal the
+    # single-workspace resident path bit for bit, and the oracle on a sample of regions
+    from lorikeet_b200 import synth
+    b = synth.pairhmm_regions(2200, first_region=20000)
+    host, hflags = ctx.pairhmm_batch(b, want_flags=True)
+    res = ctx.pairhmm_upload(b)
+    res.run()
+    dev, dflags = res.download(want_flags=True)
+    res.free()
+    assert np.array_equal(host, dev) and np.array_equal(hflags, dflags)
+    for g in (0, 1099, 2199):
+        exp = O.pairhmm_batch(b.region_slice(g, g + 1))
+        assert np.max(rel_err(host[g * 1024:(g + 1) * 1024], exp)) < REL_TOL
+    # a second call reuses the context's workspaces
+    again = ctx.pairhmm_batch(b)
+    assert np.array_equal(again, host)
