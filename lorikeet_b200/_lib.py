@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "liblorikeet_b200.so")
+SO_PATH = os.environ.get("LK_SO") or os.path.join(HERE, "liblorikeet_b200.so")  # LK_SO: developer override (kernel variants)
 
 u8p = C.POINTER(C.c_uint8)
 i32p = C.POINTER(C.c_int32)

@@ -60,11 +60,16 @@ class Context:
         return v.value
 
     # ---------------------------------------------------------------- PairHMM
-    def pairhmm_batch(self, batch, want_flags=False):
-        """lk_pairhmm_batch_host: host arrays in, log10 likelihoods out (layout r*A + h per region)."""
+    def pairhmm_batch(self, batch, want_flags=False, out=None, flags=None):
+        """lk_pairhmm_batch_host: host arrays in, log10 likelihoods out (layout r*A + h per region).
+        `out` / `flags` may be preallocated (e.g. pinned) float64 / uint8 arrays of n_pairs entries."""
         n = batch.n_pairs
-        out = np.empty(n, dtype=np.float64)
-        flags = np.zeros(n, dtype=np.uint8)
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        if flags is None:
+            flags = np.zeros(n, dtype=np.uint8)
+        assert out.dtype == np.float64 and out.size >= n and out.flags.c_contiguous
+        assert flags.dtype == np.uint8 and flags.size >= n and flags.flags.c_contiguous
         s = batch.as_struct()
         self._check(self._L.lk_pairhmm_batch_host(self._h, C.byref(s), out.ctypes.data_as(_lib.f64p),
                                                   flags.ctypes.data_as(_lib.u8p)))

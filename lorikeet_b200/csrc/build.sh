@@ -2,25 +2,26 @@
 # Build liblorikeet_b200.so in-tree for sm_100a (cross-compiles without a GPU).
 set -e
 cd "$(dirname "$0")"
-OUT=../liblorikeet_b200.so
+OUT=${LK_OUT:-../liblorikeet_b200.so}
+BUILD=${LK_BUILD_DIR:-../_build}
 NVCC=${NVCC:-nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function"
-mkdir -p ../_build
+FLAGS="${LK_EXTRA_FLAGS} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function"
+mkdir -p $BUILD
 pids=()
 for f in pairhmm_kernels.cu sw_kernels.cu lk_api.cu lk_sw_api.cu tools_kernels.cu; do
   [ -f "$f" ] || continue
-  o=../_build/${f%.cu}.o
+  o=$BUILD/${f%.cu}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$o" -print -quit)" ] || [ ../../include/lorikeet_b200.h -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" & pids+=($!)
   fi
 done
 for f in host_model.cpp host_prep.cpp host_engine.cpp host_synth.cpp; do
   [ -f "$f" ] || continue
-  o=../_build/${f%.cpp}.o
+  o=$BUILD/${f%.cpp}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 -name '*.h' -newer "$o" -print -quit)" ] || [ ../../include/lorikeet_b200.h -nt "$o" ]; then
     g++ -O3 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c "$f" -o "$o" & pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT ../_build/*.o -Xcompiler -fPIC -lcudart_static -lpthread -ldl -lrt
+$NVCC -shared -o $OUT $BUILD/*.o -Xcompiler -fPIC -lcudart_static -lpthread -ldl -lrt
 echo "built $OUT"

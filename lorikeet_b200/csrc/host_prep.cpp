@@ -18,7 +18,8 @@ const int *fast_k_values(int *n) {
 // Pick rows-per-lane for a read of length R: maximise useful cell-updates per issue slot.
 //   lanes per read G = ceil(R/K); reads per warp p = floor(32/G);
 //   row efficiency = p*R / (32*K); skew efficiency ~ H/(H+G-1) with H ~ 2R;
-//   issue slots per cell ~ 8 + 9/K; a mild penalty for the lower occupancy of the big-K variants.
+//   issue slots per cell ~ 7 + 10/K; a mild penalty for the lower occupancy of the big-K variants
+//   (measured on B200 for R = 150: K = 10 / 15 / 19 within 4 % of each other, profiles/).
 int choose_k(int R, int force_k) {
     int n = 0;
     const int *ks = fast_k_values(&n);
@@ -36,8 +37,8 @@ int choose_k(int R, int force_k) {
         const double row_eff = (double)(p * R) / (32.0 * K);
         const double H = std::max(2.0 * R, 64.0);
         const double skew = H / (H + G - 1);
-        const double occ = K <= 10 ? 1.0 : (K <= 12 ? 0.97 : 0.93);
-        const double score = row_eff * skew * occ / (8.0 + 9.0 / K);
+        const double occ = K <= 10 ? 1.0 : (K <= 15 ? 0.97 : 0.95);
+        const double score = row_eff * skew * occ / (7.0 + 10.0 / K);
         if (score > best) { best = score; best_k = K; }
     }
     return best_k;  // 0: too long for the fast path
@@ -92,7 +93,9 @@ void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, 
     P.n_pairs = base;
     if (!fast_enabled) return;
     P.groups.reserve((size_t)n_reads);
-    // one launch per K; inside a launch tasks follow region order so neighbouring warps share haplotypes
+    // one launch per K; inside a launch tasks follow region order so neighbouring warps share haplotypes.
+    // Reads of a region (same K) are packed longest first so that lanes of a warp finish together.
+    std::vector<int64_t> bucket;
     for (int ki = 0; ki < nk; ki++) {
         const int K = ks[ki];
         if (!k_present[K]) continue;
@@ -102,18 +105,23 @@ void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, 
         for (int64_t g = g0; g < g1; g++) {
             const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
             if (b->region_hap_start[g + 1] == b->region_hap_start[g]) continue;
+            bucket.clear();
+            for (int64_t r = r0; r < r1; r++)
+                if (read_k[(size_t)(r - rbase)] == K) bucket.push_back(r);
+            if (bucket.empty()) continue;
+            auto len = [&](int64_t r) { return (int)(b->read_off[r + 1] - b->read_off[r]); };
+            std::stable_sort(bucket.begin(), bucket.end(), [&](int64_t x, int64_t y) { return len(x) > len(y); });
             int lane = 0;
             WarpTask t{ (int32_t)P.groups.size(), 0 };
-            for (int64_t r = r0; r < r1; r++) {
-                if (read_k[(size_t)(r - rbase)] != K) continue;
-                const int R = (int)(b->read_off[r + 1] - b->read_off[r]);
-                const int G = (R + K - 1) / K;
+            for (size_t i = 0; i < bucket.size(); i++) {
+                const int64_t rx = bucket[i];
+                const int G = (len(rx) + K - 1) / K;
                 if (lane + G > 32) {
                     P.tasks.push_back(t);
                     t = WarpTask{ (int32_t)P.groups.size(), 0 };
                     lane = 0;
                 }
-                P.groups.push_back(TaskGroup{ (int32_t)(r - rbase), (int16_t)lane, (int16_t)G });
+                P.groups.push_back(TaskGroup{ (int32_t)(rx - rbase), (int16_t)lane, (int16_t)G });
                 t.n_groups++;
                 lane += G;
             }

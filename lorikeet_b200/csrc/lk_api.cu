@@ -339,7 +339,7 @@ static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, b
     } else {
         if ((e = launch_encode_haps(A.hap_bases, A.hap_off, A.henc_off, R->n_haps, (uint32_t *)R->henc.p, (uint8_t *)R->hap_flags.p, st)) != cudaSuccess)
             return lk_cuda_fail(ctx, e, "encode_haps");
-        if ((e = launch_scan_reads(A.read_bases, A.read_qual, A.read_ins, A.read_off, R->n_reads, (uint8_t *)R->read_flags.p, st)) != cudaSuccess)
+        if ((e = launch_scan_reads(A.read_bases, A.read_qual, A.read_ins, A.read_del, A.read_off, R->n_reads, (uint8_t *)R->read_flags.p, st)) != cudaSuccess)
             return lk_cuda_fail(ctx, e, "scan_reads");
         R->launch_count += 2;
         if (timed) { cudaEventCreate(&R->ev_fast0); cudaEventCreate(&R->ev_fast1); cudaEventRecord(R->ev_fast0, st); }

@@ -8,9 +8,8 @@
 // Rows per lane (K) the fp32 fast kernel is instantiated for, with the launch-bounds
 // "min blocks per SM" that sets its register budget (128 threads/block: 4 -> 128 regs, 3 -> 168,
 // 2 -> 255).  The host picks K per read from this list (host_prep.cpp: choose_k).
-#define LK_FAST_K_TABLE(X) X(4, 4) X(6, 4) X(8, 4) X(10, 4) X(12, 3) X(14, 2) X(16, 2) X(19, 2) X(20, 2)
-#define LK_FAST_KS 4, 6, 8, 10, 12, 14, 16, 19, 20
-
+#define LK_FAST_K_TABLE(X) X(4, 4) X(6, 4) X(8, 4) X(10, 4) X(12, 3) X(14, 3) X(15, 3) X(16, 2) X(19, 2) X(20, 2)
+#define LK_FAST_KS 4, 6, 8, 10, 12, 14, 15, 16, 19, 20
 // Smith-Waterman: rows per lane (K) variants; a pair with n reference rows uses the smallest K with 32*K >= n,
 // longer references are processed in bands of 32*17 rows.
 #define LK_SW_THREADS 128

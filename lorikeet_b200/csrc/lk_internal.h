@@ -13,7 +13,7 @@ struct SwArgs;
 cudaError_t launch_encode_haps(const uint8_t *hap_bases, const int64_t *hap_off, const int64_t *henc_off,
                                int64_t n_haps, uint32_t *henc, uint8_t *hap_flags, cudaStream_t st);
 cudaError_t launch_scan_reads(const uint8_t *read_bases, const uint8_t *read_qual, const uint8_t *read_ins,
-                              const int64_t *read_off, int64_t n_reads, uint8_t *read_flags, cudaStream_t st);
+                              const uint8_t *read_del, const int64_t *read_off, int64_t n_reads, uint8_t *read_flags, cudaStream_t st);
 cudaError_t launch_list_all_pairs(const PairHmmArgs &A, int64_t n_reads, cudaStream_t st);
 cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t st);
 cudaError_t launch_plain(const PairHmmArgs &A, int n_blocks, cudaStream_t st);

@@ -10,10 +10,10 @@
 //     strip's last row (M, I, D) to the next lane with one __shfl_up_sync per value;
 //   * per-row constants (transition x prior products) are built once per read and reused for every
 //     haplotype of the region;
-//   * "hat form" (fp32 fast path): I^ = I / tMI[i], D^ = D / tMD[i] turn the I and D updates into one
-//     FMA each and the match prior is folded into the row constants, so a cell costs 8 issue slots
-//     (3 for the M sum, compare, select, scale, I^, D^) for the 12 flops the reference spends
-//     (pair_hmm.rs:575-591);
+//   * "scaled hat form" (fp32 fast path): I^ = I / tMI[i], D^ = D / tMD[i] turn the I and D updates into
+//     one FMA each, the match prior is folded into the row constants and each row's state carries the
+//     next row's match->match factor, so a cell costs 7 issue slots (compare, select, FMUL, 4 FFMA)
+//     for the 12 flops the reference spends (pair_hmm.rs:575-591);
 //   * "plain form" (f64 pass): the reference's own operation order, initial condition 2^1020,
 //     un-fused multiplies/adds, any read / haplotype length (row bands with power-of-two
 //     renormalisation between bands).
@@ -66,7 +66,7 @@ enum : uint8_t { SEQ_EXOTIC = 1, SEQ_QUAL_DOMAIN = 2 };
 enum : uint8_t { PAIR_RESCUED = 1, PAIR_NEG_INF = 2 };
 
 struct TaskGroup {       // one read inside a warp task
-    int32_t read;        // batch-global read index
+    int32_t read;        // read index (local to the staged chunk)
     int16_t lane_start;  // first lane of the group
     int16_t lanes;       // ceil(R / K)
 };
@@ -123,6 +123,27 @@ LK_DEV int lk_popc(unsigned v) {
 #endif
 }
 
+
+#ifndef LK_FAST_UNROLL
+#define LK_FAST_UNROLL 8
+#endif
+#define LK_PRAGMA_(x) _Pragma(#x)
+#define LK_PRAGMA(x) LK_PRAGMA_(x)
+#define LK_UNROLL_N(n) LK_PRAGMA(unroll n)
+
+// M' = mm * (match ? s : s*r).  Default: compare -> select -> FMUL (LOP3 + FSEL on the half-rate ALU pipe).
+// LK_PRED_FMUL: compare -> FMUL -> predicated FMUL, which moves the select onto the full-rate FMA pipe.
+LK_DEV float prior_scale(float mm, uint32_t match_bits, float s_match, float s_mismatch) {
+#if defined(__CUDA_ARCH__) && defined(LK_PRED_FMUL)
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmul.f32 %0, %1, %4;\n\t@p mul.f32 %0, %1, %3;\n\t}"
+        : "=&f"(r) : "f"(mm), "r"(match_bits), "f"(s_match), "f"(s_mismatch));
+    return r;
+#else
+    return mm * ((match_bits != 0u) ? s_match : s_mismatch);
+#endif
+}
+
 // match->match, pair_hmm_model.rs:442-461 (table) — quals are bytes so max <= 255; 255 > MAX_QUAL uses
 // the closed form of :453-458 which the host folded into row 255 of the table.
 LK_DEV double m2m_lookup(const double *m2m, int ins, int del) {
@@ -154,28 +175,46 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
     const int R = (int)(A.read_off[read + 1] - ro);
     const uint8_t rflag = A.read_flags[read];
 
-    // ---- per-row constants (hat form), built in f64 and rounded once -------------------------
-    float ca[K], cb[K], cc[K], ce[K], cr[K];
+    // ---- per-row constants (scaled hat form), built in f64 and rounded once --------------------
+    // True recurrences in hat variables (I^ = I/tMI[i], D^ = D/tMD[i], prior folded in, a = pm*tMM, b = pm*tGM*tMI[i-1],
+    // c = pm*tGM*tMD[i-1], e = tII*tMI[i-1]/tMI[i], r = px/pm):
+    //     mm[i]  = a[i] M[i-1] + b[i] I^[i-1] + c[i] D^[i-1]      (previous column)
+    //     M[i]   = mm[i] * (match ? 1 : r[i])
+    //     D^[i]  = f D^[i] + M[i]                                  (previous column)
+    //     I^[i]  = e[i] I^[i-1] + M[i-1]                           (same column)
+    // Row i's state is additionally stored scaled: M' = s[i] M, D' = s[i] D^ with s[i] = a~[i+1], and I' = a~[i] I^
+    // (a~ = a for real rows >= 2, 1 for row 1 and for padding rows).  With that choice the M[i-1] term of mm and of
+    // I^ has coefficient 1 and is absorbed as an FMA addend:
+    //     mm    = fma(D'[i-1], c', fma(I'[i-1], b', M'[i-1]))      b' = b/a~[i-1], c' = c/a~[i]
+    //     M'[i] = mm * (match ? s[i] : s[i] r[i])
+    //     D'[i] = fma(D'[i], f, M'[i]),   I'[i] = fma(I'[i-1], e', M'[i-1]),   e' = a~[i] e / a~[i-1]
+    // i.e. 7 issue slots per cell: compare (LOP3 -> predicate), select, FMUL, 4 FFMA.
+    float cb[K], cc[K], ce[K], cs[K], csr[K];
     float cf[VARGCP ? K : 1];
     uint32_t rm[(K + 3) / 4];
 #pragma unroll
     for (int i = 0; i < (K + 3) / 4; i++) rm[i] = 0u;
     float kcoef = 0.f, wM = 0.f, wI = 0.f;
     if (!VARGCP) cf[0] = A.qerr_f[A.gcp_constant];
+    // a~ of a 0-based read position: pm*tMM for real rows >= 1, else 1
+    auto a_tilde = [&](int i) -> double {
+        if (i < 1 || i >= R) return 1.0;
+        return (1.0 - A.qerr_d[A.read_qual[ro + i]]) * m2m_lookup(A.m2m, A.read_ins[ro + i], A.read_del[ro + i]);
+    };
 #pragma unroll
     for (int k = 0; k < K; k++) {
         const int i = lig * K + k;  // 0-based read position of this row
-        float a = 0.f, b = 0.f, c = 0.f, e = (i > R) ? 1.f : 0.f, r = 1.f, f = 1.f;
+        float b = 0.f, c = 0.f, e = (i > R) ? 1.f : 0.f, sm = 0.f, sx = 0.f, f = 1.f;
         uint32_t mask = 0u;
         if (i < R) {
-            const int q = A.read_qual[ro + i], qi = A.read_ins[ro + i], qd = A.read_del[ro + i];
+            const int q = A.read_qual[ro + i], qi = A.read_ins[ro + i];
             const int qg = A.read_gcp ? A.read_gcp[ro + i] : A.gcp_constant;
             const double err = A.qerr_d[q];
             const double pm = 1.0 - err;                         // pair_hmm.rs:644
             const double px = err / (double)A.mismatch_div;       // :646-651
-            const double tMM = m2m_lookup(A.m2m, qi, qd);         // pair_hmm_model.rs:149
-            const double tGM = 1.0 - A.qerr_d[qg];                // :152
+            const double tGM = 1.0 - A.qerr_d[qg];                // pair_hmm_model.rs:152
             const double tII = A.qerr_d[qg];                      // :153-155
+            const double s_i = a_tilde(i + 1);
             bool ex = false;
             mask = encode_base(A.read_bases[ro + i], ex) & 0xFFu;
             if (i == 0) {
@@ -183,24 +222,25 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
             } else {
                 const double tMIp = A.qerr_d[A.read_ins[ro + i - 1]];
                 const double tMDp = A.qerr_d[A.read_del[ro + i - 1]];
-                a = (float)(pm * tMM);
-                b = (float)(pm * tGM * tMIp);
-                c = (float)(pm * tGM * tMDp);
-                e = (float)(tII * tMIp / A.qerr_d[qi]);
+                const double a_i = a_tilde(i), a_p = a_tilde(i - 1);
+                b = (float)(pm * tGM * tMIp / a_p);
+                c = (float)(pm * tGM * tMDp / a_i);
+                e = (float)(a_i * tII * tMIp / (A.qerr_d[qi] * a_p));
             }
-            r = (pm > 0.0) ? (float)(px / pm) : 0.f;
+            sm = (float)s_i;
+            sx = (pm > 0.0) ? (float)(s_i * px / pm) : 0.f;
             f = (float)tII;  // tDD == tII
         } else if (i == R) {
-            // first padding row under the read: I^ becomes the column's summand M[R][j] + I[R][j]
-            e = (R > 0) ? A.qerr_f[A.read_ins[ro + R - 1]] : 0.f;
+            // first padding row under the read: I' becomes the column's summand M[R][j] + I[R][j]
+            e = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1));
         }
-        ca[k] = a; cb[k] = b; cc[k] = c; ce[k] = e; cr[k] = r;
+        cb[k] = b; cc[k] = c; ce[k] = e; cs[k] = sm; csr[k] = sx;
         if (VARGCP) cf[k] = f;
         rm[k >> 2] |= mask << (8 * (k & 3));
     }
     if (lig == glanes - 1) {
         const int kstar = (R - 1) - lig * K;
-        if (kstar == K - 1) { wM = 1.f; wI = A.qerr_f[A.read_ins[ro + R - 1]]; }
+        if (kstar == K - 1) { wM = 1.f; wI = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1)); }
         else { wM = 0.f; wI = 1.f; }
     }
 
@@ -219,27 +259,24 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
         const int n_steps = H + maxlanes - 1;
         const int s_last = H + lig;  // last step at which this lane's column is still <= H
 
-#pragma unroll 4
+LK_UNROLL_N(LK_FAST_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
             const uint32_t hrep = w.ldg(hp + s);
-            // ---- M and D^ (descending so that row k-1 still holds column c-1) ----
+            // ---- M' and D' (descending so that row k-1 still holds column c-1) ----
 #pragma unroll
             for (int k = K - 1; k >= 0; k--) {
                 float mm;
                 if (k == 0) {
-                    mm = fmaf(Md, ca[0], kinit);
-                    mm = fmaf(Id, cb[0], mm);
+                    mm = fmaf(Id, cb[0], Md + kinit);  // start lanes: Md = 0 and b' = c' = 0, so mm = kinit
                     mm = fmaf(Dd, cc[0], mm);
                 } else {
-                    mm = M[k - 1] * ca[k];
-                    mm = fmaf(I[k - 1], cb[k], mm);
+                    mm = fmaf(I[k - 1], cb[k], M[k - 1]);
                     mm = fmaf(D[k - 1], cc[k], mm);
                 }
                 D[k] = fmaf(D[k], VARGCP ? cf[k] : cf[0], M[k]);
-                const bool match = (rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3)))) != 0u;
-                M[k] = mm * (match ? 1.0f : cr[k]);
+                M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
             }
-            // ---- I^ (ascending: same column, row above) ----
+            // ---- I' (ascending: same column, row above) ----
             I[0] = fmaf(Iu, ce[0], Mu);
 #pragma unroll
             for (int k = 1; k < K; k++) I[k] = fmaf(I[k - 1], ce[k], M[k - 1]);
@@ -251,7 +288,7 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
             Mu = w.shfl_up1(M[K - 1]);
             Iu = w.shfl_up1(I[K - 1]);
             Du = w.shfl_up1(D[K - 1]);
-            if (is_start) Mu = 0.f;  // a0 = b0 = c0 = e0 = 0 already mute the other inputs
+            if (is_start) Mu = 0.f;  // b'0 = c'0 = e'0 = 0 already mute the other inputs of a group's first lane
         }
 
         if (lig == glanes - 1) {

@@ -47,7 +47,8 @@ __global__ void encode_haps_kernel(const uint8_t *__restrict__ hap_bases, const 
 }
 
 __global__ void scan_reads_kernel(const uint8_t *__restrict__ read_bases, const uint8_t *__restrict__ read_qual,
-                                  const uint8_t *__restrict__ read_ins, const int64_t *__restrict__ read_off,
+                                  const uint8_t *__restrict__ read_ins, const uint8_t *__restrict__ read_del,
+                                  const int64_t *__restrict__ read_off,
                                   int64_t n_reads, uint8_t *__restrict__ read_flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -61,6 +62,7 @@ __global__ void scan_reads_kernel(const uint8_t *__restrict__ read_bases, const 
             (void)encode_base(read_bases[ro + i], exotic);
             qzero |= (read_qual[ro + i] == 0);  // match prior would be exactly 0: hat form divides by it
             const int qi = read_ins[ro + i];
+            qzero |= (qi < 4) || (read_del[ro + i] < 4);  // match->match may be exactly 0: scaled form divides by it
             imin = min(imin, qi);
             imax = max(imax, qi);
         }
@@ -130,12 +132,12 @@ cudaError_t launch_encode_haps(const uint8_t *hap_bases, const int64_t *hap_off,
 }
 
 cudaError_t launch_scan_reads(const uint8_t *read_bases, const uint8_t *read_qual, const uint8_t *read_ins,
-                              const int64_t *read_off, int64_t n_reads, uint8_t *read_flags, cudaStream_t st) {
+                              const uint8_t *read_del, const int64_t *read_off, int64_t n_reads, uint8_t *read_flags, cudaStream_t st) {
     if (n_reads == 0) return cudaSuccess;
     const int threads = 256;
     int64_t blocks = (n_reads * 32 + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    scan_reads_kernel<<<(unsigned)blocks, threads, 0, st>>>(read_bases, read_qual, read_ins, read_off, n_reads, read_flags);
+    scan_reads_kernel<<<(unsigned)blocks, threads, 0, st>>>(read_bases, read_qual, read_ins, read_del, read_off, n_reads, read_flags);
     return cudaGetLastError();
 }
 

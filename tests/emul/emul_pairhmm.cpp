@@ -116,7 +116,7 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
         int imin = 255, imax = 0;
         for (int64_t i = b->read_off[r]; i < b->read_off[r + 1]; i++) {
             (void)encode_base(b->read_bases[i], ex);
-            qz |= b->read_qual[i] == 0;
+            qz |= b->read_qual[i] == 0 || b->read_ins[i] < 4 || b->read_del[i] < 4;
             imin = std::min<int>(imin, b->read_ins[i]);
             imax = std::max<int>(imax, b->read_ins[i]);
         }

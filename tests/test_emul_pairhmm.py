@@ -16,7 +16,7 @@ def _golden_batch(rows):
     return PC.pack_cases(cases)
 
 
-@pytest.mark.parametrize("force_k", [0, 4, 10, 19])
+@pytest.mark.parametrize("force_k", [0, 4, 10, 15, 19])
 def test_golden_rows_fast_path(force_k):
     rows = load_pairhmm_golden()[::4]
     got, flags, n_resc = E.pairhmm_batch(_golden_batch(rows), force_k=force_k)

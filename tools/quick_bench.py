@@ -28,8 +28,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         print("   e2e host call: %.1f ms" % ((time.time() - t) * 1e3), flush=True)
 else:
     n = sys.argv[1] if len(sys.argv) > 1 else "2000"
-    for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0", "8", "10", "16", "19", "20"]):
+    for k in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["p0", "p5", "p6", "p8", "p10", "s0", "s19"]):
         env = dict(os.environ)
+        k = k.lstrip("ps")
         if k != "0":
             env["LK_FORCE_K"] = k
         subprocess.run([sys.executable, __file__, "child", n], env=env)
