@@ -23,6 +23,7 @@ const int *fast_k_values(int *n) {
 int choose_k(int R, int force_k) {
     int n = 0;
     const int *ks = fast_k_values(&n);
+    if (force_k < 0) return 0;  // developer switch: route every read to the band kernel
     if (force_k > 0) {
         for (int i = 0; i < n; i++)
             if (ks[i] == force_k && R <= 32 * force_k) return force_k;

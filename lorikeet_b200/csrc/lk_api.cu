@@ -240,8 +240,11 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
     R->n_pairs = P.n_pairs; R->n_cells = P.n_cells; R->h_max = P.h_max;
     R->launches = P.launches;
     R->all_f64 = ctx->force_f64;
-    R->n_direct = ctx->force_f64 ? 0 : (int32_t)P.direct.size();
     R->vargcp = gcp.vargcp; R->gcp_constant = gcp.constant;
+    // reads too long for the fast kernel: fp32 band kernel, or straight to the f64 pass when gcp varies per base
+    const bool use_band = !ctx->force_f64 && !gcp.vargcp;
+    R->n_band = use_band ? (int32_t)P.direct.size() : 0;
+    R->n_direct = (ctx->force_f64 || use_band) ? 0 : (int32_t)P.direct.size();
     R->read_byte0 = n_reads ? b->read_off[rbase] : 0;
     R->hap_byte0 = n_haps ? b->hap_off[hbase] : 0;
     const int64_t read_bytes = n_reads ? b->read_off[rbase + n_reads] - R->read_byte0 : 0;
@@ -261,6 +264,7 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
         { &R->tasks, P.tasks.data(), P.tasks.size() * sizeof(WarpTask) },
         { &R->groups, P.groups.data(), P.groups.size() * sizeof(TaskGroup) },
         { &R->rescue_pairs, P.direct.data(), (size_t)R->n_direct * sizeof(RescuePair) },
+        { &R->band_pairs, P.direct.data(), (size_t)R->n_band * sizeof(RescuePair) },
     };
     size_t total = 0;
     for (const Piece &pc : pieces) total += (pc.bytes + 255) & ~(size_t)255;
@@ -278,6 +282,9 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
     R->plain_blocks = ctx->n_sm * 2;
     R->scratch_stride = 6 * ((int64_t)P.h_max + 1);
     RS(scratch, (int64_t)R->plain_blocks * (LK_PLAIN_THREADS / 32) * R->scratch_stride * 8);
+    R->band_blocks = ctx->n_sm * LK_BAND_MINB;
+    R->band_stride = 2 * ((int64_t)P.h_max + 1);
+    if (R->n_band > 0) { RS(band_scratch, (int64_t)R->band_blocks * (LK_BAND_THREADS / 32) * R->band_stride * 16); }
     size_t off = 0;
     for (const Piece &pc : pieces) {
         if (pc.dst != &R->rescue_pairs && (e = pc.dst->reserve(std::max<size_t>(pc.bytes, 16))) != cudaSuccess)
@@ -318,6 +325,9 @@ static void fill_args(lk_ctx *ctx, lk_resident *R, PairHmmArgs &A) {
     A.rescue_count = (int32_t *)R->counters.p; A.rescue_cursor = (int32_t *)R->counters.p + 1;
     A.rescue_pairs = (RescuePair *)R->rescue_pairs.p; A.rescue_capacity = (int32_t)R->n_pairs;
     A.scratch = (double *)R->scratch.p; A.scratch_stride = R->scratch_stride;
+    A.band_pairs = (const RescuePair *)R->band_pairs.p; A.n_band = R->n_band;
+    A.band_cursor = (int32_t *)R->counters.p + 2;
+    A.band_scratch = R->band_scratch.p; A.band_scratch_stride = R->band_stride;
     A.gcp_constant = R->gcp_constant;
     A.mismatch_div = ctx->tristate ? 3.0f : 1.0f;
 }
@@ -329,7 +339,8 @@ static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, b
     fill_args(ctx, R, A);
     R->counter_init[0] = R->all_f64 ? (int32_t)R->n_pairs : R->n_direct;
     R->counter_init[1] = 0;
-    if ((e = cudaMemcpyAsync(R->counters.p, R->counter_init, 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    R->counter_init[2] = 0;
+    if ((e = cudaMemcpyAsync(R->counters.p, R->counter_init, 12, cudaMemcpyHostToDevice, st)) != cudaSuccess)
         return lk_cuda_fail(ctx, e, "reset counters");
     R->launch_count = 0;
     if (R->n_pairs == 0) return LK_OK;
@@ -348,6 +359,10 @@ static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, b
             AL.tasks = (const WarpTask *)R->tasks.p + L.first_task;
             AL.n_tasks = L.n_tasks;
             if ((e = launch_fast(L.K, AL, R->vargcp, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_fast");
+            R->launch_count++;
+        }
+        if (R->n_band > 0) {
+            if ((e = launch_band(A, R->band_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_band");
             R->launch_count++;
         }
         if (timed) cudaEventRecord(R->ev_fast1, st);
@@ -434,7 +449,7 @@ static void release_buffers(lk_resident *R) {
     DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
                        &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
                        &R->hap_bases, &R->henc, &R->henc_off, &R->hap_flags, &R->tasks, &R->groups, &R->out,
-                       &R->flags, &R->counters, &R->rescue_pairs, &R->scratch,
+                       &R->flags, &R->counters, &R->rescue_pairs, &R->scratch, &R->band_pairs, &R->band_scratch,
                        &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,
                        &R->sw_ops, &R->sw_nops, &R->sw_offsets, &R->sw_order };
     for (DevBuf *b : bufs) b->release();

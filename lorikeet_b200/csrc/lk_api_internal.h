@@ -48,7 +48,10 @@ struct lk_resident {
     bool vargcp = false, all_f64 = false;
     uint8_t gcp_constant = 10;
     int32_t n_direct = 0;
-    int32_t counter_init[2] = { 0, 0 };
+    int32_t counter_init[3] = { 0, 0, 0 };
+    int32_t n_band = 0;
+    int band_blocks = 0;
+    int64_t band_stride = 0;
     int plain_blocks = 0;
     int64_t scratch_stride = 0;
     int32_t launch_count = 0;
@@ -61,7 +64,7 @@ struct lk_resident {
     int64_t read_byte0 = 0, hap_byte0 = 0;  // first arena byte staged: device pointers are biased by these
     DevBuf read_bases, read_qual, read_ins, read_del, read_gcp, read_off, read_region, read_out_base, read_flags;
     DevBuf region_hap_start, hap_off, hap_bases, henc, henc_off, hap_flags;
-    DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch;
+    DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch, band_pairs, band_scratch;
     // ---- Smith-Waterman ----
     struct SwLaunch { int K; int32_t first; int32_t count; };
     std::vector<SwLaunch> sw_launches;

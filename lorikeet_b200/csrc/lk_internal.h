@@ -16,6 +16,7 @@ cudaError_t launch_scan_reads(const uint8_t *read_bases, const uint8_t *read_qua
                               const uint8_t *read_del, const int64_t *read_off, int64_t n_reads, uint8_t *read_flags, cudaStream_t st);
 cudaError_t launch_list_all_pairs(const PairHmmArgs &A, int64_t n_reads, cudaStream_t st);
 cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t st);
+cudaError_t launch_band(const PairHmmArgs &A, int n_blocks, cudaStream_t st);
 cudaError_t launch_plain(const PairHmmArgs &A, int n_blocks, cudaStream_t st);
 cudaError_t launch_sw(int K, const SwArgs &A, int n_blocks, cudaStream_t st);
 

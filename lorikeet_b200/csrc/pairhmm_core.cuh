@@ -107,6 +107,12 @@ struct PairHmmArgs {
     int32_t *rescue_count;
     RescuePair *rescue_pairs;
     int32_t rescue_capacity;
+    // band path (long reads, fp32)
+    const RescuePair *band_pairs;
+    int32_t n_band;
+    int32_t *band_cursor;
+    void *band_scratch;            // per-warp boundary rows (Bnd4)
+    int64_t band_scratch_stride;   // elements per warp
     // f64 pass
     double *scratch;               // per-warp band boundaries
     int64_t scratch_stride;        // doubles per warp
@@ -302,6 +308,205 @@ LK_UNROLL_N(LK_FAST_UNROLL)
                 if (A.flags) A.flags[oi] = 0;
             }
         }
+    }
+}
+
+// =============================================================================================
+// Band path: fp32 scaled hat form for reads longer than the fast path's 32*K rows (cfg#3: 10 kbp reads).
+// One warp per (read, haplotype) pair; rows go in bands of 32*K, the band's last row travels through
+// per-warp scratch as 16-byte (M', I', D') elements.  fp32 cannot hold the decay of hundreds of noisy
+// rows, so every row carries a power-of-two exponent e_i that is folded into its constants for free
+// (cs,csr *= 2^e_i; b',e' *= 2^e_{i-1}); the band's total exponent T is chosen from the decay observed
+// in the previous band, and a band whose output left the safe fp32 window is simply redone with a
+// corrected T (its input row is still in scratch).  The result is log10(sum) - (100 + sum T) log10 2.
+// =============================================================================================
+struct Bnd4 { float m, i, d, pad; };
+
+LK_DEV int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+template <class W, int K>
+LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, Bnd4 *scratch) {
+    const int lane = w.lane();
+    const int64_t ro = A.read_off[read];
+    const int R = (int)(A.read_off[read + 1] - ro);
+    const int H = (int)(A.hap_off[h + 1] - A.hap_off[h]);
+    const int32_t region = A.read_region[read];
+    const int64_t oi = A.read_out_base[read] + (h - A.region_hap_start[region]);
+    auto to_rescue = [&]() {
+        if (lane == 0) {
+            const int slot = w.atomic_add(A.rescue_count, 1);
+            if (slot < A.rescue_capacity) { A.rescue_pairs[slot].read = read; A.rescue_pairs[slot].hap = (int32_t)h; }
+        }
+    };
+    if (A.read_flags[read] != 0 || A.hap_flags[h] != 0 || A.read_gcp != nullptr) { to_rescue(); return; }
+
+    const int BAND = 32 * K;
+    const int n_bands = (R + BAND - 1) / BAND;
+    const int64_t W1 = (int64_t)H + 1;
+    Bnd4 *bnd[2] = { scratch, scratch + W1 };
+    const uint32_t *hp = A.henc + A.henc_off[h] - 1 - lane;  // hp[s] = encoded column (s - lane)
+    const float cf = A.qerr_f[A.gcp_constant];
+    auto a_tilde = [&](int i) -> double {
+        if (i < 1 || i >= R) return 1.0;
+        return (1.0 - A.qerr_d[A.read_qual[ro + i]]) * m2m_lookup(A.m2m, A.read_ins[ro + i], A.read_del[ro + i]);
+    };
+
+    const float initH = FAST_INIT / (float)H;
+    int x_in = ilogbf(initH);  // binary exponent of the magnitudes entering the band
+    long e_total = 0;          // sum of the exponents applied so far
+    int e_prev_last = 0;       // exponent of the last row of the previous band
+    int T = 0;                 // exponent budget of the current band
+    constexpr int X_TARGET = 75;
+    float acc_final = 0.f;
+    bool failed = false;
+
+    for (int band = 0; band < n_bands && !failed; band++) {
+        const int row0 = band * BAND;
+        const int rows = (R - row0 < BAND) ? (R - row0) : BAND;
+        const int lanes = (rows + K - 1) / K;
+        const bool last_band = (band == n_bands - 1);
+        const Bnd4 *bin = bnd[band & 1];
+        Bnd4 *bout = bnd[(band + 1) & 1];
+        if (band == 0) {
+            // first guess: the decay of an all-match path through this band, -sum log2(pm * tMM)
+            float dsum = 0.f;
+            for (int k = 0; k < K; k++) {
+                const int i = lane * K + k;
+                if (i >= 1 && i < rows) dsum -= log2f((float)a_tilde(i));
+            }
+            for (int d = 16; d >= 1; d >>= 1) dsum += w.shfl_xor(dsum, d);
+            T = (int)dsum;
+        }
+        int tries = 0;
+        for (;;) {
+            // ---- row constants with the exponent schedule e(r) = floor((r+1)T/rows) - floor(rT/rows) ----
+            float cb[K], cc[K], ce[K], cs[K], csr[K];
+            uint32_t rm[(K + 3) / 4];
+#pragma unroll
+            for (int i = 0; i < (K + 3) / 4; i++) rm[i] = 0u;
+            float kcoef = 0.f, wM = 0.f, wI = 0.f;
+            auto expo = [&](int r) -> int {  // exponent of local row r of this band (0 for padding rows)
+                if (r < 0) return e_prev_last;
+                if (r >= rows) return 0;
+                return floor_div((r + 1) * T, rows) - floor_div(r * T, rows);
+            };
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int r = lane * K + k;   // local row
+                const int i = row0 + r;       // 0-based read position
+                float b = 0.f, c = 0.f, e = (i > R) ? 1.f : 0.f, sm = 0.f, sx = 0.f;
+                uint32_t mask = 0u;
+                const int e_i = expo(r), e_p = expo(r - 1);
+                if (i < R) {
+                    const int q = A.read_qual[ro + i], qi = A.read_ins[ro + i];
+                    const double err = A.qerr_d[q];
+                    const double pm = 1.0 - err, px = err / (double)A.mismatch_div;
+                    const double tGM = 1.0 - A.qerr_d[A.gcp_constant], tII = A.qerr_d[A.gcp_constant];
+                    const double s_i = a_tilde(i + 1);
+                    bool ex = false;
+                    mask = encode_base(A.read_bases[ro + i], ex) & 0xFFu;
+                    if (i == 0) {
+                        kcoef = (float)(pm * tGM);
+                    } else {
+                        const double tMIp = A.qerr_d[A.read_ins[ro + i - 1]], tMDp = A.qerr_d[A.read_del[ro + i - 1]];
+                        const double a_i = a_tilde(i), a_p = a_tilde(i - 1);
+                        b = (float)ldexp(pm * tGM * tMIp / a_p, e_p);
+                        c = (float)(pm * tGM * tMDp / a_i);
+                        e = (float)ldexp(a_i * tII * tMIp / (A.qerr_d[qi] * a_p), e_p);
+                    }
+                    sm = (float)ldexp(s_i, e_i);
+                    sx = (pm > 0.0) ? (float)ldexp(s_i * px / pm, e_i) : 0.f;
+                } else if (i == R) {
+                    e = (float)ldexp(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1), e_p);
+                }
+                cb[k] = b; cc[k] = c; ce[k] = e; cs[k] = sm; csr[k] = sx;
+                rm[k >> 2] |= mask << (8 * (k & 3));
+            }
+            if (last_band && lane == lanes - 1) {
+                const int kstar = (rows - 1) - lane * K;
+                if (kstar == K - 1) { wM = 1.f; wI = (float)ldexp(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1), expo(rows - 1)); }
+                else { wM = 0.f; wI = 1.f; }
+            }
+            const float kinit = (band == 0) ? kcoef * initH : 0.f;  // only row 1 (band 0, lane 0) has kcoef != 0
+
+            float M[K], I[K], D[K];
+#pragma unroll
+            for (int k = 0; k < K; k++) { M[k] = 0.f; I[k] = 0.f; D[k] = 0.f; }
+            float Mu = 0.f, Iu = 0.f, Du = 0.f, Md = 0.f, Id = 0.f, Dd = 0.f, acc = 0.f, mx = 0.f;
+            const int n_steps = H + lanes - 1;
+            const int s_last = H + lane;
+            const bool feeds = (lane == 0) && (band > 0);
+            const bool writes = !last_band && (lane == lanes - 1);
+            if (writes) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = 0.f; z.pad = 0.f; bout[0] = z; }
+
+LK_UNROLL_N(LK_FAST_UNROLL)
+            for (int s = 1; s <= n_steps; ++s) {
+                const uint32_t hrep = w.ldg(hp + s);
+                if (feeds) {  // row above = last row of the previous band
+                    if (s <= H) { const Bnd4 v = bin[s]; Mu = v.m; Iu = v.i; Du = v.d; w.prefetch(bin + (s + 24 <= H ? s + 24 : H)); }
+                    else { Mu = 0.f; Iu = 0.f; Du = 0.f; }
+                }
+#pragma unroll
+                for (int k = K - 1; k >= 0; k--) {
+                    float mm;
+                    if (k == 0) {
+                        mm = fmaf(Id, cb[0], Md + kinit);
+                        mm = fmaf(Dd, cc[0], mm);
+                    } else {
+                        mm = fmaf(I[k - 1], cb[k], M[k - 1]);
+                        mm = fmaf(D[k - 1], cc[k], mm);
+                    }
+                    D[k] = fmaf(D[k], cf, M[k]);
+                    M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
+                }
+                I[0] = fmaf(Iu, ce[0], Mu);
+#pragma unroll
+                for (int k = 1; k < K; k++) I[k] = fmaf(I[k - 1], ce[k], M[k - 1]);
+                if (s <= s_last) {
+                    acc = fmaf(M[K - 1], wM, acc);
+                    acc = fmaf(I[K - 1], wI, acc);
+                    if (writes && s > lane) {
+                        Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.pad = 0.f;
+                        bout[s - lane] = v;
+                        mx = fmaxf(mx, fmaxf(v.m, fmaxf(v.i, v.d)));
+                    }
+                }
+                Md = Mu; Id = Iu; Dd = Du;
+                Mu = w.shfl_up1(M[K - 1]);
+                Iu = w.shfl_up1(I[K - 1]);
+                Du = w.shfl_up1(D[K - 1]);
+                if (lane == 0) Mu = 0.f;  // band 0: virtual row 0; later bands: overwritten from scratch next step
+            }
+            // ---- was the exponent budget right? ----
+            const float probe = last_band ? w.shfl(acc, lanes - 1) : w.shfl(mx, lanes - 1);
+            const bool too_small = !(probe >= 1048576.0f);               // < 2^20; includes 0 and NaN
+            const bool too_big = !(probe <= 1.3292279957849159e36f);     // > 2^120; includes inf and NaN
+            if ((too_small || too_big) && tries < 10) {
+                tries++;
+                if (probe != probe || probe > 3.0e38f) T -= 96;          // NaN / inf: overflowed inside the band
+                else if (probe > 0.f) T += X_TARGET - ilogbf(probe);     // finite: linear correction
+                else T += 160;                                           // flushed to zero: decay unknown, step up
+                continue;
+            }
+            if (too_small || too_big) { failed = true; break; }
+            w.sync();  // the band's boundary row is visible to lane 0 of the next band
+            e_total += T;
+            e_prev_last = expo(rows - 1);
+            if (last_band) acc_final = probe;
+            else {
+                const int x_out = ilogbf(probe);
+                const int decay = x_in + T - x_out;  // bits lost to the data over this band
+                const int next_rows = (R - (row0 + BAND) < BAND) ? (R - (row0 + BAND)) : BAND;
+                T = (X_TARGET - x_out) + (int)((long)decay * next_rows / rows);
+                x_in = x_out;
+            }
+            break;
+        }
+    }
+    if (failed) { to_rescue(); return; }
+    if (lane == 0) {
+        A.out[oi] = log10((double)acc_final) - FAST_INIT_LOG10 - (double)e_total * 0.30102999566398120;
+        if (A.flags) A.flags[oi] = 0;
     }
 }
 

@@ -17,11 +17,13 @@ struct DevWarp {
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
     template <class T> __device__ __forceinline__ T shfl_up1(T v) const { return __shfl_up_sync(0xffffffffu, v, 1); }
     template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
     __device__ __forceinline__ unsigned reduce_or(unsigned v) const { return __reduce_or_sync(0xffffffffu, v); }
     __device__ __forceinline__ unsigned reduce_max(unsigned v) const { return __reduce_max_sync(0xffffffffu, v); }
     template <class T> __device__ __forceinline__ T ldg(const T *p) const { return __ldg(p); }
     __device__ __forceinline__ int atomic_add(int32_t *p, int v) const { return atomicAdd(p, v); }
     __device__ __forceinline__ void sync() const { __syncwarp(); __threadfence_block(); }
+    __device__ __forceinline__ void prefetch(const void *p) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -102,6 +104,22 @@ __global__ void __launch_bounds__(LK_FAST_THREADS, MINB) pairhmm_fast_kernel(con
 }
 
 template <int K>
+__global__ void __launch_bounds__(LK_BAND_THREADS, LK_BAND_MINB) pairhmm_band_kernel(const PairHmmArgs A) {
+    DevWarp w;
+    const int warp_in_grid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    Bnd4 *scratch = (Bnd4 *)A.band_scratch + (int64_t)warp_in_grid * A.band_scratch_stride;
+    for (;;) {
+        int idx = 0;
+        if (w.lane() == 0) idx = atomicAdd(A.band_cursor, 1);
+        idx = w.shfl(idx, 0);
+        if (idx >= A.n_band) break;
+        const RescuePair p = A.band_pairs[idx];
+        pairhmm_band_pair<DevWarp, K>(w, A, p.read, (int64_t)p.hap, scratch);
+        __syncwarp();
+    }
+}
+
+template <int K>
 __global__ void __launch_bounds__(LK_PLAIN_THREADS) pairhmm_plain_kernel(const PairHmmArgs A) {
     DevWarp w;
     const int warp_in_grid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -164,6 +182,12 @@ cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t s
 #undef LK_CASE
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_band(const PairHmmArgs &A, int n_blocks, cudaStream_t st) {
+    if (A.n_band == 0) return cudaSuccess;
+    pairhmm_band_kernel<LK_BAND_K><<<n_blocks, LK_BAND_THREADS, 0, st>>>(A);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_plain(const PairHmmArgs &A, int n_blocks, cudaStream_t st) {

@@ -37,6 +37,7 @@ struct EmulWarp {
     }
     template <class T> T shfl_up1(T v) { return exchange(v, lane_ - 1); }
     template <class T> T shfl(T v, int src) { return exchange(v, src & 31); }
+    template <class T> T shfl_xor(T v, int m) { return exchange(v, lane_ ^ m); }
     unsigned reduce_or(unsigned v) {
         sh->slot[lane_] = v;
         sh->bar.arrive_and_wait();
@@ -56,6 +57,7 @@ struct EmulWarp {
     template <class T> T ldg(const T *p) const { return *p; }
     int atomic_add(int32_t *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
     void sync() { sh->bar.arrive_and_wait(); }
+    void prefetch(const void *) const {}
 };
 
 template <int K>
@@ -71,6 +73,20 @@ static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *ta
             for (int t = 0; t < n_tasks; t++) {
                 if (vargcp) pairhmm_fast_task<EmulWarp, K, true>(w, AL, t);
                 else pairhmm_fast_task<EmulWarp, K, false>(w, AL, t);
+            }
+        });
+    for (auto &t : th) t.join();
+}
+
+static void run_band(const PairHmmArgs &A, int k_band) {
+    WarpShared sh;
+    std::vector<std::thread> th;
+    for (int l = 0; l < 32; l++)
+        th.emplace_back([&, l]() {
+            EmulWarp w{ l, &sh };
+            for (int i = 0; i < A.n_band; i++) {
+                if (k_band == 4) pairhmm_band_pair<EmulWarp, 4>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch);
+                else pairhmm_band_pair<EmulWarp, LK_BAND_K>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch);
             }
         });
     for (auto &t : th) t.join();
@@ -95,6 +111,7 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
     const int64_t n_reads = b->region_read_start[b->n_regions], n_haps = b->region_hap_start[b->n_regions];
     HostPrep P;
     build_prep(b, 0, b->n_regions, force_k, !force_f64, P);
+    if (force_k == -4) { HostPrep Q; build_prep(b, 0, b->n_regions, -1, !force_f64, Q); P = Q; }
     ModelTables T;
     build_model_tables(T);
     std::vector<uint32_t> henc((size_t)P.henc_words, 0u);
@@ -146,7 +163,16 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
                 rescue[(size_t)counters[0]++] = RescuePair{ (int32_t)r, (int32_t)h };
         }
     } else {
-        for (const auto &d : P.direct) rescue[(size_t)counters[0]++] = d;
+        // long reads: fp32 band routine (force_k == -4 runs it with K = 4 so that short test reads span many bands)
+        std::vector<Bnd4> band_scratch((size_t)(2 * (P.h_max + 1)));
+        int32_t band_cursor = 0;
+        if (!vargcp) {
+            A.band_pairs = P.direct.data(); A.n_band = (int32_t)P.direct.size();
+            A.band_cursor = &band_cursor; A.band_scratch = band_scratch.data(); A.band_scratch_stride = (int64_t)band_scratch.size();
+            run_band(A, force_k == -4 ? 4 : LK_BAND_K);
+        } else {
+            for (const auto &d : P.direct) rescue[(size_t)counters[0]++] = d;
+        }
         for (const auto &L : P.launches) {
             const WarpTask *t = P.tasks.data() + L.first_task;
             switch (L.K) {

@@ -105,7 +105,7 @@ def test_underflow_is_rescued_and_long_read_bands():
     n = len(read)
     c1 = dict(hap=hap, read=read, qual=np.full(n, 40, np.uint8), ins=np.full(n, 45, np.uint8),
               dele=np.full(n, 45, np.uint8), gcp=np.full(n, 10, np.uint8))
-    # (b) read longer than the fast path's 32*20 rows -> f64 pass with several row bands
+    # (b) read longer than the fast path's 32*20 rows -> band kernel (fp32), or the f64 pass when forced
     hap_l = rng.choice(acgt, 900)
     read_l = hap_l[50:50 + 700].copy()
     m = len(read_l)
@@ -115,6 +115,50 @@ def test_underflow_is_rescued_and_long_read_bands():
     exp = O.pairhmm_batch(batch)
     exp_resc = O.pairhmm_batch(batch, rescaled=True)
     got, flags, n_resc = E.pairhmm_batch(batch)
-    assert n_resc == 2 and np.all(flags == 1)
+    assert n_resc == 1 and list(flags) == [1, 0]   # (b) now runs in the fp32 band kernel
     assert abs(got[0] - exp[0]) < 1e-9
+    assert abs(got[1] - exp_resc[1]) / abs(exp_resc[1]) < 1e-4
+    got, flags, n_resc = E.pairhmm_batch(batch, force_f64=True)  # the f64 pass still handles several row bands
     assert abs(got[1] - exp_resc[1]) < 1e-8
+
+
+def _noisy_long_case(rng, R, H, qlo=7, qhi=21, indel=0.03):
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    hap = rng.choice(acgt, H)
+    out, pos = [], int(rng.integers(0, H - R - 60))
+    while len(out) < R:
+        u = rng.random()
+        if u < indel / 2:
+            out.append(rng.choice(acgt))
+        else:
+            if u < indel:
+                pos += 1
+            out.append(hap[pos]); pos += 1
+    read = np.array(out, dtype=np.uint8)
+    q = rng.integers(qlo, qhi, R).astype(np.uint8)
+    flip = rng.random(R) < 10 ** (-q / 10.0)
+    read[flip] = rng.choice(acgt, int(flip.sum()))
+    return dict(hap=hap, read=read, qual=q, ins=np.full(R, 45, np.uint8), dele=np.full(R, 45, np.uint8), gcp=np.full(R, 10, np.uint8))
+
+
+def test_band_path_many_bands_noisy_reads():
+    # K = 4 -> bands of 128 rows: 700-1100 row reads cross 6-9 bands; ONT-like noise forces the exponent schedule to work
+    rng = np.random.default_rng(21)
+    cases = [_noisy_long_case(rng, 700, 900), _noisy_long_case(rng, 1100, 1300), _noisy_long_case(rng, 513, 800, 30, 41, 0.0),
+             _noisy_long_case(rng, 128, 300), _noisy_long_case(rng, 129, 300)]
+    batch = PC.pack_cases(cases)
+    exp = O.pairhmm_batch(batch, rescaled=True)
+    got, flags, n_resc = E.pairhmm_batch(batch, force_k=-4)
+    assert n_resc == 0 and np.all(flags == 0)
+    assert np.max(np.abs(got - exp) / np.abs(exp)) < 1e-4
+
+
+def test_band_path_default_k_and_hopeless_pair():
+    rng = np.random.default_rng(22)
+    ok = _noisy_long_case(rng, 900, 1200)
+    bad = dict(ok, read=rng.choice(np.frombuffer(b"ACGT", np.uint8), 900), qual=np.full(900, 40, np.uint8))  # unrelated read
+    batch = PC.pack_cases([ok, bad])
+    exp = O.pairhmm_batch(batch, rescaled=True)
+    got, flags, n_resc = E.pairhmm_batch(batch)  # R = 900 > 32*20: band kernel with its production K
+    assert flags[0] == 0
+    assert np.max(np.abs(got - exp) / np.abs(exp)) < 1e-4
