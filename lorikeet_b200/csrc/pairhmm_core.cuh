@@ -24,6 +24,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define LK_DEV __device__ __forceinline__
@@ -314,15 +315,37 @@ LK_UNROLL_N(LK_FAST_UNROLL)
 // =============================================================================================
 // Band path: fp32 scaled hat form for reads longer than the fast path's 32*K rows (cfg#3: 10 kbp reads).
 // One warp per (read, haplotype) pair; rows go in bands of 32*K, the band's last row travels through
-// per-warp scratch as 16-byte (M', I', D') elements.  fp32 cannot hold the decay of hundreds of noisy
-// rows, so every row carries a power-of-two exponent e_i that is folded into its constants for free
-// (cs,csr *= 2^e_i; b',e' *= 2^e_{i-1}); the band's total exponent T is chosen from the decay observed
-// in the previous band, and a band whose output left the safe fp32 window is simply redone with a
-// corrected T (its input row is still in scratch).  The result is log10(sum) - (100 + sum T) log10 2.
+// per-warp scratch as 16-byte (M', I', D', exponent) elements.
+//
+// fp32 cannot hold the decay of hundreds of noisy rows (a 10 kbp ONT-like read loses ~7000 binary orders),
+// so every lane carries a private binary exponent xi ("stored = true * 2^xi", block floating point per
+// lane): every 16 columns a lane looks at the magnitude of its strip and, if it drifted out of
+// [2^-20, 2^60], multiplies its whole state by 2^(+-40) and adjusts xi.  The exponent travels with the
+// data (a 4th shuffle / the 4th word of the boundary element) and the receiver re-aligns what it gets
+// with one FMUL per value.  Fully adaptive: no a-priori decay estimate, no retries.
 // =============================================================================================
-struct Bnd4 { float m, i, d, pad; };
+struct Bnd4 { float m, i, d; int32_t xi; };
 
-LK_DEV int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+constexpr int BAND_INIT_EXP = 40;  // initial condition 2^40 / H
+
+LK_DEV int __float_as_int_hd(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    int i;
+    memcpy(&i, &f, 4);
+    return i;
+#endif
+}
+
+LK_DEV float pow2i(int e) {  // 2^e for e in [-126, 127]
+    e = e < -126 ? -126 : (e > 127 ? 127 : e);
+#if defined(__CUDA_ARCH__)
+    return __int_as_float((e + 127) << 23);
+#else
+    return ldexpf(1.0f, e);
+#endif
+}
 
 template <class W, int K>
 LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, Bnd4 *scratch) {
@@ -350,162 +373,152 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         if (i < 1 || i >= R) return 1.0;
         return (1.0 - A.qerr_d[A.read_qual[ro + i]]) * m2m_lookup(A.m2m, A.read_ins[ro + i], A.read_del[ro + i]);
     };
-
-    const float initH = FAST_INIT / (float)H;
-    int x_in = ilogbf(initH);  // binary exponent of the magnitudes entering the band
-    long e_total = 0;          // sum of the exponents applied so far
-    int e_prev_last = 0;       // exponent of the last row of the previous band
-    int T = 0;                 // exponent budget of the current band
-    constexpr int X_TARGET = 75;
+    const float initH = ldexpf(1.0f, BAND_INIT_EXP) / (float)H;
     float acc_final = 0.f;
-    bool failed = false;
+    int xi_final = 0;
 
-    for (int band = 0; band < n_bands && !failed; band++) {
+    for (int band = 0; band < n_bands; band++) {
         const int row0 = band * BAND;
         const int rows = (R - row0 < BAND) ? (R - row0) : BAND;
         const int lanes = (rows + K - 1) / K;
         const bool last_band = (band == n_bands - 1);
         const Bnd4 *bin = bnd[band & 1];
         Bnd4 *bout = bnd[(band + 1) & 1];
-        if (band == 0) {
-            // first guess: the decay of an all-match path through this band, -sum log2(pm * tMM)
-            float dsum = 0.f;
-            for (int k = 0; k < K; k++) {
-                const int i = lane * K + k;
-                if (i >= 1 && i < rows) dsum -= log2f((float)a_tilde(i));
-            }
-            for (int d = 16; d >= 1; d >>= 1) dsum += w.shfl_xor(dsum, d);
-            T = (int)dsum;
-        }
-        int tries = 0;
-        for (;;) {
-            // ---- row constants with the exponent schedule e(r) = floor((r+1)T/rows) - floor(rT/rows) ----
-            float cb[K], cc[K], ce[K], cs[K], csr[K];
-            uint32_t rm[(K + 3) / 4];
-#pragma unroll
-            for (int i = 0; i < (K + 3) / 4; i++) rm[i] = 0u;
-            float kcoef = 0.f, wM = 0.f, wI = 0.f;
-            auto expo = [&](int r) -> int {  // exponent of local row r of this band (0 for padding rows)
-                if (r < 0) return e_prev_last;
-                if (r >= rows) return 0;
-                return floor_div((r + 1) * T, rows) - floor_div(r * T, rows);
-            };
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const int r = lane * K + k;   // local row
-                const int i = row0 + r;       // 0-based read position
-                float b = 0.f, c = 0.f, e = (i > R) ? 1.f : 0.f, sm = 0.f, sx = 0.f;
-                uint32_t mask = 0u;
-                const int e_i = expo(r), e_p = expo(r - 1);
-                if (i < R) {
-                    const int q = A.read_qual[ro + i], qi = A.read_ins[ro + i];
-                    const double err = A.qerr_d[q];
-                    const double pm = 1.0 - err, px = err / (double)A.mismatch_div;
-                    const double tGM = 1.0 - A.qerr_d[A.gcp_constant], tII = A.qerr_d[A.gcp_constant];
-                    const double s_i = a_tilde(i + 1);
-                    bool ex = false;
-                    mask = encode_base(A.read_bases[ro + i], ex) & 0xFFu;
-                    if (i == 0) {
-                        kcoef = (float)(pm * tGM);
-                    } else {
-                        const double tMIp = A.qerr_d[A.read_ins[ro + i - 1]], tMDp = A.qerr_d[A.read_del[ro + i - 1]];
-                        const double a_i = a_tilde(i), a_p = a_tilde(i - 1);
-                        b = (float)ldexp(pm * tGM * tMIp / a_p, e_p);
-                        c = (float)(pm * tGM * tMDp / a_i);
-                        e = (float)ldexp(a_i * tII * tMIp / (A.qerr_d[qi] * a_p), e_p);
-                    }
-                    sm = (float)ldexp(s_i, e_i);
-                    sx = (pm > 0.0) ? (float)ldexp(s_i * px / pm, e_i) : 0.f;
-                } else if (i == R) {
-                    e = (float)ldexp(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1), e_p);
-                }
-                cb[k] = b; cc[k] = c; ce[k] = e; cs[k] = sm; csr[k] = sx;
-                rm[k >> 2] |= mask << (8 * (k & 3));
-            }
-            if (last_band && lane == lanes - 1) {
-                const int kstar = (rows - 1) - lane * K;
-                if (kstar == K - 1) { wM = 1.f; wI = (float)ldexp(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1), expo(rows - 1)); }
-                else { wM = 0.f; wI = 1.f; }
-            }
-            const float kinit = (band == 0) ? kcoef * initH : 0.f;  // only row 1 (band 0, lane 0) has kcoef != 0
 
-            float M[K], I[K], D[K];
+        // ---- row constants (same scaled hat form as the fast kernel) ----
+        float cb[K], cc[K], ce[K], cs[K], csr[K];
+        uint32_t rm[(K + 3) / 4];
 #pragma unroll
-            for (int k = 0; k < K; k++) { M[k] = 0.f; I[k] = 0.f; D[k] = 0.f; }
-            float Mu = 0.f, Iu = 0.f, Du = 0.f, Md = 0.f, Id = 0.f, Dd = 0.f, acc = 0.f, mx = 0.f;
-            const int n_steps = H + lanes - 1;
-            const int s_last = H + lane;
-            const bool feeds = (lane == 0) && (band > 0);
-            const bool writes = !last_band && (lane == lanes - 1);
-            if (writes) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = 0.f; z.pad = 0.f; bout[0] = z; }
+        for (int i = 0; i < (K + 3) / 4; i++) rm[i] = 0u;
+        float kcoef = 0.f, wM = 0.f, wI = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const int i = row0 + lane * K + k;  // 0-based read position
+            float b = 0.f, c = 0.f, e = (i > R) ? 1.f : 0.f, sm = 0.f, sx = 0.f;
+            uint32_t mask = 0u;
+            if (i < R) {
+                const int q = A.read_qual[ro + i], qi = A.read_ins[ro + i];
+                const double err = A.qerr_d[q];
+                const double pm = 1.0 - err, px = err / (double)A.mismatch_div;
+                const double tGM = 1.0 - A.qerr_d[A.gcp_constant], tII = A.qerr_d[A.gcp_constant];
+                const double s_i = a_tilde(i + 1);
+                bool ex = false;
+                mask = encode_base(A.read_bases[ro + i], ex) & 0xFFu;
+                if (i == 0) {
+                    kcoef = (float)(pm * tGM);
+                } else {
+                    const double tMIp = A.qerr_d[A.read_ins[ro + i - 1]], tMDp = A.qerr_d[A.read_del[ro + i - 1]];
+                    const double a_i = a_tilde(i), a_p = a_tilde(i - 1);
+                    b = (float)(pm * tGM * tMIp / a_p);
+                    c = (float)(pm * tGM * tMDp / a_i);
+                    e = (float)(a_i * tII * tMIp / (A.qerr_d[qi] * a_p));
+                }
+                sm = (float)s_i;
+                sx = (pm > 0.0) ? (float)(s_i * px / pm) : 0.f;
+            } else if (i == R) {
+                e = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1));
+            }
+            cb[k] = b; cc[k] = c; ce[k] = e; cs[k] = sm; csr[k] = sx;
+            rm[k >> 2] |= mask << (8 * (k & 3));
+        }
+        if (last_band && lane == lanes - 1) {
+            const int kstar = (rows - 1) - lane * K;
+            if (kstar == K - 1) { wM = 1.f; wI = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1)); }
+            else { wM = 0.f; wI = 1.f; }
+        }
+        const float kinit0 = (band == 0) ? kcoef * initH : 0.f;  // only row 1 (band 0, lane 0) has kcoef != 0
+
+        float M[K], I[K], D[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) { M[k] = 0.f; I[k] = 0.f; D[k] = 0.f; }
+        float Mu = 0.f, Iu = 0.f, Du = 0.f, Md = 0.f, Id = 0.f, Dd = 0.f, acc = 0.f, kinit = kinit0;
+        int xi = 0, xi_up = 0;  // my exponent; exponent of the values in Mu/Iu/Du
+        const int n_steps = H + lanes - 1;
+        const int s_last = H + lane;
+        const bool feeds = (lane == 0) && (band > 0);
+        const bool writes = !last_band && (lane == lanes - 1);
+        if (writes) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = 0.f; z.xi = 0; bout[0] = z; }
 
 LK_UNROLL_N(LK_FAST_UNROLL)
-            for (int s = 1; s <= n_steps; ++s) {
-                const uint32_t hrep = w.ldg(hp + s);
-                if (feeds) {  // row above = last row of the previous band
-                    if (s <= H) { const Bnd4 v = bin[s]; Mu = v.m; Iu = v.i; Du = v.d; w.prefetch(bin + (s + 24 <= H ? s + 24 : H)); }
-                    else { Mu = 0.f; Iu = 0.f; Du = 0.f; }
-                }
+        for (int s = 1; s <= n_steps; ++s) {
+            const uint32_t hrep = w.ldg(hp + s);
+            if (feeds) {  // row above = last row of the previous band
+                if (s <= H) { const Bnd4 v = bin[s]; Mu = v.m; Iu = v.i; Du = v.d; xi_up = v.xi; w.prefetch(bin + (s + 24 <= H ? s + 24 : H)); }
+                else { Mu = 0.f; Iu = 0.f; Du = 0.f; }
+            }
+            // ---- bring what the row above sent into my exponent ----
+            // A lane that has not started adopts the sender's exponent.  If the incoming values would exceed 2^60 in my
+            // scale (I had scaled up while only tiny far-off-diagonal values were around), I scale myself down first:
+            // whatever I hold is negligible next to what is arriving.
+            if (s <= lane + 1) xi = xi_up;
+            {
+                const int eb = (__float_as_int_hd(fmaxf(Mu, fmaxf(Iu, Du))) >> 23) & 0xFF;  // biased exponent of the largest
+                const int over = (eb - 127) + (xi - xi_up) - 60;
+                if (over > 0 && eb != 0) {
+                    const float f = pow2i(-over);
 #pragma unroll
-                for (int k = K - 1; k >= 0; k--) {
-                    float mm;
-                    if (k == 0) {
-                        mm = fmaf(Id, cb[0], Md + kinit);
-                        mm = fmaf(Dd, cc[0], mm);
-                    } else {
-                        mm = fmaf(I[k - 1], cb[k], M[k - 1]);
-                        mm = fmaf(D[k - 1], cc[k], mm);
-                    }
-                    D[k] = fmaf(D[k], cf, M[k]);
-                    M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
+                    for (int k = 0; k < K; k++) { M[k] *= f; I[k] *= f; D[k] *= f; }
+                    Md *= f; Id *= f; Dd *= f; acc *= f; kinit *= f;
+                    xi -= over;
                 }
-                I[0] = fmaf(Iu, ce[0], Mu);
+            }
+            const float al = pow2i(xi - xi_up);
+            Mu *= al; Iu *= al; Du *= al;
 #pragma unroll
-                for (int k = 1; k < K; k++) I[k] = fmaf(I[k - 1], ce[k], M[k - 1]);
-                if (s <= s_last) {
-                    acc = fmaf(M[K - 1], wM, acc);
-                    acc = fmaf(I[K - 1], wI, acc);
-                    if (writes && s > lane) {
-                        Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.pad = 0.f;
-                        bout[s - lane] = v;
-                        mx = fmaxf(mx, fmaxf(v.m, fmaxf(v.i, v.d)));
-                    }
+            for (int k = K - 1; k >= 0; k--) {
+                float mm;
+                if (k == 0) {
+                    mm = fmaf(Id, cb[0], Md + kinit);
+                    mm = fmaf(Dd, cc[0], mm);
+                } else {
+                    mm = fmaf(I[k - 1], cb[k], M[k - 1]);
+                    mm = fmaf(D[k - 1], cc[k], mm);
                 }
-                Md = Mu; Id = Iu; Dd = Du;
-                Mu = w.shfl_up1(M[K - 1]);
-                Iu = w.shfl_up1(I[K - 1]);
-                Du = w.shfl_up1(D[K - 1]);
-                if (lane == 0) Mu = 0.f;  // band 0: virtual row 0; later bands: overwritten from scratch next step
+                D[k] = fmaf(D[k], cf, M[k]);
+                M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
             }
-            // ---- was the exponent budget right? ----
-            const float probe = last_band ? w.shfl(acc, lanes - 1) : w.shfl(mx, lanes - 1);
-            const bool too_small = !(probe >= 1048576.0f);               // < 2^20; includes 0 and NaN
-            const bool too_big = !(probe <= 1.3292279957849159e36f);     // > 2^120; includes inf and NaN
-            if ((too_small || too_big) && tries < 10) {
-                tries++;
-                if (probe != probe || probe > 3.0e38f) T -= 96;          // NaN / inf: overflowed inside the band
-                else if (probe > 0.f) T += X_TARGET - ilogbf(probe);     // finite: linear correction
-                else T += 160;                                           // flushed to zero: decay unknown, step up
-                continue;
+            I[0] = fmaf(Iu, ce[0], Mu);
+#pragma unroll
+            for (int k = 1; k < K; k++) I[k] = fmaf(I[k - 1], ce[k], M[k - 1]);
+            if (s <= s_last) {
+                acc = fmaf(M[K - 1], wM, acc);
+                acc = fmaf(I[K - 1], wI, acc);
+                if (writes && s > lane) {
+                    Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi;
+                    bout[s - lane] = v;
+                }
             }
-            if (too_small || too_big) { failed = true; break; }
-            w.sync();  // the band's boundary row is visible to lane 0 of the next band
-            e_total += T;
-            e_prev_last = expo(rows - 1);
-            if (last_band) acc_final = probe;
-            else {
-                const int x_out = ilogbf(probe);
-                const int decay = x_in + T - x_out;  // bits lost to the data over this band
-                const int next_rows = (R - (row0 + BAND) < BAND) ? (R - (row0 + BAND)) : BAND;
-                T = (X_TARGET - x_out) + (int)((long)decay * next_rows / rows);
-                x_in = x_out;
+            // ---- block-floating-point upkeep: at the lane's first column and every 16 columns re-centre the strip ----
+            if ((s & 15) == 0 || s == lane + 1) {
+                float m = acc;  // the running column sum must stay in range too: never scale up past it
+#pragma unroll
+                for (int k = 0; k < K; k++) m = fmaxf(m, fmaxf(M[k], I[k]));
+                if (m > 0.f && (m < 9.5367431640625e-07f || m > 1.152921504606847e18f)) {  // outside [2^-20, 2^60]
+                    int sh = 20 - ilogbf(m);
+                    sh = sh > 120 ? 120 : (sh < -120 ? -120 : sh);
+                    const float f = pow2i(sh);
+#pragma unroll
+                    for (int k = 0; k < K; k++) { M[k] *= f; I[k] *= f; D[k] *= f; }
+                    Mu *= f; Iu *= f; Du *= f; acc *= f; kinit *= f;
+                    xi += sh;
+                }
             }
-            break;
+            Md = Mu; Id = Iu; Dd = Du;
+            Mu = w.shfl_up1(M[K - 1]);
+            Iu = w.shfl_up1(I[K - 1]);
+            Du = w.shfl_up1(D[K - 1]);
+            xi_up = w.shfl_up1(xi);
+            if (lane == 0) { Mu = 0.f; xi_up = xi; }  // band 0: virtual row 0; later bands: overwritten from scratch next step
         }
+        w.sync();  // the band's boundary row is visible to lane 0 of the next band
+        if (last_band) { acc_final = w.shfl(acc, lanes - 1); xi_final = w.shfl(xi, lanes - 1); }
     }
-    if (failed) { to_rescue(); return; }
+#if !defined(__CUDACC__) && defined(LK_EMUL_DEBUG)
+    if (lane == 0) fprintf(stderr, "band result acc %g xi %d\n", (double)acc_final, xi_final);
+#endif
+    if (!(acc_final > 0.f) || !(acc_final < 3.0e38f)) { to_rescue(); return; }  // flushed to zero / overflowed: f64 pass
     if (lane == 0) {
-        A.out[oi] = log10((double)acc_final) - FAST_INIT_LOG10 - (double)e_total * 0.30102999566398120;
+        A.out[oi] = log10((double)acc_final) - (double)(xi_final + BAND_INIT_EXP) * 0.30102999566398120;
         if (A.flags) A.flags[oi] = 0;
     }
 }

@@ -136,7 +136,7 @@ def _noisy_long_case(rng, R, H, qlo=7, qhi=21, indel=0.03):
             out.append(hap[pos]); pos += 1
     read = np.array(out, dtype=np.uint8)
     q = rng.integers(qlo, qhi, R).astype(np.uint8)
-    flip = rng.random(R) < 10 ** (-q / 10.0)
+    flip = rng.random(R) < 10 ** (-q.astype(np.float64) / 10.0)
     read[flip] = rng.choice(acgt, int(flip.sum()))
     return dict(hap=hap, read=read, qual=q, ins=np.full(R, 45, np.uint8), dele=np.full(R, 45, np.uint8), gcp=np.full(R, 10, np.uint8))
 
@@ -160,5 +160,5 @@ def test_band_path_default_k_and_hopeless_pair():
     batch = PC.pack_cases([ok, bad])
     exp = O.pairhmm_batch(batch, rescaled=True)
     got, flags, n_resc = E.pairhmm_batch(batch)  # R = 900 > 32*20: band kernel with its production K
-    assert flags[0] == 0
+    assert n_resc == 0 and np.all(flags == 0)    # block floating point also copes with the ~1e-1700 of an unrelated read
     assert np.max(np.abs(got - exp) / np.abs(exp)) < 1e-4
