@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -507,13 +508,20 @@ extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *
         if (ce != cudaSuccess) return lk_cuda_fail(ctx, ce, "D2H");
         return LK_OK;
     };
+    const bool trace = getenv("LK_TRACE") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
     for (int i = 0; i < C && st == LK_OK; i++) {
         lk_resident *R = ctx->ws[i & 1];
         cudaStream_t s = ctx->stream[i & 1];
+        const double t0 = now_ms();
         st = stage_range(ctx, batch, cut[(size_t)i], cut[(size_t)i + 1], gcp, R, s);
+        const double t1 = now_ms();
         if (st == LK_OK) st = enqueue_kernels(ctx, R, s, false);
         launches += R->launch_count;
+        const double t2 = now_ms();
         if (st == LK_OK && i >= 1) st = collect(i - 1);  // may block on a pageable destination: chunk i is already queued
+        if (trace) fprintf(stderr, "[lk] chunk %d/%d: stage %.2f ms, enqueue %.2f ms, collect %.2f ms (t=%.2f)\n", i, C, t1 - t0, t2 - t1, now_ms() - t2, now_ms() - t_begin);
     }
     if (st == LK_OK) st = collect(C - 1);
     for (int i = 0; i < 2; i++) {

@@ -76,9 +76,11 @@ lk_status sw_upload_locked(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off,
     const int warps_per_block = LK_SW_THREADS / 32;
     int64_t warps = (int64_t)ctx->n_sm * 16;
     const int64_t budget_words = (12LL << 30) / 4;
+    max_words = (max_words + 3) & ~(int64_t)3;
     warps = std::max<int64_t>(warps_per_block, std::min(warps, budget_words / max_words));
     warps = std::min<int64_t>(warps, std::max<int64_t>(warps_per_block, ((n_pairs + warps_per_block - 1) / warps_per_block) * warps_per_block));
     R->sw_blocks = (int)(warps / warps_per_block);
+    max_words = (max_words + 3) & ~(int64_t)3;  // uint4 plane stores need 16-byte aligned per-warp slices
     R->sw_scratch_words = max_words;
     cudaStream_t st = ctx->stream[0];
     const int64_t ref_bytes = n_pairs ? ref_off[n_pairs] : 0, alt_bytes = n_pairs ? alt_off[n_pairs] : 0;

@@ -12,14 +12,17 @@
 // processed in bands of 32*K; a band's last row travels through per-warp scratch.
 //
 // The reference keeps two (n+1)x(m+1) i32 matrices (sw, btrack).  Here nothing of `sw` is stored
-// except the band boundary; `btrack` is compressed to 4 bits per cell
-//     bits 0-1  move: 0 diagonal, 1 horizontal ("step right", insertion), 2 vertical ("step down", deletion)
-//     bit  2    a horizontal gap was (re)opened at this cell  (gap_size_h[i] reset to 1, :235-239)
-//     bit  3    a vertical gap was (re)opened at this cell    (gap_size_v[j] reset to 1, :212-218)
+// except the band boundary; `btrack` is compressed to 4 bits per cell, kept as four bit-planes
+//     pd  step_diag >= step_down and step_diag >= step_right   (diagonal move, :248-252)
+//     pr  step_right >= step_down                               (else: horizontal if set, vertical if not, :253-260)
+//     ho  a horizontal gap was (re)opened at this cell  (gap_size_h[i] reset to 1, :235-239)
+//     vo  a vertical gap was (re)opened at this cell    (gap_size_v[j] reset to 1, :212-218)
 // from which the stored gap length k of the reference's btrack (-ki / +kd) is recovered during the
-// traceback by walking back to the cell where the gap was opened.  Nibbles of one lane's K rows are
-// packed into ceil(K/8) words and stored step-major ([step][word][lane]) so every store is a
-// coalesced 128-byte line.
+// traceback by walking back to the cell where the gap was opened.  Bit k of a plane word belongs to
+// the lane's k-th row; the four words of one (step, lane) are stored as one 16-byte element,
+// step-major ([step][lane]) so every warp store is one coalesced 512-byte run.
+// Per cell: compare+select+add (diagonal), add + VIADDMNMX + compare (each gap direction),
+// max + 2 compares + VIMNMX3 (choice, the -1e8 clamp rides in the 3-input max), 4 predicated ORs.
 #pragma once
 #include <stdint.h>
 
@@ -56,12 +59,42 @@ struct SwArgs {
 
 LK_DEV uint32_t sw_cigar_el(uint32_t op, int32_t len) { return ((uint32_t)len << 4) | op; }
 
+LK_DEV int32_t sw_addmax(int32_t a, int32_t b, int32_t c) {  // max(a + b, c): one VIADDMNMX on sm_100a
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s32(a, b, c);
+#else
+    return a + b > c ? a + b : c;
+#endif
+}
+LK_DEV int32_t sw_max3(int32_t a, int32_t b, int32_t c) {    // one VIMNMX3
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s32(a, b, c);
+#else
+    const int32_t t = a > b ? a : b;
+    return t > c ? t : c;
+#endif
+}
+// H[k] for a warp-uniform runtime k (a switch keeps it to one branch instead of a K-long select chain)
+template <int K>
+LK_DEV int32_t sw_pick(const int32_t (&H)[K], int k) {
+    int32_t v = H[0];
+    switch (k) {
+#define LK_PICK(i) case i: if (i < K) v = H[i < K ? i : 0]; break;
+        LK_PICK(1) LK_PICK(2) LK_PICK(3) LK_PICK(4) LK_PICK(5) LK_PICK(6) LK_PICK(7) LK_PICK(8) LK_PICK(9) LK_PICK(10)
+        LK_PICK(11) LK_PICK(12) LK_PICK(13) LK_PICK(14) LK_PICK(15) LK_PICK(16) LK_PICK(17) LK_PICK(18) LK_PICK(19)
+        LK_PICK(20) LK_PICK(21) LK_PICK(22) LK_PICK(23) LK_PICK(24) LK_PICK(25) LK_PICK(26) LK_PICK(27) LK_PICK(28)
+        LK_PICK(29) LK_PICK(30) LK_PICK(31)
+#undef LK_PICK
+        default: break;
+    }
+    return v;
+}
+
 // number of backtrack words one pair needs (host + device agree on this)
 LK_HD int64_t sw_bt_words(int n, int m, int K) {
     const int band_rows = 32 * K;
     const int n_bands = (n + band_rows - 1) / band_rows;
-    const int W = (K + 7) / 8;
-    return (int64_t)n_bands * (int64_t)(m + 32) * W * 32;
+    return (int64_t)n_bands * (int64_t)(m + 32) * 4 * 32;  // one uint4 of bit-planes per (step, lane)
 }
 
 template <class Wp, int K>
@@ -107,9 +140,9 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
     const bool edge_gaps = (strategy == SW_INDEL || strategy == SW_LEADING_INDEL);  // :146-179
     const int BAND = 32 * K;
     const int n_bands = (n + BAND - 1) / BAND;
-    constexpr int W = (K + 7) / 8;
-    const int64_t band_words = (int64_t)(m + 32) * W * 32;
-    uint32_t *bt = scratch;                                         // [band][step][W][32]
+    static_assert(K <= 32, "one plane bit per row");
+    const int64_t band_words = (int64_t)(m + 32) * 4 * 32;
+    uint32_t *bt = scratch;                                         // [band][step][lane] x uint4 {pd, pr, ho, vo}
     int32_t *bndH = (int32_t *)(scratch + sw_bt_words(n, m, K));    // two boundary rows: H then F
     int32_t *bndF = bndH + (m + 1);
     // best cell of the last column (scan top->bottom with >=, :301-307) and bottom-row summary
@@ -151,34 +184,27 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
             if (active) {
                 const uint32_t ab = w.ldg(alt + c - 1);
                 int32_t hdiag = Hd, hup = Hu, fup = Fu;
-                uint32_t words[W];
-#pragma unroll
-                for (int i = 0; i < W; i++) words[i] = 0u;
+                uint32_t pl_d = 0u, pl_r = 0u, pl_h = 0u, pl_v = 0u;
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const int32_t hold = H[k];
                     const int32_t step_diag = hdiag + ((rb[k] == ab) ? wm : wx);     // :197-202
-                    const int32_t open_v = hup + wo, ext_v = fup + we;               // :210-222
-                    const bool vopen = open_v > ext_v;
-                    const int32_t step_down = vopen ? open_v : ext_v;
-                    const int32_t open_h = hold + wo, ext_h = E[k] + we;             // :232-245
-                    const bool hopen = open_h > ext_h;
-                    const int32_t step_right = hopen ? open_h : ext_h;
-                    uint32_t mv;
-                    int32_t best;
-                    if (step_diag >= step_down && step_diag >= step_right) { mv = 0u; best = step_diag; }  // :248-260
-                    else if (step_right >= step_down) { mv = 1u; best = step_right; }
-                    else { mv = 2u; best = step_down; }
-                    best = best > SW_MATRIX_MIN_CUTOFF ? best : SW_MATRIX_MIN_CUTOFF;
-                    const uint32_t nib = mv | (hopen ? 4u : 0u) | (vopen ? 8u : 0u);
-                    words[k >> 3] |= nib << (4 * (k & 7));
+                    const int32_t ext_v = fup + we;                                  // :210-222
+                    const int32_t step_down = sw_addmax(hup, wo, ext_v);             // max(hup + wo, ext_v)
+                    const int32_t ext_h = E[k] + we;                                 // :232-245
+                    const int32_t step_right = sw_addmax(hold, wo, ext_h);
+                    const int32_t gap = step_right > step_down ? step_right : step_down;
+                    if (step_down != ext_v) pl_v |= 1u << k;    // opened: hup + wo > fup + we
+                    if (step_right != ext_h) pl_h |= 1u << k;
+                    if (step_diag >= gap) pl_d |= 1u << k;       // :248-260 priority diag, right, down
+                    if (step_right >= step_down) pl_r |= 1u << k;
+                    const int32_t best = sw_max3(step_diag, gap, SW_MATRIX_MIN_CUTOFF);
                     E[k] = step_right;
                     H[k] = best;
                     hdiag = hold; hup = best; fup = step_down;
                 }
                 h_last = H[K - 1]; f_last = fup;
-#pragma unroll
-                for (int i = 0; i < W; i++) btb[((int64_t)s * W + i) * 32 + lane] = words[i];
+                w.store4(btb + ((int64_t)s * 32 + lane) * 4, pl_d, pl_r, pl_h, pl_v);
                 if (c == m) {  // this lane's rows of the last column, top -> bottom with >=  (:301-307)
 #pragma unroll
                     for (int k = 0; k < K; k++) {
@@ -187,9 +213,7 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
                     }
                 }
                 if (has_bottom && lane == bottom_lane) {  // bottom row summary (:316-329), see below
-                    int32_t cur = H[0];
-#pragma unroll
-                    for (int k = 1; k < K; k++) cur = (k == bottom_k) ? H[k] : cur;
+                    int32_t cur = sw_pick<K>(H, bottom_k);
                     const int dj = (n > c) ? (n - c) : (c - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
                     if (cur > bot_max || (cur == bot_max && dj < db)) { bot_max = cur; bot_j = c; }
                 }
@@ -236,10 +260,13 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
     }
 
     // ---- traceback (:335-442), warp-cooperative: 32 cells of a run are fetched per round trip -----
-    auto nibble = [&](int i, int j) -> uint32_t {  // backtrack nibble of matrix cell (i, j), 1-based
+    // nibble of matrix cell (i, j), 1-based: bits 0-1 move (0 diagonal, 1 horizontal, 2 vertical), bit 2 ho, bit 3 vo
+    auto nibble = [&](int i, int j) -> uint32_t {
         const int band = (i - 1) / BAND, r = (i - 1) % BAND, ln = r / K, k = r % K;
-        const uint32_t wd = bt[(int64_t)band * band_words + ((int64_t)(j + ln) * W + (k >> 3)) * 32 + ln];
-        return (wd >> (4 * (k & 7))) & 15u;
+        uint32_t pd, pr, ho, vo;
+        w.load4(bt + (int64_t)band * band_words + ((int64_t)(j + ln) * 32 + ln) * 4, pd, pr, ho, vo);
+        const uint32_t mv = ((pd >> k) & 1u) ? 0u : (((pr >> k) & 1u) ? 1u : 2u);
+        return mv | (((ho >> k) & 1u) << 2) | (((vo >> k) & 1u) << 3);
     };
     int n_out = 0;
     bool overflow = false;

@@ -16,6 +16,13 @@ struct SwDevWarp {
     __device__ __forceinline__ int ffs(unsigned v) const { return __ffs((int)v); }
     template <class T> __device__ __forceinline__ T ldg(const T *p) const { return __ldg(p); }
     __device__ __forceinline__ void sync() const { __threadfence_block(); __syncwarp(); }
+    __device__ __forceinline__ void store4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+        *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
+    }
+    __device__ __forceinline__ void load4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        a = v.x; b = v.y; c = v.z; d = v.w;
+    }
 };
 
 template <int K>

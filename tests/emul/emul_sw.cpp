@@ -44,6 +44,8 @@ struct SwEmulWarp {
     int ffs(unsigned v) const { return __builtin_ffs((int)v); }
     template <class T> T ldg(const T *p) const { return *p; }
     void sync() { sh->bar.arrive_and_wait(); }
+    void store4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+    void load4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const { a = p[0]; b = p[1]; c = p[2]; d = p[3]; }
 };
 
 static int choose_k(int n, int force_k) {
