@@ -13,8 +13,8 @@
 //
 // The reference keeps two (n+1)x(m+1) i32 matrices (sw, btrack).  Here nothing of `sw` is stored
 // except the band boundary; `btrack` is compressed to 4 bits per cell, kept as four bit-planes
-//     pd  step_diag >= step_down and step_diag >= step_right   (diagonal move, :248-252)
-//     pr  step_right >= step_down                               (else: horizontal if set, vertical if not, :253-260)
+//     pd  set when the move is NOT diagonal (step_diag < max(step_down, step_right), :248-252)
+//     pr  set when step_right < step_down: vertical; clear: horizontal (:253-260)
 //     ho  a horizontal gap was (re)opened at this cell  (gap_size_h[i] reset to 1, :235-239)
 //     vo  a vertical gap was (re)opened at this cell    (gap_size_v[j] reset to 1, :212-218)
 // from which the stored gap length k of the reference's btrack (-ki / +kd) is recovered during the
@@ -72,6 +72,13 @@ LK_DEV int32_t sw_max3(int32_t a, int32_t b, int32_t c) {    // one VIMNMX3
 #else
     const int32_t t = a > b ? a : b;
     return t > c ? t : c;
+#endif
+}
+LK_DEV uint32_t sw_push_sign(uint32_t plane, int32_t d) {      // (plane << 1) | (d < 0): one SHF
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l((uint32_t)d, plane, 1);
+#else
+    return (plane << 1) | ((uint32_t)d >> 31);
 #endif
 }
 // H[k] for a warp-uniform runtime k (a switch keeps it to one branch instead of a K-long select chain)
@@ -194,10 +201,12 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
                     const int32_t ext_h = E[k] + we;                                 // :232-245
                     const int32_t step_right = sw_addmax(hold, wo, ext_h);
                     const int32_t gap = step_right > step_down ? step_right : step_down;
-                    if (step_down != ext_v) pl_v |= 1u << k;    // opened: hup + wo > fup + we
-                    if (step_right != ext_h) pl_h |= 1u << k;
-                    if (step_diag >= gap) pl_d |= 1u << k;       // :248-260 priority diag, right, down
-                    if (step_right >= step_down) pl_r |= 1u << k;
+                    // each plane shifts in the SIGN BIT of a difference (one funnel shift per bit; the subtractions can
+                    // issue on the otherwise idle FMA pipe): row k ends up at bit K-1-k
+                    pl_v = sw_push_sign(pl_v, ext_v - step_down);      // set: opened (hup + wo > fup + we)
+                    pl_h = sw_push_sign(pl_h, ext_h - step_right);     // set: opened
+                    pl_d = sw_push_sign(pl_d, step_diag - gap);        // set: NOT diagonal (:248-252 wants diag >= both)
+                    pl_r = sw_push_sign(pl_r, step_right - step_down); // set: vertical (right < down), clear: horizontal
                     const int32_t best = sw_max3(step_diag, gap, SW_MATRIX_MIN_CUTOFF);
                     E[k] = step_right;
                     H[k] = best;
@@ -265,8 +274,9 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
         const int band = (i - 1) / BAND, r = (i - 1) % BAND, ln = r / K, k = r % K;
         uint32_t pd, pr, ho, vo;
         w.load4(bt + (int64_t)band * band_words + ((int64_t)(j + ln) * 32 + ln) * 4, pd, pr, ho, vo);
-        const uint32_t mv = ((pd >> k) & 1u) ? 0u : (((pr >> k) & 1u) ? 1u : 2u);
-        return mv | (((ho >> k) & 1u) << 2) | (((vo >> k) & 1u) << 3);
+        const int bit = K - 1 - k;  // planes were filled by shifting left once per row
+        const uint32_t mv = ((pd >> bit) & 1u) ? (((pr >> bit) & 1u) ? 2u : 1u) : 0u;
+        return mv | (((ho >> bit) & 1u) << 2) | (((vo >> bit) & 1u) << 3);
     };
     int n_out = 0;
     bool overflow = false;
