@@ -170,6 +170,27 @@ lk_status lk_sw_align(lk_ctx *ctx, const uint8_t *ref, int64_t ref_len, const ui
                       const lk_sw_params *params, lk_sw_overhang strategy, char *cigar_text, size_t cigar_cap,
                       int32_t *alignment_offset);
 
+/* ---------------------------------------------------------------- haplotype -> reference CIGARs */
+
+/*
+ * Batch form of CigarUtils::calculate_cigar (src/reads/cigar_utils.rs:358-457): per pair the trivial cases
+ * (empty alternate; equal lengths with <= 2 mismatches) are resolved on the host, every other pair is wrapped in
+ * 10 x 'N' (SW_PAD, :10,387-398) and aligned in ONE Smith-Waterman batch on the GPU, then trimmed
+ * (AlignmentUtils::trim_cigar_by_bases), left-aligned (left_align_indels) and given back its leading / trailing
+ * deletions exactly as the reference does.  Results as in lk_sw_batch_host; n_ops[p] = -3 when the reference
+ * returns None (is_s_w_failure, :469-487), -4 where the reference would panic, -2 on capacity.
+ */
+lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                                   const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                                   lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops);
+/* The two host-side halves of the above, usable on their own: returns 1 if the pair needs no alignment. */
+int lk_calculate_cigar_shortcut(const uint8_t *ref, int64_t ref_len, const uint8_t *alt, int64_t alt_len, int32_t max_ops,
+                                uint32_t *out_ops, int32_t *out_n_ops);
+/* From the SW result (BAM-encoded ops + offset) on the 10 x 'N' padded pair to the final CIGAR. */
+lk_status lk_calculate_cigar_finish(const uint8_t *ref, int64_t ref_len, const uint8_t *alt, int64_t alt_len,
+                                    const uint32_t *sw_ops, int32_t sw_n_ops, int32_t sw_offset, int32_t max_ops,
+                                    uint32_t *out_ops, int32_t *out_n_ops);
+
 /* ---------------------------------------------------------------- engine pre/post-ops (host side) */
 
 /* PCRErrorModel (pair_hmm_likelihood_calculation_engine.rs:60-70) */

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "lk_pairhmm_batch_dims", "lk_pairhmm_batch_host", "lk_pairhmm_upload", "lk_pairhmm_run_resident",
     "lk_pairhmm_download", "lk_resident_free", "lk_pairhmm_forward",
     "lk_sw_batch_host", "lk_sw_upload", "lk_sw_run_resident", "lk_sw_download", "lk_sw_align",
+    "lk_calculate_cigar_batch", "lk_calculate_cigar_shortcut", "lk_calculate_cigar_finish",
     "lk_engine_modify_read_qualities", "lk_engine_compute_read_likelihoods",
 ]
 
@@ -122,6 +123,12 @@ def load():
     L.lk_sw_download.argtypes = [vp, vp, u32p, i32p, i32p]
     L.lk_sw_align.restype = C.c_int
     L.lk_sw_align.argtypes = [vp, u8p, C.c_int64, u8p, C.c_int64, sp, C.c_int, C.c_char_p, C.c_size_t, i32p]
+    L.lk_calculate_cigar_batch.restype = C.c_int
+    L.lk_calculate_cigar_batch.argtypes = [vp, C.c_int64, i64p, u8p, i64p, u8p, sp, C.c_int, C.c_int32, u32p, i32p]
+    L.lk_calculate_cigar_shortcut.restype = C.c_int
+    L.lk_calculate_cigar_shortcut.argtypes = [u8p, C.c_int64, u8p, C.c_int64, C.c_int32, u32p, i32p]
+    L.lk_calculate_cigar_finish.restype = C.c_int
+    L.lk_calculate_cigar_finish.argtypes = [u8p, C.c_int64, u8p, C.c_int64, u32p, C.c_int32, C.c_int32, C.c_int32, u32p, i32p]
     ep = C.POINTER(EngineArgs)
     L.lk_engine_modify_read_qualities.restype = C.c_int
     L.lk_engine_modify_read_qualities.argtypes = [ep, C.c_int64, i64p, u8p, u8p, u8p, u8p, u8p, C.c_int]

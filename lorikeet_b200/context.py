@@ -118,6 +118,31 @@ class Context:
                                         alt.size, C.byref(prm), int(strategy), buf, cigar_cap, C.byref(off)))
         return off.value, buf.value.decode()
 
+    def calculate_cigar_batch(self, ref_off, refs, alt_off, alts, params, strategy="InDel", max_ops=64):
+        """CigarUtils::calculate_cigar (reads/cigar_utils.rs:358-457) for a batch: list of CIGAR strings (None where the
+        reference returns None)."""
+        from .batch import _u8, _i64
+        ref_off, alt_off, refs, alts = _i64(ref_off), _i64(alt_off), _u8(refs), _u8(alts)
+        n = len(ref_off) - 1
+        if isinstance(strategy, str):
+            strategy = SW_STRATEGY[strategy]
+        prm = _lib.SwParams(*[int(x) for x in params])
+        ops = np.zeros((n, max_ops), dtype=np.uint32)
+        n_ops = np.zeros(n, dtype=np.int32)
+        self._check(self._L.lk_calculate_cigar_batch(self._h, n, ref_off.ctypes.data_as(_lib.i64p), refs.ctypes.data_as(_lib.u8p),
+                                                     alt_off.ctypes.data_as(_lib.i64p), alts.ctypes.data_as(_lib.u8p), C.byref(prm),
+                                                     int(strategy), int(max_ops), ops.ctypes.data_as(_lib.u32p),
+                                                     n_ops.ctypes.data_as(_lib.i32p)))
+        out = []
+        for i in range(n):
+            if n_ops[i] == -3:
+                out.append(None)
+            elif n_ops[i] < 0:
+                raise LorikeetError(_lib.LK_ERR_INVALID, "calculate_cigar failed for pair %d (code %d)" % (i, n_ops[i]))
+            else:
+                out.append(cigar_to_string(ops[i, :n_ops[i]]))
+        return out
+
     def sw_upload(self, ref_off, refs, alt_off, alts, params, strategy, max_ops=64):
         return ResidentSw(self, ref_off, refs, alt_off, alts, params, strategy, max_ops)
 

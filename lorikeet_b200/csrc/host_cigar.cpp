@@ -1,0 +1,346 @@
+// host_cigar.cpp — CigarUtils::calculate_cigar around the batched Smith-Waterman kernel.
+//
+// Reference:
+//   CigarUtils::calculate_cigar / is_s_w_failure      src/reads/cigar_utils.rs:358-487 (SW_PAD :10)
+//   AlignmentUtils::trim_cigar_by_bases / trim_cigar   src/reads/alignment_utils.rs:321-386
+//   AlignmentUtils::left_align_indels                  src/reads/alignment_utils.rs:425-555
+//   AlignmentUtils::normalize_alleles                  src/reads/alignment_utils.rs:583-680
+//   CigarBuilder                                       src/reads/cigar_builder.rs
+//
+// The O(n*m) part (one SW per haplotype, <= 128 per region: read_threading_assembler.rs:787,827) runs on the GPU as
+// ONE lk_sw batch; what remains here is O(n+m) CIGAR surgery per pair, kept on the host like the reference.
+// CIGAR elements are BAM-encoded u32 (len << 4 | op; M=0 I=1 D=2 N=3 S=4 H=5 P=6 '='=7 X=8).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "../../include/lorikeet_b200.h"
+#include "lk_api_internal.h"
+
+namespace {
+
+enum Op : uint32_t { M = 0, I = 1, D = 2, N = 3, S = 4, H = 5, P = 6, EQ = 7, X = 8 };
+constexpr int kSwPad = 10;  // cigar_utils.rs:10
+
+inline uint32_t el(uint32_t op, uint32_t len) { return (len << 4) | op; }
+inline uint32_t op_of(uint32_t e) { return e & 0xF; }
+inline uint32_t len_of(uint32_t e) { return e >> 4; }
+inline bool is_clipping(uint32_t e) { return op_of(e) == S || op_of(e) == H; }
+inline bool is_indel(uint32_t e) { return op_of(e) == I || op_of(e) == D; }
+inline bool is_alignment(uint32_t e) { return op_of(e) == M || op_of(e) == EQ || op_of(e) == X; }
+inline bool consumes_read(uint32_t e) { const uint32_t o = op_of(e); return o == M || o == I || o == S || o == EQ || o == X; }
+inline bool consumes_ref(uint32_t e) { const uint32_t o = op_of(e); return o == M || o == D || o == N || o == EQ || o == X; }
+inline uint32_t len_on_read(uint32_t e) { return consumes_read(e) ? len_of(e) : 0; }
+inline uint32_t len_on_ref(uint32_t e) { return consumes_ref(e) ? len_of(e) : 0; }
+
+struct BuilderResult {
+    std::vector<uint32_t> cigar;
+    uint32_t leading_deletion_bases_removed = 0, trailing_deletion_bases_removed = 0;
+    bool ok = true;
+};
+
+// CigarBuilder (cigar_builder.rs), remove_deletions_at_ends as a constructor flag
+class CigarBuilder {
+  public:
+    explicit CigarBuilder(bool remove_deletions_at_ends) : remove_(remove_deletions_at_ends) {}
+
+    bool add(uint32_t e) {
+        if (len_of(e) == 0) return true;
+        if (remove_ && op_of(e) == D && leading_position()) {
+            leading_removed_ += len_of(e);
+            return true;
+        }
+        if (!advance_section(e)) return false;
+        if (has_last_ && op_of(e) == op_of(last_)) {  // same type as the last operator: merge into the last element
+            // (combine_cigar_operators(..).unwrap_or(old): if the vector's tail is of another type the element is dropped)
+            if (op_of(els_.back()) == op_of(e)) els_.back() = el(op_of(e), len_of(e) + len_of(els_.back()));
+            return true;
+        }
+        if (!has_last_) { push(e); return true; }
+        if (is_clipping(e)) {
+            const size_t n = els_.size();
+            if (remove_ && !consumes_read(last_) && !is_clipping(last_)) {  // trailing deletion before the clip
+                trailing_removed_ += len_of(els_[n - 1]);
+                els_[n - 1] = e;
+                last_ = e;
+            } else if (remove_ && last_two_del_ins()) {
+                trailing_removed_ += len_of(els_[n - 2]);
+                els_[n - 2] = els_[n - 1];
+                els_[n - 1] = e;  // last_operator deliberately left as is (as in the reference)
+            } else {
+                push(e);
+            }
+            return true;
+        }
+        if (op_of(e) == D && op_of(last_) == I) {  // keep D before I
+            const size_t n = els_.size();
+            if (n > 1 && op_of(els_[n - 2]) == D) els_[n - 2] = el(D, len_of(els_[n - 2]) + len_of(e));
+            else els_.insert(els_.begin() + (long)(n - 1), e);
+            return true;
+        }
+        push(e);
+        return true;
+    }
+
+    BuilderResult make_and_record_deletions_removed_result() {
+        BuilderResult r;
+        r.leading_deletion_bases_removed = leading_removed_;
+        if (error_ || !has_last_) { r.ok = false; return r; }
+        if (section_ == LeftSoftClip && op_of(els_[0]) == S) { r.ok = false; return r; }  // completely soft clipped
+        uint32_t in_make = 0;
+        if (remove_ && op_of(last_) == D) {
+            in_make = len_of(els_.back());
+            els_.pop_back();
+        } else if (remove_ && last_two_del_ins()) {
+            in_make = len_of(els_[els_.size() - 2]);
+            els_.erase(els_.end() - 2);
+        }
+        if (els_.empty()) { r.ok = false; return r; }  // make(allow_empty = false)
+        r.cigar = els_;
+        r.trailing_deletion_bases_removed = trailing_removed_ + in_make;
+        return r;
+    }
+
+  private:
+    enum Section { LeftHardClip, LeftSoftClip, Middle, RightSoftClip, RightHardClip };
+    bool remove_;
+    std::vector<uint32_t> els_;
+    uint32_t last_ = 0;
+    bool has_last_ = false, error_ = false;
+    Section section_ = LeftHardClip;
+    uint32_t leading_removed_ = 0, trailing_removed_ = 0;
+
+    void push(uint32_t e) { els_.push_back(e); last_ = e; has_last_ = true; }
+    bool leading_position() const {  // a deletion here would lead the alignment
+        if (!has_last_) return true;
+        if (is_clipping(last_)) return true;
+        if (op_of(last_) == I) return els_.size() == 1 || is_clipping(els_[els_.size() - 2]);
+        return false;
+    }
+    bool last_two_del_ins() const {
+        return has_last_ && els_.size() > 1 && op_of(last_) == I && op_of(els_[els_.size() - 2]) == D;
+    }
+    bool advance_section(uint32_t e) {
+        if (op_of(e) == H) {
+            if (section_ == LeftSoftClip || section_ == Middle || section_ == RightSoftClip) section_ = RightHardClip;
+        } else if (op_of(e) == S) {
+            if (section_ == RightHardClip) { error_ = true; return false; }
+            if (section_ == LeftHardClip) section_ = LeftSoftClip;
+            else if (section_ == Middle) section_ = RightSoftClip;
+        } else {
+            if (section_ == RightSoftClip || section_ == RightHardClip) { error_ = true; return false; }
+            if (section_ == LeftHardClip || section_ == LeftSoftClip) section_ = Middle;
+        }
+        return true;
+    }
+};
+
+// AlignmentUtils::trim_cigar(cigar, start, end, by_reference = false)  (alignment_utils.rs:334-386)
+BuilderResult trim_cigar_by_bases(const std::vector<uint32_t> &cigar, uint32_t start, uint32_t end) {
+    BuilderResult bad;
+    bad.ok = false;
+    if (end < start) return bad;
+    CigarBuilder nb(true);
+    uint32_t element_start, element_end = 0;
+    for (uint32_t e : cigar) {
+        element_start = element_end;
+        element_end = element_start + len_on_read(e);
+        if (element_end < start || (element_end == start && element_start < start)) continue;
+        if (element_start > end && element_end > end + 1) break;
+        const uint32_t overlap = (element_end == element_start) ? len_of(e)
+                                                                 : std::min(end + 1, element_end) - std::max(start, element_start);
+        if (!nb.add(el(op_of(e), overlap))) return bad;
+    }
+    if (element_end < end) return bad;  // "Cigar elements don't reach end position"
+    return nb.make_and_record_deletions_removed_result();
+}
+
+struct Range { int start, end; int len() const { return end > start ? end - start : 0; } };
+
+// AlignmentUtils::normalize_alleles for two sequences, trim = true (alignment_utils.rs:583-640)
+bool normalize_alleles(const uint8_t *s0, int n0, const uint8_t *s1, int n1, Range &b0, Range &b1, int max_shift, int &start_shift,
+                       int &end_shift) {
+    if (max_shift > b0.start || max_shift > b1.start) return false;
+    auto at = [&](const uint8_t *s, int n, int i, bool &ok) -> uint8_t { if (i < 0 || i >= n) { ok = false; return 0; } return s[i]; };
+    bool ok = true;
+    start_shift = 0; end_shift = 0;
+    int min_size = std::min(b0.len(), b1.len());
+    while (min_size > 0 && at(s0, n0, b0.end - 1, ok) == at(s1, n1, b1.end - 1, ok) && ok) {
+        b0.end--; b1.end--; min_size--; end_shift++;
+    }
+    while (ok && min_size > 0 && at(s0, n0, b0.start, ok) == at(s1, n1, b1.start, ok) && ok) {
+        b0.start++; b1.start++; min_size--; start_shift--;
+    }
+    while (ok && start_shift < max_shift && at(s0, n0, b0.start - 1, ok) == at(s1, n1, b1.start - 1, ok) && ok &&
+           at(s0, n0, b0.end - 1, ok) == at(s1, n1, b1.end - 1, ok) && ok) {
+        b0.start--; b0.end--; b1.start--; b1.end--; start_shift++; end_shift++;
+    }
+    return ok;  // an out-of-range access is a panic in the reference
+}
+
+// AlignmentUtils::left_align_indels (alignment_utils.rs:425-555)
+BuilderResult left_align_indels(const std::vector<uint32_t> &cigar, const uint8_t *ref, int ref_len, const uint8_t *read, int read_len,
+                                uint32_t read_start) {
+    BuilderResult r;
+    bool any_indel = false;
+    for (uint32_t e : cigar) any_indel |= is_indel(e);
+    if (!any_indel) { r.cigar = cigar; return r; }
+    BuilderResult bad;
+    bad.ok = false;
+    int last_indel = 0;
+    for (int n = 0; n < (int)cigar.size(); n++) if (is_indel(cigar[(size_t)n])) last_indel = n;
+    uint32_t necessary_ref = read_start;
+    for (int n = 0; n <= last_indel; n++) necessary_ref += len_on_ref(cigar[(size_t)n]);
+    if (necessary_ref > (uint32_t)ref_len) return bad;  // "Read goes past end of reference"
+    std::vector<uint32_t> rtl;
+    uint32_t ref_length = 0;
+    for (uint32_t e : cigar) ref_length += len_on_ref(e);
+    Range ref_rng{ (int)(read_start + ref_length), (int)(read_start + ref_length) };
+    Range read_rng{ read_len, read_len };
+    for (int n = (int)cigar.size() - 1; n >= 0; n--) {
+        const uint32_t e = cigar[(size_t)n];
+        if (is_indel(e)) {
+            ref_rng.start -= (int)len_on_ref(e);
+            read_rng.start -= (int)len_on_read(e);
+        } else if (ref_rng.len() == 0 && read_rng.len() == 0) {
+            ref_rng.start -= (int)len_on_ref(e); read_rng.start -= (int)len_on_read(e);
+            ref_rng.end -= (int)len_on_ref(e); read_rng.end -= (int)len_on_read(e);
+            rtl.push_back(e);
+        } else {
+            const int max_shift = is_alignment(e) ? (int)len_of(e) : 0;
+            int s0, s1;
+            if (!normalize_alleles(ref, ref_len, read, read_len, ref_rng, read_rng, max_shift, s0, s1)) return bad;
+            rtl.push_back(el(M, (uint32_t)s1));
+            const bool emit_indel = n == 0 || s0 < max_shift || !is_alignment(e);
+            const int new_match_left = s0 < 0 ? -s0 : 0;
+            const int remaining_left = s0 < 0 ? (int)len_of(e) : (int)len_of(e) - s0;
+            if (emit_indel) {
+                rtl.push_back(el(D, (uint32_t)ref_rng.len()));
+                rtl.push_back(el(I, (uint32_t)read_rng.len()));
+                ref_rng.end -= ref_rng.len();
+                read_rng.end -= read_rng.len();
+                const int dref = new_match_left + (consumes_ref(e) ? remaining_left : 0);
+                const int dread = new_match_left + (consumes_read(e) ? remaining_left : 0);
+                ref_rng.start -= dref; ref_rng.end -= dref;
+                read_rng.start -= dread; read_rng.end -= dread;
+            }
+            rtl.push_back(el(M, (uint32_t)new_match_left));
+            rtl.push_back(el(op_of(e), (uint32_t)remaining_left));
+        }
+    }
+    rtl.push_back(el(D, (uint32_t)ref_rng.len()));
+    rtl.push_back(el(I, (uint32_t)read_rng.len()));
+    if (read_rng.start != 0) return bad;  // "Given cigar does not account for all bases of the read"
+    CigarBuilder cb(true);
+    for (auto it = rtl.rbegin(); it != rtl.rend(); ++it)
+        if (!cb.add(*it)) return bad;
+    return cb.make_and_record_deletions_removed_result();
+}
+
+int write_ops(const std::vector<uint32_t> &c, int32_t max_ops, uint32_t *out) {
+    if ((int)c.size() > max_ops) return -2;
+    for (size_t i = 0; i < c.size(); i++) out[i] = c[i];
+    return (int)c.size();
+}
+
+}  // namespace
+
+// First half of calculate_cigar (cigar_utils.rs:365-385): cases that need no alignment.  Returns 1 and fills the
+// result if resolved, 0 if the padded pair has to be aligned.
+extern "C" int lk_calculate_cigar_shortcut(const uint8_t *ref, int64_t ref_len, const uint8_t *alt, int64_t alt_len, int32_t max_ops,
+                                           uint32_t *out_ops, int32_t *out_n_ops) {
+    if (alt_len == 0) {  // "horrible edge case from the unit tests, where this path has no bases"
+        if (max_ops < 1) { *out_n_ops = -2; return 1; }
+        out_ops[0] = el(D, (uint32_t)ref_len);
+        *out_n_ops = 1;
+        return 1;
+    }
+    if (alt_len == ref_len) {
+        int64_t mism = 0;
+        for (int64_t i = 0; i < ref_len && mism <= 2; i++) mism += alt[i] != ref[i];
+        if (mism <= 2) {
+            if (max_ops < 1) { *out_n_ops = -2; return 1; }
+            out_ops[0] = el(M, (uint32_t)ref_len);
+            *out_n_ops = 1;
+            return 1;
+        }
+    }
+    return 0;
+}
+
+// Second half (cigar_utils.rs:399-457): from the SW result on the 10xN-padded pair to the final CIGAR.
+// out_n_ops: >= 0 number of elements; -2 capacity; -3 the reference returns None (is_s_w_failure); -4 the reference would panic.
+extern "C" lk_status lk_calculate_cigar_finish(const uint8_t *ref, int64_t ref_len, const uint8_t *alt, int64_t alt_len,
+                                               const uint32_t *sw_ops, int32_t sw_n_ops, int32_t sw_offset, int32_t max_ops,
+                                               uint32_t *out_ops, int32_t *out_n_ops) {
+    if (!out_n_ops || (sw_n_ops > 0 && !sw_ops) || !out_ops) return LK_ERR_INVALID;
+    if (sw_n_ops < 0) { *out_n_ops = -4; return LK_OK; }
+    // is_s_w_failure (:469-487)
+    if (sw_offset > 0) { *out_n_ops = -3; return LK_OK; }
+    for (int i = 0; i < sw_n_ops; i++)
+        if (op_of(sw_ops[i]) == S) { *out_n_ops = -3; return LK_OK; }
+    const std::vector<uint32_t> aligned(sw_ops, sw_ops + sw_n_ops);
+    const int64_t padded_path_len = alt_len + 2 * kSwPad;
+    BuilderResult trimmed = trim_cigar_by_bases(aligned, (uint32_t)kSwPad, (uint32_t)(padded_path_len - kSwPad - 1));
+    if (!trimmed.ok) { *out_n_ops = -4; return LK_OK; }
+    std::vector<uint32_t> non_standard = trimmed.cigar;
+    if (trimmed.trailing_deletion_bases_removed > 0) non_standard.push_back(el(D, trimmed.trailing_deletion_bases_removed));
+    BuilderResult la = left_align_indels(non_standard, ref, (int)ref_len, alt, (int)alt_len, trimmed.leading_deletion_bases_removed);
+    if (!la.ok) { *out_n_ops = -4; return LK_OK; }
+    const uint32_t lead = trimmed.leading_deletion_bases_removed + la.leading_deletion_bases_removed;
+    const uint32_t trail = la.trailing_deletion_bases_removed;
+    std::vector<uint32_t> result;
+    if (lead > 0) result.push_back(el(D, lead));
+    result.insert(result.end(), la.cigar.begin(), la.cigar.end());
+    if (trail > 0) result.push_back(el(D, trail));
+    *out_n_ops = write_ops(result, max_ops, out_ops);
+    return LK_OK;
+}
+
+// CigarUtils::calculate_cigar for a batch of (reference, alternate) pairs: shortcuts on the host, every remaining pair
+// padded with 10 x 'N' and aligned in ONE lk_sw_batch_host call, CIGAR surgery on the host.
+extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                                              const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                                              lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (n_pairs < 0 || !params || max_ops < 1) return lk_fail(ctx, LK_ERR_INVALID, "bad calculate_cigar arguments");
+    if (n_pairs == 0) return LK_OK;
+    if (!ref_off || !alt_off || !cigar_ops || !n_ops) return lk_fail(ctx, LK_ERR_INVALID, "null calculate_cigar arrays");
+    std::vector<int64_t> todo;
+    for (int64_t p = 0; p < n_pairs; p++) {
+        const int64_t rl = ref_off[p + 1] - ref_off[p], al = alt_off[p + 1] - alt_off[p];
+        if (rl < 0 || al < 0) return lk_fail(ctx, LK_ERR_INVALID, "decreasing offsets");
+        if (!lk_calculate_cigar_shortcut(refs + ref_off[p], rl, alts + alt_off[p], al, max_ops, cigar_ops + p * max_ops, &n_ops[p]))
+            todo.push_back(p);
+    }
+    if (todo.empty()) return LK_OK;
+    // padded copies (cigar_utils.rs:387-398)
+    std::vector<int64_t> pro(todo.size() + 1, 0), pao(todo.size() + 1, 0);
+    for (size_t i = 0; i < todo.size(); i++) {
+        const int64_t p = todo[i];
+        pro[i + 1] = pro[i] + (ref_off[p + 1] - ref_off[p]) + 2 * kSwPad;
+        pao[i + 1] = pao[i] + (alt_off[p + 1] - alt_off[p]) + 2 * kSwPad;
+    }
+    std::vector<uint8_t> prefs((size_t)pro.back(), 'N'), palts((size_t)pao.back(), 'N');
+    int64_t sw_max_ops = 8;
+    for (size_t i = 0; i < todo.size(); i++) {
+        const int64_t p = todo[i];
+        memcpy(prefs.data() + pro[i] + kSwPad, refs + ref_off[p], (size_t)(ref_off[p + 1] - ref_off[p]));
+        memcpy(palts.data() + pao[i] + kSwPad, alts + alt_off[p], (size_t)(alt_off[p + 1] - alt_off[p]));
+        sw_max_ops = std::max<int64_t>(sw_max_ops, max_ops + 8);
+    }
+    std::vector<uint32_t> sw_ops(todo.size() * (size_t)sw_max_ops);
+    std::vector<int32_t> sw_n(todo.size()), sw_off(todo.size());
+    lk_status st = lk_sw_batch_host(ctx, (int64_t)todo.size(), pro.data(), prefs.data(), pao.data(), palts.data(), params, strategy,
+                                    (int32_t)sw_max_ops, sw_ops.data(), sw_n.data(), sw_off.data());
+    if (st != LK_OK) return st;
+    for (size_t i = 0; i < todo.size(); i++) {
+        const int64_t p = todo[i];
+        if (sw_n[i] == -2) { n_ops[p] = -2; continue; }
+        st = lk_calculate_cigar_finish(refs + ref_off[p], ref_off[p + 1] - ref_off[p], alts + alt_off[p], alt_off[p + 1] - alt_off[p],
+                                       sw_ops.data() + i * (size_t)sw_max_ops, sw_n[i], sw_off[i], max_ops, cigar_ops + p * max_ops,
+                                       &n_ops[p]);
+        if (st != LK_OK) return lk_fail(ctx, st, "calculate_cigar_finish failed");
+    }
+    return LK_OK;
+}
