@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "PairHMM GCUPS (read-bp x hap-bp / s)"
 UNIT = "GCUPS"
 FLOP_PER_CELL = 12  # pair_hmm.rs:575-591: M = 4 mul + 2 add, I = 2 mul + 1 add, D = 2 mul + 1 add
+NCU_DRAM_BYTES_PER_REGION = 65.4e3  # ncu: 62.9 MB read + 2.5 MB written by pairhmm_fast_kernel over 1000 regions (profiles/)
 
 
 def workload_name(regions):
@@ -109,6 +110,32 @@ def cpu_baseline_run(batch, n_regions_sample, native=True):
     return sample.n_cells / dt / 1e9, cores, dt, sample
 
 
+def run_extras(ctx):
+    """Side measurements of BASELINE.json's other configs (kernel-resident, best of 3; NOT the bench metric)."""
+    from lorikeet_b200 import synth
+    out = {}
+    try:
+        ro, refs, ao, alts = synth.sw_pairs(100000)  # cfg4: 100k pairs, 500 bp + 10xN pads, NEW_SW_PARAMETERS, SoftClip
+        res = ctx.sw_upload(ro, refs, ao, alts, [200, -150, -260, -11], "SoftClip", max_ops=64)
+        res.run()
+        ms = min(res.run() for _ in range(3))
+        out["cfg4_smith_waterman"] = {"pairs": 100000, "cells": res.n_cells, "ms": ms, "gcups": res.n_cells / ms / 1e6,
+                                      "note": "fill + in-kernel traceback, CIGARs bit-exact vs oracle (tests/test_gpu_sw.py)"}
+        res.free()
+        b = synth.pairhmm_regions(96, **synth.CFG3)  # cfg3 slice: 96 of 2000 regions (8 reads x 10 kbp, 4 haps x 12 kbp)
+        res = ctx.pairhmm_upload(b)
+        res.run()
+        ms = min(res.run() for _ in range(2))
+        _, flags = res.download(want_flags=True)
+        out["cfg3_long_reads_slice"] = {"regions": 96, "cells": res.n_cells, "ms": ms, "gcups": res.n_cells / ms / 1e6,
+                                        "pairs_redone_in_f64": int((flags & 1).sum()),
+                                        "note": "fp32 band kernel with per-lane block floating point"}
+        res.free()
+    except Exception as e:  # side measurements must never break the bench line
+        out["error"] = str(e)
+    return out
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU algorithm (oracle port; the Rust original cannot be built here)."""
     if rank != 0:
@@ -156,6 +183,7 @@ def main():
     ap.add_argument("--ref-sample-regions", type=int, default=192, help="regions per step of the reference arm")
     ap.add_argument("--cpu-sample-regions", type=int, default=256, help="regions of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the SW (cfg4) and long-read (cfg3 slice) side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -281,9 +309,13 @@ def main():
         achieved = FLOP_PER_CELL * cells / (avg_fast_ms * 1e-3) / 1e12
         hbm = (peaks or {}).get("hbm_gbs", 6650.0)
         alg_bytes = h2d + out_host.nbytes
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
+        # (profiles/r01_pairhmm_fast_k19_scaledhat_ncu_details.txt: dram read+write of a 1000-region launch), scaled to
+        # this launch's region count; ncu itself is never run inside the bench
+        traffic = NCU_DRAM_BYTES_PER_REGION * args.regions
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": peak_derived, "unit": "TFLOP/s", "frac": achieved / peak_derived,
-            "traffic": None,
+            "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch set (ncu capture, scaled by regions)",
             "peak_source": "SMs x 128 lanes x 2 flop x sm_max_mhz of MEASURED_PEAKS.json" if peaks else
                            "SMs x 128 x 2 x 1965 MHz (fallback: MEASURED_PEAKS.json absent)",
             "peak_fma_microbench": fma_measured, "frac_of_fma_microbench": achieved / fma_measured if fma_measured else None,
@@ -298,6 +330,9 @@ def main():
             v, cores, dt, sample = cpu_baseline_run(batch, args.cpu_sample_regions)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "first %d regions of the same batch (%.3e cells, %.1f s)" % (sample.n_regions, sample.n_cells, dt)}
+        extras = None
+        if world == 1 and not args.no_extras:
+            extras = run_extras(ctx)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -314,6 +349,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall,
+            "other_configs": extras,
         }
         print(json.dumps(line), flush=True)
     res.free()

@@ -269,24 +269,22 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
 LK_UNROLL_N(LK_FAST_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
             const uint32_t hrep = w.ldg(hp + s);
-            // ---- M' and D' (descending so that row k-1 still holds column c-1) ----
+            // ---- one column of the strip, rows top to bottom.  Row k reads row k-1 of the previous column (pm, pi, pd)
+            // and, for I', row k-1 of this column (im, ii).  Written in this order the serial I' chain (one FFMA per row)
+            // is spread evenly between the independent M'/D' work of the rows instead of being bunched at the end. ----
+            {
+                float pm = Md + kinit, pi = Id, pd = Dd, im = Mu, ii = Iu;  // start lanes: Md = 0, b'0 = c'0 = 0 -> mm = kinit
 #pragma unroll
-            for (int k = K - 1; k >= 0; k--) {
-                float mm;
-                if (k == 0) {
-                    mm = fmaf(Id, cb[0], Md + kinit);  // start lanes: Md = 0 and b' = c' = 0, so mm = kinit
-                    mm = fmaf(Dd, cc[0], mm);
-                } else {
-                    mm = fmaf(I[k - 1], cb[k], M[k - 1]);
-                    mm = fmaf(D[k - 1], cc[k], mm);
+                for (int k = 0; k < K; k++) {
+                    const float om = M[k], oi = I[k], od = D[k];
+                    float mm = fmaf(pi, cb[k], pm);
+                    mm = fmaf(pd, cc[k], mm);
+                    D[k] = fmaf(od, VARGCP ? cf[k] : cf[0], om);
+                    M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
+                    I[k] = fmaf(ii, ce[k], im);
+                    pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
                 }
-                D[k] = fmaf(D[k], VARGCP ? cf[k] : cf[0], M[k]);
-                M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
             }
-            // ---- I' (ascending: same column, row above) ----
-            I[0] = fmaf(Iu, ce[0], Mu);
-#pragma unroll
-            for (int k = 1; k < K; k++) I[k] = fmaf(I[k - 1], ce[k], M[k - 1]);
             if (s <= s_last) {
                 acc = fmaf(M[K - 1], wM, acc);
                 acc = fmaf(I[K - 1], wI, acc);
@@ -464,22 +462,22 @@ LK_UNROLL_N(LK_FAST_UNROLL)
             }
             const float al = pow2i(xi - xi_up);
             Mu *= al; Iu *= al; Du *= al;
+            // ---- one column of the strip, rows top to bottom.  Row k reads row k-1 of the previous column (pm, pi, pd)
+            // and, for I', row k-1 of this column (im, ii).  Written in this order the serial I' chain (one FFMA per row)
+            // is spread evenly between the independent M'/D' work of the rows instead of being bunched at the end. ----
+            {
+                float pm = Md + kinit, pi = Id, pd = Dd, im = Mu, ii = Iu;  // start lanes: Md = 0, b'0 = c'0 = 0 -> mm = kinit
 #pragma unroll
-            for (int k = K - 1; k >= 0; k--) {
-                float mm;
-                if (k == 0) {
-                    mm = fmaf(Id, cb[0], Md + kinit);
-                    mm = fmaf(Dd, cc[0], mm);
-                } else {
-                    mm = fmaf(I[k - 1], cb[k], M[k - 1]);
-                    mm = fmaf(D[k - 1], cc[k], mm);
+                for (int k = 0; k < K; k++) {
+                    const float om = M[k], oi = I[k], od = D[k];
+                    float mm = fmaf(pi, cb[k], pm);
+                    mm = fmaf(pd, cc[k], mm);
+                    D[k] = fmaf(od, cf, om);
+                    M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
+                    I[k] = fmaf(ii, ce[k], im);
+                    pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
                 }
-                D[k] = fmaf(D[k], cf, M[k]);
-                M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
             }
-            I[0] = fmaf(Iu, ce[0], Mu);
-#pragma unroll
-            for (int k = 1; k < K; k++) I[k] = fmaf(I[k - 1], ce[k], M[k - 1]);
             if (s <= s_last) {
                 acc = fmaf(M[K - 1], wM, acc);
                 acc = fmaf(I[K - 1], wI, acc);
