@@ -331,6 +331,7 @@ static void fill_args(lk_ctx *ctx, lk_resident *R, PairHmmArgs &A) {
     A.band_scratch = R->band_scratch.p; A.band_scratch_stride = R->band_stride;
     A.gcp_constant = R->gcp_constant;
     A.mismatch_div = ctx->tristate ? 3.0f : 1.0f;
+    A.cf_uniform = (float)std::pow(10.0, (double)R->gcp_constant / -10.0);
 }
 
 // Queue every kernel of one staged workspace on st (no synchronisation).

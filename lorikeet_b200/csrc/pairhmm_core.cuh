@@ -120,6 +120,9 @@ struct PairHmmArgs {
     int32_t *rescue_cursor;
     uint8_t gcp_constant;
     float mismatch_div;            // 3 (tristate, pair_hmm.rs:53) or 1
+    float cf_uniform;              // 10^(-gcp_constant/10) = tII = tDD when gcp is uniform.  Lives in the kernel-parameter
+                                   // constant bank so FFMAs can take it as a c[][] operand: a 3-register-source FFMA issues at
+                                   // only ~2/3 rate on B200 (tools/microbench/ffma3.cu), a 2-register one at full rate.
 };
 
 LK_DEV int lk_popc(unsigned v) {
@@ -279,7 +282,7 @@ LK_UNROLL_N(LK_FAST_UNROLL)
                     const float om = M[k], oi = I[k], od = D[k];
                     float mm = fmaf(pi, cb[k], pm);
                     mm = fmaf(pd, cc[k], mm);
-                    D[k] = fmaf(od, VARGCP ? cf[k] : cf[0], om);
+                    D[k] = fmaf(od, VARGCP ? cf[k] : A.cf_uniform, om);
                     M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
                     I[k] = fmaf(ii, ce[k], im);
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
@@ -366,7 +369,6 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
     const int64_t W1 = (int64_t)H + 1;
     Bnd4 *bnd[2] = { scratch, scratch + W1 };
     const uint32_t *hp = A.henc + A.henc_off[h] - 1 - lane;  // hp[s] = encoded column (s - lane)
-    const float cf = A.qerr_f[A.gcp_constant];
     auto a_tilde = [&](int i) -> double {
         if (i < 1 || i >= R) return 1.0;
         return (1.0 - A.qerr_d[A.read_qual[ro + i]]) * m2m_lookup(A.m2m, A.read_ins[ro + i], A.read_del[ro + i]);
@@ -472,7 +474,7 @@ LK_UNROLL_N(LK_FAST_UNROLL)
                     const float om = M[k], oi = I[k], od = D[k];
                     float mm = fmaf(pi, cb[k], pm);
                     mm = fmaf(pd, cc[k], mm);
-                    D[k] = fmaf(od, cf, om);
+                    D[k] = fmaf(od, A.cf_uniform, om);
                     M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
                     I[k] = fmaf(ii, ce[k], im);
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];

@@ -156,6 +156,7 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
     A.scratch = scratch.data(); A.scratch_stride = (int64_t)scratch.size();
     A.gcp_constant = gcp_const;
     A.mismatch_div = use_tristate ? 3.0f : 1.0f;
+    A.cf_uniform = T.qerr_f[gcp_const];
     if (force_f64) {
         for (int64_t r = 0; r < n_reads; r++) {
             const int32_t g = P.read_region[(size_t)r];
