@@ -5,9 +5,11 @@
 #define LK_PLAIN_THREADS 128
 #define LK_PLAIN_K 4
 // band path (fp32, reads longer than 32 * max fast K): rows per lane, threads per block, min blocks per SM
+#ifndef LK_BAND_K
 #define LK_BAND_K 12
-#define LK_BAND_THREADS 128
 #define LK_BAND_MINB 3
+#endif
+#define LK_BAND_THREADS 128
 
 // Rows per lane (K) the fp32 fast kernel is instantiated for, with the launch-bounds
 // "min blocks per SM" that sets its register budget (128 threads/block: 4 -> 128 regs, 3 -> 168,

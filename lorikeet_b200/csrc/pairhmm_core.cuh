@@ -438,13 +438,24 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         const bool feeds = (lane == 0) && (band > 0);
         const bool writes = !last_band && (lane == lanes - 1);
         if (writes) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = 0.f; z.xi = 0; bout[0] = z; }
+        Bnd4 cur_b;  // boundary element of the column lane 0 works on next
+        cur_b.m = 0.f; cur_b.i = 0.f; cur_b.d = 0.f; cur_b.xi = 0;
+        if (band > 0) cur_b = bin[1 <= H ? 1 : H];
 
 LK_UNROLL_N(LK_FAST_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
             const uint32_t hrep = w.ldg(hp + s);
-            if (feeds) {  // row above = last row of the previous band
-                if (s <= H) { const Bnd4 v = bin[s]; Mu = v.m; Iu = v.i; Du = v.d; xi_up = v.xi; w.prefetch(bin + (s + 24 <= H ? s + 24 : H)); }
-                else { Mu = 0.f; Iu = 0.f; Du = 0.f; }
+            // row above lane 0 = last row of the previous band.  Every lane reads the same element (one broadcast
+            // transaction, no divergence) one step AHEAD of its use, so the L1/L2 latency hides behind a whole step.
+            if (band > 0) {
+                const Bnd4 v = cur_b;
+                cur_b = bin[s + 1 <= H ? s + 1 : H];
+                w.prefetch(bin + (s + 32 <= H ? s + 32 : H));
+                if (feeds) {
+                    const bool in = s <= H;
+                    Mu = in ? v.m : 0.f; Iu = in ? v.i : 0.f; Du = in ? v.d : 0.f;
+                    xi_up = in ? v.xi : xi_up;
+                }
             }
             // ---- bring what the row above sent into my exponent ----
             // A lane that has not started adopts the sender's exponent.  If the incoming values would exceed 2^60 in my
