@@ -482,9 +482,11 @@ extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
     const GcpMode gcp = resolve_gcp(batch, n_reads);
-    // chunk boundaries: ~equal pair counts, at most 8 chunks, at least ~1M pairs each
-    int n_chunks = (int)std::min<int64_t>(8, std::max<int64_t>(1, n_pairs / (1 << 20)));
-    n_chunks = (int)std::min<int64_t>(n_chunks, batch->n_regions);
+    // chunk boundaries: ~equal pair counts; ~1M pairs per chunk up to 8 chunks, then chunks of <= 4M pairs so the two
+    // workspaces stay bounded however large the batch is
+    int64_t n_chunks = std::min<int64_t>(8, std::max<int64_t>(1, n_pairs / (1 << 20)));
+    n_chunks = std::max<int64_t>(n_chunks, (n_pairs + (4 << 20) - 1) / (4 << 20));
+    n_chunks = std::min<int64_t>(n_chunks, batch->n_regions);
     std::vector<int64_t> cut(1, 0), pair_base(1, 0);
     {
         int64_t acc = 0, next = 1;
