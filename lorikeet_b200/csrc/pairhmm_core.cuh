@@ -42,6 +42,25 @@ namespace lk {
 constexpr int HENC_PADL = 36;
 constexpr int HENC_PADR = 44;
 
+// Slice of the per-warp prior table (fast kernel) a haplotype base selects.
+constexpr int N_PRIOR_SLICES = 5;
+LK_DEV uint8_t base_slice(uint8_t b) {
+    switch (b) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        case 'N': return 4;
+        default: return 0;  // exotic bytes flag the haplotype; its pairs are redone in f64
+    }
+}
+// floats of per-warp shared memory pairhmm_fast_task<K> needs
+template <int K> struct FastTable { static constexpr int floats = N_PRIOR_SLICES * ((K + 3) / 4) * 32 * 4; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int fast_table_floats(int K) { return N_PRIOR_SLICES * ((K + 3) / 4) * 32 * 4; }
+
 LK_DEV uint32_t encode_base(uint8_t b, bool &exotic) {
     uint32_t m;
     switch (b) {
@@ -92,7 +111,8 @@ struct PairHmmArgs {
     const int64_t *hap_off;
     const uint8_t *hap_bases;
     const uint32_t *henc;
-    const int64_t *henc_off;       // index of column 1 of haplotype h inside henc
+    const uint8_t *hidx;           // same indexing as henc: prior-table slice of the column's base (A C G T N = 0..4, padding 0)
+    const int64_t *henc_off;       // index of column 1 of haplotype h inside henc / hidx
     const uint8_t *hap_flags;
     // tables
     const float *qerr_f;           // 10^(-q/10), q = 0..255
@@ -165,8 +185,16 @@ LK_DEV double m2m_lookup(const double *m2m, int ins, int del) {
 // Fast path: fp32 hat form, one warp task = up to 32 lanes of read groups, every haplotype of the
 // region in turn.  Requires R <= 32*K for every read of the task.
 // =============================================================================================
+//
+// Match/mismatch prior WITHOUT per-cell compare + select: LOP3->predicate and FSEL issue on the half-rate ALU pipe
+// and cost ~1.8 cycles each next to ~1.05 for an FMA-pipe instruction (tools/microbench/pipes.cu: 5 FMA + LOP3.P +
+// FSEL = 8.4 cycles, 5 FMA = 5.3).  Instead each lane keeps, in per-warp shared memory, the finished multiplier
+// s[i] * (match ? 1 : r[i]) of each of its K rows against each possible haplotype base (A C G T N), built once per
+// task and reused for every haplotype and column:  tab[slice][k/4][lane] is a float4, so a step fetches its K
+// multipliers with ceil(K/4) conflict-free LDS.128 at an address picked by the column's base, and the cell is
+// FMUL + 4 FFMA.
 template <class W, int K, bool VARGCP>
-LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
+LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id, float *tab) {
     const int lane = w.lane();
     const WarpTask t = A.tasks[task_id];
     TaskGroup g;
@@ -199,11 +227,10 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
     //     M'[i] = mm * (match ? s[i] : s[i] r[i])
     //     D'[i] = fma(D'[i], f, M'[i]),   I'[i] = fma(I'[i-1], e', M'[i-1]),   e' = a~[i] e / a~[i-1]
     // i.e. 7 issue slots per cell: compare (LOP3 -> predicate), select, FMUL, 4 FFMA.
-    float cb[K], cc[K], ce[K], cs[K], csr[K];
+    constexpr int KQ = (K + 3) / 4;
+    w.sync();  // the table may still be in use by the warp's previous task
+    float cb[K], cc[K], ce[K];
     float cf[VARGCP ? K : 1];
-    uint32_t rm[(K + 3) / 4];
-#pragma unroll
-    for (int i = 0; i < (K + 3) / 4; i++) rm[i] = 0u;
     float kcoef = 0.f, wM = 0.f, wI = 0.f;
     if (!VARGCP) cf[0] = A.qerr_f[A.gcp_constant];
     // a~ of a 0-based read position: pm*tMM for real rows >= 1, else 1
@@ -244,10 +271,21 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
             // first padding row under the read: I' becomes the column's summand M[R][j] + I[R][j]
             e = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1));
         }
-        cb[k] = b; cc[k] = c; ce[k] = e; cs[k] = sm; csr[k] = sx;
+        cb[k] = b; cc[k] = c; ce[k] = e;
         if (VARGCP) cf[k] = f;
-        rm[k >> 2] |= mask << (8 * (k & 3));
+        // prior table: multiplier of row k against haplotype base A, C, G, T (one-hot bit of the read base's mask; a read
+        // 'N' has all bits set) and against a haplotype 'N' (matches every real base), pair_hmm.rs:638-654
+#pragma unroll
+        for (int sl = 0; sl < N_PRIOR_SLICES; sl++) {
+            const bool match = sl < 4 ? ((mask >> sl) & 1u) != 0u : mask != 0u;
+            tab[(((sl * KQ) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = match ? sm : sx;
+        }
     }
+#pragma unroll
+    for (int k = K; k < KQ * 4; k++)
+#pragma unroll
+        for (int sl = 0; sl < N_PRIOR_SLICES; sl++) tab[(((sl * KQ) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = 0.f;
+    w.sync();
     if (lig == glanes - 1) {
         const int kstar = (R - 1) - lig * K;
         if (kstar == K - 1) { wM = 1.f; wI = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1)); }
@@ -260,7 +298,7 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
 
     for (int64_t h = h0; h < h1; ++h) {
         const int H = (int)(A.hap_off[h + 1] - A.hap_off[h]);
-        const uint32_t *hp = A.henc + A.henc_off[h] - 1 - lig;  // hp[s] = encoded column (s - lig)
+        const uint8_t *hp = A.hidx + A.henc_off[h] - 1 - lig;  // hp[s] = table slice of column (s - lig)
         const float kinit = kcoef * (FAST_INIT / (float)H);
         float M[K], I[K], D[K];
 #pragma unroll
@@ -271,7 +309,10 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id) {
 
 LK_UNROLL_N(LK_FAST_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
-            const uint32_t hrep = w.ldg(hp + s);
+            const float *trow = tab + ((int)w.ldg(hp + s) * KQ * 32 + lane) * 4;
+            float sel[KQ * 4];
+#pragma unroll
+            for (int q = 0; q < KQ; q++) w.lds4(sel + 4 * q, trow + q * 128);
             // ---- one column of the strip, rows top to bottom.  Row k reads row k-1 of the previous column (pm, pi, pd)
             // and, for I', row k-1 of this column (im, ii).  Written in this order the serial I' chain (one FFMA per row)
             // is spread evenly between the independent M'/D' work of the rows instead of being bunched at the end. ----
@@ -283,7 +324,7 @@ LK_UNROLL_N(LK_FAST_UNROLL)
                     float mm = fmaf(pi, cb[k], pm);
                     mm = fmaf(pd, cc[k], mm);
                     D[k] = fmaf(od, VARGCP ? cf[k] : A.cf_uniform, om);
-                    M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
+                    M[k] = mm * sel[k];
                     I[k] = fmaf(ii, ce[k], im);
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
                 }

@@ -23,13 +23,17 @@ struct DevWarp {
     template <class T> __device__ __forceinline__ T ldg(const T *p) const { return __ldg(p); }
     __device__ __forceinline__ int atomic_add(int32_t *p, int v) const { return atomicAdd(p, v); }
     __device__ __forceinline__ void sync() const { __syncwarp(); __threadfence_block(); }
+    __device__ __forceinline__ void lds4(float *dst, const float *src) const {
+        const float4 v = *reinterpret_cast<const float4 *>(src);
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
     __device__ __forceinline__ void prefetch(const void *p) const { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 };
 
 // ---------------------------------------------------------------------------------------------
 __global__ void encode_haps_kernel(const uint8_t *__restrict__ hap_bases, const int64_t *__restrict__ hap_off,
                                    const int64_t *__restrict__ henc_off, int64_t n_haps, uint32_t *__restrict__ henc,
-                                   uint8_t *__restrict__ hap_flags) {
+                                   uint8_t *__restrict__ hidx, uint8_t *__restrict__ hap_flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -37,11 +41,14 @@ __global__ void encode_haps_kernel(const uint8_t *__restrict__ hap_bases, const 
         const int64_t ho = hap_off[h];
         const int H = (int)(hap_off[h + 1] - ho);
         uint32_t *dst = henc + henc_off[h];  // column 1
+        uint8_t *dsti = hidx + henc_off[h];
         bool exotic = false;
         for (int j = lane - HENC_PADL; j < H + HENC_PADR; j += 32) {
             uint32_t v = 0u;
-            if (j >= 0 && j < H) v = encode_base(hap_bases[ho + j], exotic);
+            uint8_t sl = 0;
+            if (j >= 0 && j < H) { v = encode_base(hap_bases[ho + j], exotic); sl = base_slice(hap_bases[ho + j]); }
             dst[j] = v;
+            dsti[j] = sl;
         }
         const unsigned any = __ballot_sync(0xffffffffu, exotic);
         if (lane == 0) hap_flags[h] = any ? SEQ_EXOTIC : 0;
@@ -97,10 +104,12 @@ __global__ void list_all_pairs_kernel(PairHmmArgs A, int64_t n_reads) {
 // ---------------------------------------------------------------------------------------------
 template <int K, bool VARGCP, int MINB>
 __global__ void __launch_bounds__(LK_FAST_THREADS, MINB) pairhmm_fast_kernel(const PairHmmArgs A) {
+    extern __shared__ float4 lk_fast_smem[];  // per-warp prior tables
     const int task = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (task >= A.n_tasks) return;
     DevWarp w;
-    pairhmm_fast_task<DevWarp, K, VARGCP>(w, A, task);
+    float *tab = reinterpret_cast<float *>(lk_fast_smem) + (threadIdx.x >> 5) * fast_table_floats(K);
+    pairhmm_fast_task<DevWarp, K, VARGCP>(w, A, task, tab);
 }
 
 template <int K>
@@ -140,12 +149,12 @@ __global__ void __launch_bounds__(LK_PLAIN_THREADS) pairhmm_plain_kernel(const P
 // launchers (host)
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_encode_haps(const uint8_t *hap_bases, const int64_t *hap_off, const int64_t *henc_off,
-                               int64_t n_haps, uint32_t *henc, uint8_t *hap_flags, cudaStream_t st) {
+                               int64_t n_haps, uint32_t *henc, uint8_t *hidx, uint8_t *hap_flags, cudaStream_t st) {
     if (n_haps == 0) return cudaSuccess;
     const int threads = 256;
     int64_t blocks = (n_haps * 32 + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    encode_haps_kernel<<<(unsigned)blocks, threads, 0, st>>>(hap_bases, hap_off, henc_off, n_haps, henc, hap_flags);
+    encode_haps_kernel<<<(unsigned)blocks, threads, 0, st>>>(hap_bases, hap_off, henc_off, n_haps, henc, hidx, hap_flags);
     return cudaGetLastError();
 }
 
@@ -169,8 +178,16 @@ template <int K, int MINB>
 static cudaError_t launch_fast_k(const PairHmmArgs &A, bool vargcp, cudaStream_t st) {
     const int warps_per_block = LK_FAST_THREADS / 32;
     const unsigned blocks = (unsigned)((A.n_tasks + warps_per_block - 1) / warps_per_block);
-    if (vargcp) pairhmm_fast_kernel<K, true, MINB><<<blocks, LK_FAST_THREADS, 0, st>>>(A);
-    else pairhmm_fast_kernel<K, false, MINB><<<blocks, LK_FAST_THREADS, 0, st>>>(A);
+    const int smem = warps_per_block * fast_table_floats(K) * (int)sizeof(float);
+    static bool configured[2] = { false, false };  // per instantiation; the attribute is idempotent, races are harmless
+    if (!configured[vargcp ? 1 : 0]) {
+        cudaError_t e = vargcp ? cudaFuncSetAttribute(pairhmm_fast_kernel<K, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                               : cudaFuncSetAttribute(pairhmm_fast_kernel<K, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[vargcp ? 1 : 0] = true;
+    }
+    if (vargcp) pairhmm_fast_kernel<K, true, MINB><<<blocks, LK_FAST_THREADS, smem, st>>>(A);
+    else pairhmm_fast_kernel<K, false, MINB><<<blocks, LK_FAST_THREADS, smem, st>>>(A);
     return cudaGetLastError();
 }
 
