@@ -193,8 +193,14 @@ LK_DEV double m2m_lookup(const double *m2m, int ins, int del) {
 // task and reused for every haplotype and column:  tab[slice][k/4][lane] is a float4, so a step fetches its K
 // multipliers with ceil(K/4) conflict-free LDS.128 at an address picked by the column's base, and the cell is
 // FMUL + 4 FFMA.
-template <class W, int K, bool VARGCP>
+// GM (gap-continuation mode): GM_UNIFORM = one gcp for the whole batch (factor in a register / the parameter
+// bank), GM_VAR = per-base gcp array, GM_Q10 = uniform gcp of 10, the engine's default (`vec![gcp; R]`,
+// pair_hmm_likelihood_calculation_engine.rs:649-651): the factor 0.1f is then an FFMA immediate, which saves
+// one register-file read per cell in a kernel that is register-read bound.
+enum { GM_UNIFORM = 0, GM_VAR = 1, GM_Q10 = 2 };
+template <class W, int K, int GM>
 LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id, float *tab) {
+    constexpr bool VARGCP = (GM == GM_VAR);
     const int lane = w.lane();
     const WarpTask t = A.tasks[task_id];
     TaskGroup g;
@@ -323,7 +329,7 @@ LK_UNROLL_N(LK_FAST_UNROLL)
                     const float om = M[k], oi = I[k], od = D[k];
                     float mm = fmaf(pi, cb[k], pm);
                     mm = fmaf(pd, cc[k], mm);
-                    D[k] = fmaf(od, VARGCP ? cf[k] : A.cf_uniform, om);
+                    D[k] = fmaf(od, VARGCP ? cf[k] : (GM == GM_Q10 ? 0.1f : A.cf_uniform), om);
                     M[k] = mm * sel[k];
                     I[k] = fmaf(ii, ce[k], im);
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];

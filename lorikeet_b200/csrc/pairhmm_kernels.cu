@@ -102,14 +102,14 @@ __global__ void list_all_pairs_kernel(PairHmmArgs A, int64_t n_reads) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int K, bool VARGCP, int MINB>
+template <int K, int GM, int MINB>
 __global__ void __launch_bounds__(LK_FAST_THREADS, MINB) pairhmm_fast_kernel(const PairHmmArgs A) {
     extern __shared__ float4 lk_fast_smem[];  // per-warp prior tables
     const int task = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (task >= A.n_tasks) return;
     DevWarp w;
     float *tab = reinterpret_cast<float *>(lk_fast_smem) + (threadIdx.x >> 5) * fast_table_floats(K);
-    pairhmm_fast_task<DevWarp, K, VARGCP>(w, A, task, tab);
+    pairhmm_fast_task<DevWarp, K, GM>(w, A, task, tab);
 }
 
 template <int K>
@@ -174,21 +174,26 @@ cudaError_t launch_list_all_pairs(const PairHmmArgs &A, int64_t n_reads, cudaStr
     return cudaGetLastError();
 }
 
-template <int K, int MINB>
-static cudaError_t launch_fast_k(const PairHmmArgs &A, bool vargcp, cudaStream_t st) {
+template <int K, int GM, int MINB>
+static cudaError_t launch_fast_kg(const PairHmmArgs &A, cudaStream_t st) {
     const int warps_per_block = LK_FAST_THREADS / 32;
     const unsigned blocks = (unsigned)((A.n_tasks + warps_per_block - 1) / warps_per_block);
-    const int smem = warps_per_block * fast_table_floats(K) * (int)sizeof(float);
-    static bool configured[2] = { false, false };  // per instantiation; the attribute is idempotent, races are harmless
-    if (!configured[vargcp ? 1 : 0]) {
-        cudaError_t e = vargcp ? cudaFuncSetAttribute(pairhmm_fast_kernel<K, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                               : cudaFuncSetAttribute(pairhmm_fast_kernel<K, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = warps_per_block * FastTable<K>::floats * (int)sizeof(float);
+    static bool configured = false;  // per instantiation; the attribute is idempotent, so a race is harmless
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pairhmm_fast_kernel<K, GM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured[vargcp ? 1 : 0] = true;
+        configured = true;
     }
-    if (vargcp) pairhmm_fast_kernel<K, true, MINB><<<blocks, LK_FAST_THREADS, smem, st>>>(A);
-    else pairhmm_fast_kernel<K, false, MINB><<<blocks, LK_FAST_THREADS, smem, st>>>(A);
+    pairhmm_fast_kernel<K, GM, MINB><<<blocks, LK_FAST_THREADS, smem, st>>>(A);
     return cudaGetLastError();
+}
+
+template <int K, int MINB>
+static cudaError_t launch_fast_k(const PairHmmArgs &A, bool vargcp, cudaStream_t st) {
+    if (vargcp) return launch_fast_kg<K, GM_VAR, MINB>(A, st);
+    if (A.gcp_constant == 10 && A.cf_uniform == 0.1f) return launch_fast_kg<K, GM_Q10, MINB>(A, st);
+    return launch_fast_kg<K, GM_UNIFORM, MINB>(A, st);
 }
 
 cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t st) {

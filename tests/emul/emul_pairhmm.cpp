@@ -73,8 +73,9 @@ static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *ta
         th.emplace_back([&, l]() {
             EmulWarp w{ l, &sh };
             for (int t = 0; t < n_tasks; t++) {
-                if (vargcp) pairhmm_fast_task<EmulWarp, K, true>(w, AL, t, tab.data());
-                else pairhmm_fast_task<EmulWarp, K, false>(w, AL, t, tab.data());
+                if (vargcp) pairhmm_fast_task<EmulWarp, K, GM_VAR>(w, AL, t, tab.data());
+                else if (AL.gcp_constant == 10 && AL.cf_uniform == 0.1f) pairhmm_fast_task<EmulWarp, K, GM_Q10>(w, AL, t, tab.data());
+                else pairhmm_fast_task<EmulWarp, K, GM_UNIFORM>(w, AL, t, tab.data());
             }
         });
     for (auto &t : th) t.join();
