@@ -276,7 +276,7 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
     if (gcp.vargcp) { RS(read_gcp, read_bytes); }
     RS(hap_bases, hap_bytes);
     RS(read_flags, n_reads); RS(hap_flags, n_haps);
-    RS(henc, P.henc_words * 4); RS(hidx, P.henc_words);
+    RS(hidx, P.henc_words);
     RS(out, P.n_pairs * 8); RS(flags, P.n_pairs);
     RS(counters, 64);
     RS(rescue_pairs, std::max<int64_t>(P.n_pairs, 1) * (int64_t)sizeof(RescuePair));
@@ -318,7 +318,7 @@ static void fill_args(lk_ctx *ctx, lk_resident *R, PairHmmArgs &A) {
     A.read_off = (const int64_t *)R->read_off.p; A.read_region = (const int32_t *)R->read_region.p;
     A.read_out_base = (const int64_t *)R->read_out_base.p; A.read_flags = (const uint8_t *)R->read_flags.p;
     A.region_hap_start = (const int64_t *)R->region_hap_start.p; A.hap_off = (const int64_t *)R->hap_off.p;
-    A.hap_bases = (const uint8_t *)R->hap_bases.p - R->hap_byte0; A.henc = (const uint32_t *)R->henc.p; A.hidx = (const uint8_t *)R->hidx.p;
+    A.hap_bases = (const uint8_t *)R->hap_bases.p - R->hap_byte0; A.hidx = (const uint8_t *)R->hidx.p;
     A.henc_off = (const int64_t *)R->henc_off.p; A.hap_flags = (const uint8_t *)R->hap_flags.p;
     A.qerr_f = (const float *)ctx->d_qerr_f.p; A.qerr_d = (const double *)ctx->d_qerr_d.p; A.m2m = (const double *)ctx->d_m2m.p;
     A.groups = (const TaskGroup *)R->groups.p;
@@ -350,7 +350,7 @@ static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, b
         if ((e = launch_list_all_pairs(A, R->n_reads, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "list_all_pairs");
         R->launch_count++;
     } else {
-        if ((e = launch_encode_haps(A.hap_bases, A.hap_off, A.henc_off, R->n_haps, (uint32_t *)R->henc.p, (uint8_t *)R->hidx.p, (uint8_t *)R->hap_flags.p, st)) != cudaSuccess)
+        if ((e = launch_encode_haps(A.hap_bases, A.hap_off, A.henc_off, R->n_haps, (uint8_t *)R->hidx.p, (uint8_t *)R->hap_flags.p, st)) != cudaSuccess)
             return lk_cuda_fail(ctx, e, "encode_haps");
         if ((e = launch_scan_reads(A.read_bases, A.read_qual, A.read_ins, A.read_del, A.read_off, R->n_reads, (uint8_t *)R->read_flags.p, st)) != cudaSuccess)
             return lk_cuda_fail(ctx, e, "scan_reads");
@@ -450,7 +450,7 @@ extern "C" lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *
 static void release_buffers(lk_resident *R) {
     DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
                        &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
-                       &R->hap_bases, &R->henc, &R->hidx, &R->henc_off, &R->hap_flags, &R->tasks, &R->groups, &R->out,
+                       &R->hap_bases, &R->hidx, &R->henc_off, &R->hap_flags, &R->tasks, &R->groups, &R->out,
                        &R->flags, &R->counters, &R->rescue_pairs, &R->scratch, &R->band_pairs, &R->band_scratch,
                        &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,
                        &R->sw_ops, &R->sw_nops, &R->sw_offsets, &R->sw_order };

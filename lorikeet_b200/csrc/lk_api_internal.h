@@ -63,7 +63,7 @@ struct lk_resident {
     cudaEvent_t ev_staged = nullptr;  // pinned arena may be rewritten once this has fired
     int64_t read_byte0 = 0, hap_byte0 = 0;  // first arena byte staged: device pointers are biased by these
     DevBuf read_bases, read_qual, read_ins, read_del, read_gcp, read_off, read_region, read_out_base, read_flags;
-    DevBuf region_hap_start, hap_off, hap_bases, henc, hidx, henc_off, hap_flags;
+    DevBuf region_hap_start, hap_off, hap_bases, hidx, henc_off, hap_flags;
     DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch, band_pairs, band_scratch;
     // ---- Smith-Waterman ----
     struct SwLaunch { int K; int32_t first; int32_t count; };

@@ -11,7 +11,7 @@ struct PairHmmArgs;
 struct SwArgs;
 
 cudaError_t launch_encode_haps(const uint8_t *hap_bases, const int64_t *hap_off, const int64_t *henc_off,
-                               int64_t n_haps, uint32_t *henc, uint8_t *hidx, uint8_t *hap_flags, cudaStream_t st);
+                               int64_t n_haps, uint8_t *hidx, uint8_t *hap_flags, cudaStream_t st);
 cudaError_t launch_scan_reads(const uint8_t *read_bases, const uint8_t *read_qual, const uint8_t *read_ins,
                               const uint8_t *read_del, const int64_t *read_off, int64_t n_reads, uint8_t *read_flags, cudaStream_t st);
 cudaError_t launch_list_all_pairs(const PairHmmArgs &A, int64_t n_reads, cudaStream_t st);

@@ -34,11 +34,12 @@
 
 namespace lk {
 
-// ---- encoded haplotypes ---------------------------------------------------------------------
-// One u32 per haplotype base: the base's one-hot byte replicated into all 4 bytes
-// (A=01 C=02 G=04 T=08, N=FF so that it matches anything; anything else = 0 and the sequence is
-// flagged SEQ_EXOTIC, which routes its pairs to the byte-exact f64 pass).
-// Each encoded haplotype is surrounded by zero words so lanes can read columns <1 and >H.
+// ---- encoded sequences ----------------------------------------------------------------------
+// Haplotypes are re-coded by a prologue kernel to one byte per column: the slice of the per-warp prior
+// table its base selects (base_slice), with zero guard bands either side so lanes can read columns <1
+// and >H unconditionally.  Read bases become a one-hot mask (encode_base: A=01 C=02 G=04 T=08, N=FF so
+// that it matches anything) when the prior table is built.  Any other byte flags the sequence
+// SEQ_EXOTIC, which routes its pairs to the byte-exact f64 pass.
 constexpr int HENC_PADL = 36;
 constexpr int HENC_PADR = 44;
 
@@ -110,9 +111,8 @@ struct PairHmmArgs {
     const int64_t *region_hap_start;
     const int64_t *hap_off;
     const uint8_t *hap_bases;
-    const uint32_t *henc;
-    const uint8_t *hidx;           // same indexing as henc: prior-table slice of the column's base (A C G T N = 0..4, padding 0)
-    const int64_t *henc_off;       // index of column 1 of haplotype h inside henc / hidx
+    const uint8_t *hidx;           // per haplotype column: prior-table slice of its base (A C G T N = 0..4), guard bands = 0
+    const int64_t *henc_off;       // index of column 1 of haplotype h inside hidx
     const uint8_t *hap_flags;
     // tables
     const float *qerr_f;           // 10^(-q/10), q = 0..255
@@ -160,19 +160,6 @@ LK_DEV int lk_popc(unsigned v) {
 #define LK_PRAGMA_(x) _Pragma(#x)
 #define LK_PRAGMA(x) LK_PRAGMA_(x)
 #define LK_UNROLL_N(n) LK_PRAGMA(unroll n)
-
-// M' = mm * (match ? s : s*r).  Default: compare -> select -> FMUL (LOP3 + FSEL on the half-rate ALU pipe).
-// LK_PRED_FMUL: compare -> FMUL -> predicated FMUL, which moves the select onto the full-rate FMA pipe.
-LK_DEV float prior_scale(float mm, uint32_t match_bits, float s_match, float s_mismatch) {
-#if defined(__CUDA_ARCH__) && defined(LK_PRED_FMUL)
-    float r;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmul.f32 %0, %1, %4;\n\t@p mul.f32 %0, %1, %3;\n\t}"
-        : "=&f"(r) : "f"(mm), "r"(match_bits), "f"(s_match), "f"(s_mismatch));
-    return r;
-#else
-    return mm * ((match_bits != 0u) ? s_match : s_mismatch);
-#endif
-}
 
 // match->match, pair_hmm_model.rs:442-461 (table) — quals are bytes so max <= 255; 255 > MAX_QUAL uses
 // the closed form of :453-458 which the host folded into row 255 of the table.
@@ -395,8 +382,9 @@ LK_DEV float pow2i(int e) {  // 2^e for e in [-126, 127]
 #endif
 }
 
-template <class W, int K>
-LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, Bnd4 *scratch) {
+template <class W, int K, bool Q10 = false>
+LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, Bnd4 *scratch, float *tab) {
+    constexpr int KQ = (K + 3) / 4;
     const int lane = w.lane();
     const int64_t ro = A.read_off[read];
     const int R = (int)(A.read_off[read + 1] - ro);
@@ -415,7 +403,7 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
     const int n_bands = (R + BAND - 1) / BAND;
     const int64_t W1 = (int64_t)H + 1;
     Bnd4 *bnd[2] = { scratch, scratch + W1 };
-    const uint32_t *hp = A.henc + A.henc_off[h] - 1 - lane;  // hp[s] = encoded column (s - lane)
+    const uint8_t *hp = A.hidx + A.henc_off[h] - 1 - lane;  // hp[s] = prior-table slice of column (s - lane)
     auto a_tilde = [&](int i) -> double {
         if (i < 1 || i >= R) return 1.0;
         return (1.0 - A.qerr_d[A.read_qual[ro + i]]) * m2m_lookup(A.m2m, A.read_ins[ro + i], A.read_del[ro + i]);
@@ -433,10 +421,9 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         Bnd4 *bout = bnd[(band + 1) & 1];
 
         // ---- row constants (same scaled hat form as the fast kernel) ----
-        float cb[K], cc[K], ce[K], cs[K], csr[K];
-        uint32_t rm[(K + 3) / 4];
-#pragma unroll
-        for (int i = 0; i < (K + 3) / 4; i++) rm[i] = 0u;
+        // the match / mismatch multipliers go to the warp's shared-memory prior table, as in the fast kernel
+        w.sync();
+        float cb[K], cc[K], ce[K];
         float kcoef = 0.f, wM = 0.f, wI = 0.f;
 #pragma unroll
         for (int k = 0; k < K; k++) {
@@ -465,9 +452,18 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
             } else if (i == R) {
                 e = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1));
             }
-            cb[k] = b; cc[k] = c; ce[k] = e; cs[k] = sm; csr[k] = sx;
-            rm[k >> 2] |= mask << (8 * (k & 3));
+            cb[k] = b; cc[k] = c; ce[k] = e;
+#pragma unroll
+            for (int sl = 0; sl < N_PRIOR_SLICES; sl++) {
+                const bool match = sl < 4 ? ((mask >> sl) & 1u) != 0u : mask != 0u;
+                tab[(((sl * KQ) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = match ? sm : sx;
+            }
         }
+#pragma unroll
+        for (int k = K; k < KQ * 4; k++)
+#pragma unroll
+            for (int sl = 0; sl < N_PRIOR_SLICES; sl++) tab[(((sl * KQ) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = 0.f;
+        w.sync();
         if (last_band && lane == lanes - 1) {
             const int kstar = (rows - 1) - lane * K;
             if (kstar == K - 1) { wM = 1.f; wI = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1)); }
@@ -491,7 +487,10 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
 
 LK_UNROLL_N(LK_FAST_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
-            const uint32_t hrep = w.ldg(hp + s);
+            const float *trow = tab + ((int)w.ldg(hp + s) * KQ * 32 + lane) * 4;
+            float sel[KQ * 4];
+#pragma unroll
+            for (int q = 0; q < KQ; q++) w.lds4(sel + 4 * q, trow + q * 128);
             // row above lane 0 = last row of the previous band.  Every lane reads the same element (one broadcast
             // transaction, no divergence) one step AHEAD of its use, so the L1/L2 latency hides behind a whole step.
             if (band > 0) {
@@ -532,8 +531,8 @@ LK_UNROLL_N(LK_FAST_UNROLL)
                     const float om = M[k], oi = I[k], od = D[k];
                     float mm = fmaf(pi, cb[k], pm);
                     mm = fmaf(pd, cc[k], mm);
-                    D[k] = fmaf(od, A.cf_uniform, om);
-                    M[k] = prior_scale(mm, rm[k >> 2] & hrep & (0xFFu << (8 * (k & 3))), cs[k], csr[k]);
+                    D[k] = fmaf(od, Q10 ? 0.1f : A.cf_uniform, om);
+                    M[k] = mm * sel[k];
                     I[k] = fmaf(ii, ce[k], im);
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
                 }

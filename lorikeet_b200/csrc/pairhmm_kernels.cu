@@ -1,6 +1,6 @@
 // pairhmm_kernels.cu — sm_100a kernels of the PairHMM path and their launchers.
 //
-//   encode_haps_kernel   bytes -> replicated one-hot words (+ zero guard bands), exotic-byte flags
+//   encode_haps_kernel   bytes -> prior-table slice index per column (+ zero guard bands), exotic-byte flags
 //   scan_reads_kernel    per-read domain flags for the fp32 hat form
 //   pairhmm_fast_kernel  fp32 wavefront, one warp per task (reads of one region x all its haplotypes)
 //   pairhmm_plain_kernel f64 pass for flagged pairs (persistent warps pulling from the rescue list)
@@ -32,7 +32,7 @@ struct DevWarp {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void encode_haps_kernel(const uint8_t *__restrict__ hap_bases, const int64_t *__restrict__ hap_off,
-                                   const int64_t *__restrict__ henc_off, int64_t n_haps, uint32_t *__restrict__ henc,
+                                   const int64_t *__restrict__ henc_off, int64_t n_haps,
                                    uint8_t *__restrict__ hidx, uint8_t *__restrict__ hap_flags) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -40,14 +40,11 @@ __global__ void encode_haps_kernel(const uint8_t *__restrict__ hap_bases, const 
     for (int64_t h = warp; h < n_haps; h += n_warps) {
         const int64_t ho = hap_off[h];
         const int H = (int)(hap_off[h + 1] - ho);
-        uint32_t *dst = henc + henc_off[h];  // column 1
-        uint8_t *dsti = hidx + henc_off[h];
+        uint8_t *dsti = hidx + henc_off[h];  // column 1
         bool exotic = false;
         for (int j = lane - HENC_PADL; j < H + HENC_PADR; j += 32) {
-            uint32_t v = 0u;
             uint8_t sl = 0;
-            if (j >= 0 && j < H) { v = encode_base(hap_bases[ho + j], exotic); sl = base_slice(hap_bases[ho + j]); }
-            dst[j] = v;
+            if (j >= 0 && j < H) { (void)encode_base(hap_bases[ho + j], exotic); sl = base_slice(hap_bases[ho + j]); }
             dsti[j] = sl;
         }
         const unsigned any = __ballot_sync(0xffffffffu, exotic);
@@ -112,8 +109,10 @@ __global__ void __launch_bounds__(LK_FAST_THREADS, MINB) pairhmm_fast_kernel(con
     pairhmm_fast_task<DevWarp, K, GM>(w, A, task, tab);
 }
 
-template <int K>
+template <int K, bool Q10>
 __global__ void __launch_bounds__(LK_BAND_THREADS, LK_BAND_MINB) pairhmm_band_kernel(const PairHmmArgs A) {
+    extern __shared__ float4 lk_band_smem[];  // per-warp prior tables
+    float *tab = reinterpret_cast<float *>(lk_band_smem) + (threadIdx.x >> 5) * FastTable<K>::floats;
     DevWarp w;
     const int warp_in_grid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     Bnd4 *scratch = (Bnd4 *)A.band_scratch + (int64_t)warp_in_grid * A.band_scratch_stride;
@@ -123,7 +122,7 @@ __global__ void __launch_bounds__(LK_BAND_THREADS, LK_BAND_MINB) pairhmm_band_ke
         idx = w.shfl(idx, 0);
         if (idx >= A.n_band) break;
         const RescuePair p = A.band_pairs[idx];
-        pairhmm_band_pair<DevWarp, K>(w, A, p.read, (int64_t)p.hap, scratch);
+        pairhmm_band_pair<DevWarp, K, Q10>(w, A, p.read, (int64_t)p.hap, scratch, tab);
         __syncwarp();
     }
 }
@@ -149,12 +148,12 @@ __global__ void __launch_bounds__(LK_PLAIN_THREADS) pairhmm_plain_kernel(const P
 // launchers (host)
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_encode_haps(const uint8_t *hap_bases, const int64_t *hap_off, const int64_t *henc_off,
-                               int64_t n_haps, uint32_t *henc, uint8_t *hidx, uint8_t *hap_flags, cudaStream_t st) {
+                               int64_t n_haps, uint8_t *hidx, uint8_t *hap_flags, cudaStream_t st) {
     if (n_haps == 0) return cudaSuccess;
     const int threads = 256;
     int64_t blocks = (n_haps * 32 + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    encode_haps_kernel<<<(unsigned)blocks, threads, 0, st>>>(hap_bases, hap_off, henc_off, n_haps, henc, hidx, hap_flags);
+    encode_haps_kernel<<<(unsigned)blocks, threads, 0, st>>>(hap_bases, hap_off, henc_off, n_haps, hidx, hap_flags);
     return cudaGetLastError();
 }
 
@@ -208,7 +207,16 @@ cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t s
 
 cudaError_t launch_band(const PairHmmArgs &A, int n_blocks, cudaStream_t st) {
     if (A.n_band == 0) return cudaSuccess;
-    pairhmm_band_kernel<LK_BAND_K><<<n_blocks, LK_BAND_THREADS, 0, st>>>(A);
+    const int smem = (LK_BAND_THREADS / 32) * FastTable<LK_BAND_K>::floats * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pairhmm_band_kernel<LK_BAND_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(pairhmm_band_kernel<LK_BAND_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (A.gcp_constant == 10 && A.cf_uniform == 0.1f) pairhmm_band_kernel<LK_BAND_K, true><<<n_blocks, LK_BAND_THREADS, smem, st>>>(A);
+    else pairhmm_band_kernel<LK_BAND_K, false><<<n_blocks, LK_BAND_THREADS, smem, st>>>(A);
     return cudaGetLastError();
 }
 

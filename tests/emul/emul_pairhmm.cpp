@@ -83,13 +83,14 @@ static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *ta
 
 static void run_band(const PairHmmArgs &A, int k_band) {
     WarpShared sh;
+    std::vector<float> tab((size_t)fast_table_floats(LK_BAND_K > 4 ? LK_BAND_K : 4));
     std::vector<std::thread> th;
     for (int l = 0; l < 32; l++)
         th.emplace_back([&, l]() {
             EmulWarp w{ l, &sh };
             for (int i = 0; i < A.n_band; i++) {
-                if (k_band == 4) pairhmm_band_pair<EmulWarp, 4>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch);
-                else pairhmm_band_pair<EmulWarp, LK_BAND_K>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch);
+                if (k_band == 4) pairhmm_band_pair<EmulWarp, 4>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch, tab.data());
+                else pairhmm_band_pair<EmulWarp, LK_BAND_K>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch, tab.data());
             }
         });
     for (auto &t : th) t.join();
@@ -117,14 +118,13 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
     if (force_k == -4) { HostPrep Q; build_prep(b, 0, b->n_regions, -1, !force_f64, Q); P = Q; }
     ModelTables T;
     build_model_tables(T);
-    std::vector<uint32_t> henc((size_t)P.henc_words, 0u);
     std::vector<uint8_t> hidx((size_t)P.henc_words, 0);
     std::vector<uint8_t> hap_flags((size_t)n_haps, 0), read_flags((size_t)n_reads, 0);
     for (int64_t h = 0; h < n_haps; h++) {  // = encode_haps_kernel
         bool ex = false;
         for (int64_t j = b->hap_off[h]; j < b->hap_off[h + 1]; j++)
         {
-            henc[(size_t)(P.henc_off[(size_t)h] + (j - b->hap_off[h]))] = encode_base(b->hap_bases[j], ex);
+            (void)encode_base(b->hap_bases[j], ex);
             hidx[(size_t)(P.henc_off[(size_t)h] + (j - b->hap_off[h]))] = base_slice(b->hap_bases[j]);
         }
         hap_flags[(size_t)h] = ex ? SEQ_EXOTIC : 0;
@@ -155,7 +155,7 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
     A.read_gcp = vargcp ? b->read_gcp : nullptr;
     A.read_off = b->read_off; A.read_region = P.read_region.data(); A.read_out_base = P.read_out_base.data();
     A.read_flags = read_flags.data(); A.region_hap_start = b->region_hap_start; A.hap_off = b->hap_off;
-    A.hap_bases = b->hap_bases; A.henc = henc.data(); A.hidx = hidx.data(); A.henc_off = P.henc_off.data(); A.hap_flags = hap_flags.data();
+    A.hap_bases = b->hap_bases; A.hidx = hidx.data(); A.henc_off = P.henc_off.data(); A.hap_flags = hap_flags.data();
     A.qerr_f = T.qerr_f.data(); A.qerr_d = T.qerr_d.data(); A.m2m = T.m2m.data();
     A.groups = P.groups.data(); A.out = out; A.flags = flags;
     A.rescue_count = &counters[0]; A.rescue_cursor = &counters[1];
