@@ -157,6 +157,9 @@ LK_DEV int lk_popc(unsigned v) {
 #ifndef LK_FAST_UNROLL
 #define LK_FAST_UNROLL 8
 #endif
+#ifndef LK_BAND_UNROLL
+#define LK_BAND_UNROLL 4
+#endif
 #define LK_PRAGMA_(x) _Pragma(#x)
 #define LK_PRAGMA(x) LK_PRAGMA_(x)
 #define LK_UNROLL_N(n) LK_PRAGMA(unroll n)
@@ -485,7 +488,7 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         cur_b.m = 0.f; cur_b.i = 0.f; cur_b.d = 0.f; cur_b.xi = 0;
         if (band > 0) cur_b = bin[1 <= H ? 1 : H];
 
-LK_UNROLL_N(LK_FAST_UNROLL)
+LK_UNROLL_N(LK_BAND_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
             const float *trow = tab + ((int)w.ldg(hp + s) * KQ * 32 + lane) * 4;
             float sel[KQ * 4];
