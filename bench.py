@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 METRIC = "PairHMM GCUPS (read-bp x hap-bp / s)"
 UNIT = "GCUPS"
 FLOP_PER_CELL = 12  # pair_hmm.rs:575-591: M = 4 mul + 2 add, I = 2 mul + 1 add, D = 2 mul + 1 add
-NCU_DRAM_BYTES_PER_REGION = 65.4e3  # ncu: 62.9 MB read + 2.5 MB written by pairhmm_fast_kernel over 1000 regions (profiles/)
+NCU_DRAM_BYTES_PER_REGION = 47.3e3  # ncu: 46.9 MB read + 0.4 MB written by pairhmm_fast_kernel over 1000 regions (profiles/r01_pairhmm_fast_k19_seltab_ncu_details.txt)
 
 
 def workload_name(regions):
@@ -122,12 +122,13 @@ def run_extras(ctx):
         out["cfg4_smith_waterman"] = {"pairs": 100000, "cells": res.n_cells, "ms": ms, "gcups": res.n_cells / ms / 1e6,
                                       "note": "fill + in-kernel traceback, CIGARs bit-exact vs oracle (tests/test_gpu_sw.py)"}
         res.free()
-        b = synth.pairhmm_regions(96, **synth.CFG3)  # cfg3 slice: 96 of 2000 regions (8 reads x 10 kbp, 4 haps x 12 kbp)
+        b = synth.pairhmm_regions(111, **synth.CFG3)  # cfg3 slice: 111 of 2000 regions (8 reads x 10 kbp, 4 haps x 12 kbp);
+        # 111 x 32 pairs = 2 full waves of the band kernel's 1776 resident warps, as the 36-wave full config is
         res = ctx.pairhmm_upload(b)
         res.run()
         ms = min(res.run() for _ in range(2))
         _, flags = res.download(want_flags=True)
-        out["cfg3_long_reads_slice"] = {"regions": 96, "cells": res.n_cells, "ms": ms, "gcups": res.n_cells / ms / 1e6,
+        out["cfg3_long_reads_slice"] = {"regions": 111, "cells": res.n_cells, "ms": ms, "gcups": res.n_cells / ms / 1e6,
                                         "pairs_redone_in_f64": int((flags & 1).sum()),
                                         "note": "fp32 band kernel with per-lane block floating point"}
         res.free()
@@ -310,7 +311,7 @@ def main():
         hbm = (peaks or {}).get("hbm_gbs", 6650.0)
         alg_bytes = h2d + out_host.nbytes
         # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
-        # (profiles/r01_pairhmm_fast_k19_scaledhat_ncu_details.txt: dram read+write of a 1000-region launch), scaled to
+        # (profiles/r01_pairhmm_fast_k19_seltab_ncu_details.txt: dram read+write of a 1000-region launch), scaled to
         # this launch's region count; ncu itself is never run inside the bench
         traffic = NCU_DRAM_BYTES_PER_REGION * args.regions
         roofline = {
