@@ -191,6 +191,69 @@ lk_status lk_calculate_cigar_finish(const uint8_t *ref, int64_t ref_len, const u
                                     const uint32_t *sw_ops, int32_t sw_n_ops, int32_t sw_offset, int32_t max_ops,
                                     uint32_t *out_ops, int32_t *out_n_ops);
 
+/* ---------------------------------------------------------------- read -> best-haplotype realignment (N2) */
+
+/*
+ * Batch form of AssemblyBasedCallerUtils::realign_reads_to_their_best_haplotype
+ * (src/assembly/assembly_based_caller_utils.rs:208-246) for single-sample regions.
+ * Per read: the best haplotype with the reference's tie-breaking (AlleleLikelihoods::search_best_allele with
+ * priorities, src/model/allele_likelihoods.rs:457-554; priority = is_ref + 1 - cigar elements,
+ * assembly_based_caller_utils.rs:187-195), then AlignmentUtils::create_read_aligned_to_ref
+ * (src/reads/alignment_utils.rs:40-164): ONE Smith-Waterman batch on the GPU (haplotype vs read, SoftClip,
+ * ALIGNMENT_TO_BEST_HAPLOTYPE_SW_PARAMETERS), then the read->haplotype CIGAR is mapped through the
+ * haplotype->reference CIGAR (apply_cigar_to_cigar), left-aligned and given back the read's clips.
+ */
+typedef struct lk_realign_batch {
+    int64_t n_regions;
+    const int64_t *region_read_start;  /* [n_regions + 1] */
+    const int64_t *region_hap_start;   /* [n_regions + 1] */
+    const double *values;              /* per region an [A_g x R_g] row-major block, consecutive (the layout
+                                          lk_engine_compute_read_likelihoods returns) */
+    const int64_t *region_n_evidence;  /* reads of region g that are still evidence (<= R_g); NULL = all */
+    const int32_t *ref_allele_index;   /* index of the reference haplotype in region g; NULL = 0 */
+    const int64_t *reference_start;    /* per region: padded_reference_loc.get_start() */
+    /* haplotypes */
+    const int64_t *hap_off;            /* [n_haps + 1] */
+    const uint8_t *hap_bases;
+    const int64_t *hap_cigar_off;      /* [n_haps + 1] into hap_cigars */
+    const uint32_t *hap_cigars;        /* BAM-encoded (len << 4 | op) haplotype -> reference CIGARs */
+    const int64_t *hap_start_wrt_ref;  /* Haplotype::alignment_start_hap_wrt_ref */
+    /* reads */
+    const int64_t *read_off;           /* [n_reads + 1] */
+    const uint8_t *read_bases;         /* WITHOUT soft clips (ReadClipper::hard_clip_soft_clipped_bases is the caller's) */
+    const int64_t *read_cigar_off;     /* [n_reads + 1] into read_cigars */
+    const uint32_t *read_cigars;       /* the reads' original CIGARs (their clips are re-attached) */
+    const int64_t *read_orig_len;      /* original read lengths (with soft clips) */
+    double informative_threshold;      /* 0 = LOG_10_INFORMATIVE_THRESHOLD (0.2) */
+} lk_realign_batch;
+
+/*
+ * Outputs per read: best_allele (index inside its region, -1 = none), informative (BestAllele::is_informative; may be
+ * NULL), the new CIGAR (max_ops elements per read) with n_ops >= 0, or n_ops = -1 read not realigned, -2 capacity,
+ * -4 where the reference would panic; pos = new alignment start.
+ */
+lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch *batch, int32_t max_ops, int32_t *best_allele,
+                                 uint8_t *informative, uint32_t *cigar_ops, int32_t *n_ops, int64_t *pos);
+
+/* Host-side pieces of the above, usable (and tested) on their own. */
+lk_status lk_best_alleles_breaking_ties(const double *values, int64_t n_alleles, int64_t n_reads, int64_t n_evidence,
+                                        const int32_t *priorities /* may be NULL */, double informative_threshold,
+                                        int32_t *best_allele, double *confidence /* may be NULL */,
+                                        uint8_t *informative /* may be NULL */);
+lk_status lk_realign_finish(const uint8_t *read, int64_t read_len, const uint32_t *orig_cigar, int32_t orig_n,
+                            int64_t orig_read_len, const uint32_t *sw_ops, int32_t sw_n_ops, int32_t sw_offset,
+                            const uint32_t *hap_cigar, int32_t hap_cigar_n, int64_t hap_start_wrt_ref,
+                            const uint8_t *ref_hap, int64_t ref_hap_len, int64_t reference_start, int32_t max_ops,
+                            uint32_t *out_ops, int32_t *out_n_ops, int64_t *out_pos);
+/* AlignmentUtils::apply_cigar_to_cigar (alignment_utils.rs:240-281); out_n_ops = -4 where the reference panics */
+lk_status lk_cigar_apply_to_cigar(const uint32_t *first_to_second, int32_t n12, const uint32_t *second_to_third, int32_t n23,
+                                  int32_t max_ops, uint32_t *out_ops, int32_t *out_n_ops);
+/* AlignmentUtils::append_clipped_elements_from_cigar_to_cigar (:173-205) */
+lk_status lk_cigar_append_clipped_elements(const uint32_t *cigar, int32_t n, const uint32_t *original, int32_t n_orig,
+                                           int32_t max_ops, uint32_t *out_ops, int32_t *out_n_ops);
+/* AlignmentUtils::read_start_on_reference_haplotype (:283-312); -1 where the reference panics */
+int64_t lk_read_start_on_reference_haplotype(const uint32_t *hap_vs_ref_cigar, int32_t n, uint32_t read_start_on_haplotype);
+
 /* ---------------------------------------------------------------- engine pre/post-ops (host side) */
 
 /* PCRErrorModel (pair_hmm_likelihood_calculation_engine.rs:60-70) */

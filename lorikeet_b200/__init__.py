@@ -6,4 +6,4 @@ reference's modules (src/pair_hmm, src/smith_waterman) so the parity tests read 
 """
 from ._lib import LorikeetError  # noqa: F401
 from .batch import PairHmmBatch  # noqa: F401
-from .context import Context  # noqa: F401
+from .context import Context, RealignBatch  # noqa: F401

@@ -20,7 +20,7 @@ f32p = C.POINTER(C.c_float)
 LK_OK, LK_ERR_INVALID, LK_ERR_CUDA, LK_ERR_NOMEM, LK_ERR_CAPACITY = 0, 1, 2, 3, 4
 STATUS_NAMES = {0: "LK_OK", 1: "LK_ERR_INVALID", 2: "LK_ERR_CUDA", 3: "LK_ERR_NOMEM", 4: "LK_ERR_CAPACITY"}
 
-# the 29 entry points include/lorikeet_b200.h declares
+# the entry points include/lorikeet_b200.h declares
 EXPORTED_SYMBOLS = [
     "lk_create", "lk_destroy", "lk_last_error", "lk_version", "lk_set_tristate_correction", "lk_set_force_f64",
     "lk_pairhmm_batch_dims", "lk_pairhmm_batch_host", "lk_pairhmm_upload", "lk_pairhmm_run_resident",
@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = [
     "lk_sw_batch_host", "lk_sw_upload", "lk_sw_run_resident", "lk_sw_download", "lk_sw_align",
     "lk_calculate_cigar_batch", "lk_calculate_cigar_shortcut", "lk_calculate_cigar_finish",
     "lk_engine_modify_read_qualities", "lk_engine_compute_read_likelihoods",
+    "lk_realign_reads_batch", "lk_best_alleles_breaking_ties", "lk_realign_finish", "lk_cigar_apply_to_cigar",
+    "lk_cigar_append_clipped_elements", "lk_read_start_on_reference_haplotype",
 ]
 
 
@@ -71,6 +73,29 @@ class EngineArgs(C.Structure):
         ("symmetrically_normalize_alleles_to_reference", C.c_int32),
         ("disable_cap_read_qualities_to_mapq", C.c_int32),
         ("modify_soft_clipped_bases", C.c_int32),
+    ]
+
+
+class RealignBatchStruct(C.Structure):
+    _fields_ = [
+        ("n_regions", C.c_int64),
+        ("region_read_start", i64p),
+        ("region_hap_start", i64p),
+        ("values", f64p),
+        ("region_n_evidence", i64p),
+        ("ref_allele_index", i32p),
+        ("reference_start", i64p),
+        ("hap_off", i64p),
+        ("hap_bases", u8p),
+        ("hap_cigar_off", i64p),
+        ("hap_cigars", u32p),
+        ("hap_start_wrt_ref", i64p),
+        ("read_off", i64p),
+        ("read_bases", u8p),
+        ("read_cigar_off", i64p),
+        ("read_cigars", u32p),
+        ("read_orig_len", i64p),
+        ("informative_threshold", C.c_double),
     ]
 
 
@@ -134,6 +159,19 @@ def load():
     L.lk_engine_modify_read_qualities.argtypes = [ep, C.c_int64, i64p, u8p, u8p, u8p, u8p, u8p, C.c_int]
     L.lk_engine_compute_read_likelihoods.restype = C.c_int
     L.lk_engine_compute_read_likelihoods.argtypes = [vp, ep, bp, u8p, i32p, f64p, u8p]
+    L.lk_realign_reads_batch.restype = C.c_int
+    L.lk_realign_reads_batch.argtypes = [vp, C.POINTER(RealignBatchStruct), C.c_int32, i32p, u8p, u32p, i32p, i64p]
+    L.lk_best_alleles_breaking_ties.restype = C.c_int
+    L.lk_best_alleles_breaking_ties.argtypes = [f64p, C.c_int64, C.c_int64, C.c_int64, i32p, C.c_double, i32p, f64p, u8p]
+    L.lk_realign_finish.restype = C.c_int
+    L.lk_realign_finish.argtypes = [u8p, C.c_int64, u32p, C.c_int32, C.c_int64, u32p, C.c_int32, C.c_int32, u32p, C.c_int32,
+                                    C.c_int64, u8p, C.c_int64, C.c_int64, C.c_int32, u32p, i32p, i64p]
+    L.lk_cigar_apply_to_cigar.restype = C.c_int
+    L.lk_cigar_apply_to_cigar.argtypes = [u32p, C.c_int32, u32p, C.c_int32, C.c_int32, u32p, i32p]
+    L.lk_cigar_append_clipped_elements.restype = C.c_int
+    L.lk_cigar_append_clipped_elements.argtypes = [u32p, C.c_int32, u32p, C.c_int32, C.c_int32, u32p, i32p]
+    L.lk_read_start_on_reference_haplotype.restype = C.c_int64
+    L.lk_read_start_on_reference_haplotype.argtypes = [u32p, C.c_int32, C.c_uint32]
     # introspection helpers (not part of the public header)
     L.lk_resident_launch_count.restype = C.c_int32
     L.lk_resident_launch_count.argtypes = [vp]

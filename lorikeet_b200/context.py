@@ -14,6 +14,55 @@ def cigar_to_string(ops):
     return "".join("%d%s" % (int(o) >> 4, CIGAR_CHARS[int(o) & 0xF]) for o in ops)
 
 
+def cigar_from_string(text):
+    """'3M1I2M' -> BAM-encoded uint32 elements (len << 4 | op)."""
+    import re
+    return np.asarray([(int(n) << 4) | CIGAR_CHARS.index(c) for n, c in re.findall(r"(\d+)([MIDNSHP=X])", text)], dtype=np.uint32)
+
+
+class RealignBatch:
+    """Inputs of AssemblyBasedCallerUtils::realign_reads_to_their_best_haplotype for a batch of single-sample regions
+    (assembly/assembly_based_caller_utils.rs:208-246); see lk_realign_batch in include/lorikeet_b200.h."""
+
+    def __init__(self, region_read_start, region_hap_start, values, hap_seqs, hap_cigars, hap_start_wrt_ref, read_seqs,
+                 read_cigars, reference_start, read_orig_len=None, ref_allele_index=None, region_n_evidence=None,
+                 informative_threshold=0.0):
+        as_u8 = lambda x: np.frombuffer(x.encode(), np.uint8) if isinstance(x, str) else np.asarray(x, np.uint8)
+        self.region_read_start = np.ascontiguousarray(region_read_start, np.int64)
+        self.region_hap_start = np.ascontiguousarray(region_hap_start, np.int64)
+        self.values = np.ascontiguousarray(values, np.float64).ravel()
+        haps = [as_u8(h) for h in hap_seqs]
+        reads = [as_u8(r) for r in read_seqs]
+        hc = [cigar_from_string(c) if isinstance(c, str) else np.asarray(c, np.uint32) for c in hap_cigars]
+        rc = [cigar_from_string(c) if isinstance(c, str) else np.asarray(c, np.uint32) for c in read_cigars]
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if len(xs) else np.zeros(0, dt), dt)
+        off = lambda xs: np.ascontiguousarray(np.concatenate([[0], np.cumsum([len(x) for x in xs])]), np.int64)
+        self.hap_off, self.hap_bases = off(haps), cat(haps, np.uint8)
+        self.read_off, self.read_bases = off(reads), cat(reads, np.uint8)
+        self.hap_cigar_off, self.hap_cigars = off(hc), cat(hc, np.uint32)
+        self.read_cigar_off, self.read_cigars = off(rc), cat(rc, np.uint32)
+        self.hap_start_wrt_ref = np.ascontiguousarray(hap_start_wrt_ref, np.int64)
+        self.reference_start = np.ascontiguousarray(reference_start, np.int64)
+        self.read_orig_len = np.ascontiguousarray(read_orig_len if read_orig_len is not None else [len(r) for r in reads], np.int64)
+        self.ref_allele_index = None if ref_allele_index is None else np.ascontiguousarray(ref_allele_index, np.int32)
+        self.region_n_evidence = None if region_n_evidence is None else np.ascontiguousarray(region_n_evidence, np.int64)
+        self.informative_threshold = float(informative_threshold)
+
+    @property
+    def n_reads(self):
+        return int(self.region_read_start[-1])
+
+    def as_struct(self):
+        p = lambda a, t: None if a is None else a.ctypes.data_as(t)
+        S = _lib.RealignBatchStruct
+        return S(len(self.region_read_start) - 1, p(self.region_read_start, _lib.i64p), p(self.region_hap_start, _lib.i64p),
+                 p(self.values, _lib.f64p), p(self.region_n_evidence, _lib.i64p), p(self.ref_allele_index, _lib.i32p),
+                 p(self.reference_start, _lib.i64p), p(self.hap_off, _lib.i64p), p(self.hap_bases, _lib.u8p),
+                 p(self.hap_cigar_off, _lib.i64p), p(self.hap_cigars, _lib.u32p), p(self.hap_start_wrt_ref, _lib.i64p),
+                 p(self.read_off, _lib.i64p), p(self.read_bases, _lib.u8p), p(self.read_cigar_off, _lib.i64p),
+                 p(self.read_cigars, _lib.u32p), p(self.read_orig_len, _lib.i64p), self.informative_threshold)
+
+
 class Context:
     def __init__(self, device=-1):
         self._L = _lib.load()
@@ -142,6 +191,29 @@ class Context:
             else:
                 out.append(cigar_to_string(ops[i, :n_ops[i]]))
         return out
+
+    def realign_reads_batch(self, batch, max_ops=64):
+        """realign_reads_to_their_best_haplotype: (best_allele[int32], informative[uint8], cigars[list of str or None where
+        the read is not realigned], pos[int64])."""
+        n = batch.n_reads
+        best = np.zeros(n, np.int32)
+        info = np.zeros(n, np.uint8)
+        ops = np.zeros((max(n, 1), max_ops), np.uint32)
+        n_ops = np.zeros(n, np.int32)
+        pos = np.zeros(n, np.int64)
+        st = batch.as_struct()
+        self._check(self._L.lk_realign_reads_batch(self._h, C.byref(st), int(max_ops), best.ctypes.data_as(_lib.i32p),
+                                                   info.ctypes.data_as(_lib.u8p), ops.ctypes.data_as(_lib.u32p),
+                                                   n_ops.ctypes.data_as(_lib.i32p), pos.ctypes.data_as(_lib.i64p)))
+        cigars = []
+        for i in range(n):
+            if n_ops[i] == -1:
+                cigars.append(None)
+            elif n_ops[i] < 0:
+                raise LorikeetError(_lib.LK_ERR_INVALID, "realignment failed for read %d (code %d)" % (i, n_ops[i]))
+            else:
+                cigars.append(cigar_to_string(ops[i, :n_ops[i]]))
+        return best, info, cigars, pos
 
     def sw_upload(self, ref_off, refs, alt_off, alts, params, strategy, max_ops=64):
         return ResidentSw(self, ref_off, refs, alt_off, alts, params, strategy, max_ops)

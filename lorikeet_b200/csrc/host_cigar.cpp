@@ -11,6 +11,7 @@
 // ONE lk_sw batch; what remains here is O(n+m) CIGAR surgery per pair, kept on the host like the reference.
 // CIGAR elements are BAM-encoded u32 (len << 4 | op; M=0 I=1 D=2 N=3 S=4 H=5 P=6 '='=7 X=8).
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -341,6 +342,312 @@ extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, cons
                                        sw_ops.data() + i * (size_t)sw_max_ops, sw_n[i], sw_off[i], max_ops, cigar_ops + p * max_ops,
                                        &n_ops[p]);
         if (st != LK_OK) return lk_fail(ctx, st, "calculate_cigar_finish failed");
+    }
+    return LK_OK;
+}
+
+// =================================================================================================
+// N2: AssemblyBasedCallerUtils::realign_reads_to_their_best_haplotype
+//   best allele per read with tie-breaking   src/model/allele_likelihoods.rs:457-554, :1043-1096
+//   tie-breaking priority                    src/assembly/assembly_based_caller_utils.rs:187-195
+//   create_read_aligned_to_ref               src/reads/alignment_utils.rs:40-164
+//   append_clipped_elements_from_cigar...    :173-205      apply_cigar_to_cigar  :240-281 (+ CigarPairTransform :969-1063)
+//   read_start_on_reference_haplotype        :283-312      Haplotype::get_consolidated_padded_cigar  haplotype.rs:248-256
+// The O(R*H) part -- one Smith-Waterman per read against its best haplotype, SoftClip,
+// ALIGNMENT_TO_BEST_HAPLOTYPE_SW_PARAMETERS (10, -15, -30, -5) -- is ONE lk_sw batch on the GPU; best-allele
+// selection and the O(R+H) CIGAR composition stay on the host like the reference.
+// =================================================================================================
+namespace {
+
+constexpr uint32_t kHapPad = 1000;  // get_consolidated_padded_cigar(1000), alignment_utils.rs:89
+
+// CigarBuilder::new(true).add_all(c).make(false)
+BuilderResult consolidate(const std::vector<uint32_t> &c) {
+    CigarBuilder b(true);
+    for (uint32_t e : c)
+        if (!b.add(e)) { BuilderResult bad; bad.ok = false; return bad; }
+    return b.make_and_record_deletions_removed_result();
+}
+
+uint32_t read_length_of(const std::vector<uint32_t> &c) {
+    uint32_t n = 0;
+    for (uint32_t e : c) n += len_on_read(e);
+    return n;
+}
+
+// alignment_utils.rs:283-312; ok = false where the reference panics ("Cigar doesn't reach the read start")
+uint32_t read_start_on_reference_haplotype(const std::vector<uint32_t> &hap_vs_ref, uint32_t read_start_on_hap, bool &ok) {
+    ok = true;
+    if (read_start_on_hap == 0) return 0;
+    uint32_t ref_consumed = 0, hap_consumed = 0;
+    for (uint32_t e : hap_vs_ref) {
+        ref_consumed += len_on_ref(e);
+        hap_consumed += len_on_read(e);
+        if (hap_consumed >= read_start_on_hap) {
+            const uint32_t excess = consumes_ref(e) ? hap_consumed - read_start_on_hap : 0;
+            return ref_consumed > excess ? ref_consumed - excess : 0;  // saturating_sub
+        }
+    }
+    ok = false;
+    return 0;
+}
+
+// CigarPairTransform::new (alignment_utils.rs:969-1063): op13 (or none), advance12, advance23; false = panic
+bool pair_transform(uint32_t op12, uint32_t op23, int &op13, uint32_t &adv12, uint32_t &adv23) {
+    const bool m12 = op12 == M || op12 == EQ || op12 == X, i12 = op12 == I || op12 == S, d12 = op12 == D;
+    const bool m23 = op23 == M || op23 == EQ || op23 == X, i23 = op23 == I || op23 == S, d23 = op23 == D;
+    if (!(m23 || i23 || d23)) return false;
+    if (m12) {
+        if (m23) { op13 = M; adv12 = 1; adv23 = 1; }
+        else if (i23) { op13 = I; adv12 = 1; adv23 = 1; }
+        else { op13 = D; adv12 = 0; adv23 = 1; }
+        return true;
+    }
+    if (i12) { op13 = I; adv12 = 1; adv23 = 0; return true; }
+    if (d12) {
+        if (m23) { op13 = D; adv12 = 1; adv23 = 1; }
+        else if (i23) { op13 = -1; adv12 = 1; adv23 = 1; }
+        else { op13 = D; adv12 = 0; adv23 = 1; }
+        return true;
+    }
+    return false;
+}
+
+// alignment_utils.rs:240-281
+BuilderResult apply_cigar_to_cigar(const std::vector<uint32_t> &c12, const std::vector<uint32_t> &c23) {
+    BuilderResult bad;
+    bad.ok = false;
+    CigarBuilder nb(true);
+    size_t i12 = 0, i23 = 0;
+    uint32_t e12 = 0, e23 = 0;
+    while (i12 < c12.size() && i23 < c23.size()) {
+        int op13;
+        uint32_t a12, a23;
+        if (!pair_transform(op_of(c12[i12]), op_of(c23[i23]), op13, a12, a23)) return bad;
+        e12 += a12;
+        e23 += a23;
+        if (op13 >= 0 && !nb.add(el((uint32_t)op13, 1))) return bad;
+        if (e12 == len_of(c12[i12])) { i12++; e12 = 0; }
+        if (e23 == len_of(c23[i23])) { i23++; e23 = 0; }
+    }
+    return nb.make_and_record_deletions_removed_result();
+}
+
+// alignment_utils.rs:173-205
+std::vector<uint32_t> append_clipped(const std::vector<uint32_t> &cigar, const std::vector<uint32_t> &orig) {
+    if (orig.empty()) return cigar;
+    size_t first = 0, last = orig.size() - 1;
+    std::vector<uint32_t> out, tail;
+    while (is_clipping(orig[first]) && first != last) out.push_back(orig[first++]);
+    out.insert(out.end(), cigar.begin(), cigar.end());
+    while (is_clipping(orig[last]) && first != last) tail.push_back(orig[last--]);
+    out.insert(out.end(), tail.rbegin(), tail.rend());
+    return out;
+}
+
+}  // namespace
+
+extern "C" lk_status lk_cigar_apply_to_cigar(const uint32_t *c12, int32_t n12, const uint32_t *c23, int32_t n23, int32_t max_ops,
+                                             uint32_t *out_ops, int32_t *out_n_ops) {
+    if (!out_n_ops || !out_ops || n12 < 0 || n23 < 0 || (n12 > 0 && !c12) || (n23 > 0 && !c23)) return LK_ERR_INVALID;
+    BuilderResult r = apply_cigar_to_cigar(std::vector<uint32_t>(c12, c12 + n12), std::vector<uint32_t>(c23, c23 + n23));
+    *out_n_ops = r.ok ? write_ops(r.cigar, max_ops, out_ops) : -4;
+    return LK_OK;
+}
+
+extern "C" lk_status lk_cigar_append_clipped_elements(const uint32_t *cigar, int32_t n, const uint32_t *original, int32_t n_orig,
+                                                      int32_t max_ops, uint32_t *out_ops, int32_t *out_n_ops) {
+    if (!out_n_ops || !out_ops || n < 0 || n_orig < 1 || !original || (n > 0 && !cigar)) return LK_ERR_INVALID;
+    *out_n_ops = write_ops(append_clipped(std::vector<uint32_t>(cigar, cigar + n), std::vector<uint32_t>(original, original + n_orig)),
+                           max_ops, out_ops);
+    return LK_OK;
+}
+
+extern "C" int64_t lk_read_start_on_reference_haplotype(const uint32_t *hap_vs_ref, int32_t n, uint32_t read_start_on_haplotype) {
+    bool ok = true;
+    const uint32_t r = read_start_on_reference_haplotype(std::vector<uint32_t>(hap_vs_ref, hap_vs_ref + (n > 0 ? n : 0)),
+                                                         read_start_on_haplotype, ok);
+    return ok ? (int64_t)r : -1;
+}
+
+// AlleleLikelihoods::search_best_allele(sample, r, can_be_reference = true, Some(priorities)) for every column of one
+// [A x R] row-major block (allele_likelihoods.rs:457-554) and BestAllele::new / is_informative (:1141-1166).
+extern "C" lk_status lk_best_alleles_breaking_ties(const double *values, int64_t n_alleles, int64_t n_reads, int64_t n_evidence,
+                                                   const int32_t *priorities, double informative_threshold, int32_t *best_allele,
+                                                   double *confidence, uint8_t *informative) {
+    if (n_alleles < 0 || n_reads < 0 || n_evidence < 0 || n_evidence > n_reads || (n_alleles > 0 && n_reads > 0 && !values))
+        return LK_ERR_INVALID;
+    if (!best_allele) return LK_ERR_INVALID;
+    for (int64_t r = 0; r < n_evidence; r++) {
+        if (n_alleles == 0) {  // BestAllele with allele None
+            best_allele[r] = -1;
+            if (confidence) confidence[r] = 0.0;
+            if (informative) informative[r] = 0;
+            continue;
+        }
+        auto v = [&](int64_t a) { return values[a * n_reads + r]; };
+        int64_t best = 0, second = 0;
+        double best_lk = v(0), second_lk = -INFINITY;
+        for (int64_t a = 1; a < n_alleles; a++) {
+            const double c = v(a);
+            if (c > best_lk) { second = best; best = a; second_lk = best_lk; best_lk = c; }
+            else if (c > second_lk) { second = a; second_lk = c; }
+        }
+        if (priorities && (best_lk - second_lk) < informative_threshold) {
+            int32_t best_pr = priorities[best], second_pr = priorities[second];
+            for (int64_t a = 0; a < n_alleles; a++) {
+                const double c = v(a);
+                if (a == best || (best_lk - c) > informative_threshold) continue;
+                const int32_t pr = priorities[a];
+                if (pr > best_pr) { second = best; best = a; second_pr = best_pr; best_pr = pr; }
+                else if (pr > second_pr) { second = a; second_pr = pr; }
+            }
+        }
+        best_lk = v(best);
+        second_lk = (second != best) ? v(second) : -INFINITY;
+        const double diff = best_lk - second_lk;
+        const double conf = (fabs(diff) < 2.220446049250313e-16) ? 0.0 : diff;  // f64::EPSILON
+        best_allele[r] = (int32_t)best;
+        if (confidence) confidence[r] = conf;
+        if (informative) informative[r] = conf > informative_threshold ? 1 : 0;
+    }
+    return LK_OK;
+}
+
+// create_read_aligned_to_ref after the alignment (alignment_utils.rs:62-163).  Inputs: the read WITHOUT its soft clips
+// (ReadClipper::hard_clip_soft_clipped_bases is the caller's), its original CIGAR, the read->haplotype SW result, the
+// haplotype's CIGAR against the reference and alignment_start_hap_wrt_ref, the reference haplotype's bases and
+// reference_start.  out_n_ops: >= 0 elements of the new CIGAR (clips re-attached); -1 the read is not realigned
+// (alignment_offset == -1, :63-66); -2 capacity; -4 where the reference would panic.
+extern "C" lk_status lk_realign_finish(const uint8_t *read, int64_t read_len, const uint32_t *orig_cigar, int32_t orig_n,
+                                       int64_t orig_read_len, const uint32_t *sw_ops, int32_t sw_n_ops, int32_t sw_offset,
+                                       const uint32_t *hap_cigar, int32_t hap_cigar_n, int64_t hap_start_wrt_ref,
+                                       const uint8_t *ref_hap, int64_t ref_hap_len, int64_t reference_start, int32_t max_ops,
+                                       uint32_t *out_ops, int32_t *out_n_ops, int64_t *out_pos) {
+    if (!out_n_ops || !out_ops || !out_pos || orig_n < 1 || !orig_cigar || hap_cigar_n < 0 || (hap_cigar_n > 0 && !hap_cigar))
+        return LK_ERR_INVALID;
+    if (sw_offset == -1) { *out_n_ops = -1; return LK_OK; }
+    if (sw_n_ops < 0) { *out_n_ops = -4; return LK_OK; }
+    BuilderResult sw_cigar = consolidate(std::vector<uint32_t>(sw_ops, sw_ops + sw_n_ops));
+    if (!sw_cigar.ok) { *out_n_ops = -4; return LK_OK; }
+    std::vector<uint32_t> padded_in(hap_cigar, hap_cigar + hap_cigar_n);
+    padded_in.push_back(el(M, kHapPad));
+    BuilderResult padded = consolidate(padded_in);
+    if (!padded.ok) { *out_n_ops = -4; return LK_OK; }
+    bool ok = true;
+    const uint32_t start_on_ref_hap = read_start_on_reference_haplotype(padded.cigar, (uint32_t)sw_offset, ok);
+    if (!ok) { *out_n_ops = -4; return LK_OK; }
+    const int64_t read_start_on_reference = reference_start + hap_start_wrt_ref + (int64_t)start_on_ref_hap;
+    const uint32_t padded_read_len = read_length_of(padded.cigar);
+    if (padded_read_len == 0) { *out_n_ops = -4; return LK_OK; }
+    BuilderResult hap_to_ref = trim_cigar_by_bases(padded.cigar, (uint32_t)sw_offset, padded_read_len - 1);
+    if (!hap_to_ref.ok) { *out_n_ops = -4; return LK_OK; }
+    BuilderResult read_to_ref = apply_cigar_to_cigar(sw_cigar.cigar, hap_to_ref.cigar);
+    if (!read_to_ref.ok) { *out_n_ops = -4; return LK_OK; }
+    BuilderResult la = left_align_indels(read_to_ref.cigar, ref_hap, (int)ref_hap_len, read, (int)read_len, start_on_ref_hap);
+    if (!la.ok) { *out_n_ops = -4; return LK_OK; }
+    *out_pos = read_start_on_reference + (int64_t)la.leading_deletion_bases_removed;
+    const std::vector<uint32_t> with_clips = append_clipped(la.cigar, std::vector<uint32_t>(orig_cigar, orig_cigar + orig_n));
+    // :148-160 "Cigar ... with read length ... != read length"
+    const int64_t soft_clipped = orig_read_len - read_len;
+    if ((int64_t)read_length_of(la.cigar) + soft_clipped != orig_read_len) { *out_n_ops = -4; return LK_OK; }
+    *out_n_ops = write_ops(with_clips, max_ops, out_ops);
+    return LK_OK;
+}
+
+// realign_reads_to_their_best_haplotype for a batch of single-sample regions (assembly_based_caller_utils.rs:208-246).
+extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch *b, int32_t max_ops, int32_t *best_allele,
+                                            uint8_t *informative, uint32_t *cigar_ops, int32_t *n_ops, int64_t *pos) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (!b || max_ops < 1 || b->n_regions < 0) return lk_fail(ctx, LK_ERR_INVALID, "bad realign arguments");
+    if (b->n_regions == 0) return LK_OK;
+    if (!b->region_read_start || !b->region_hap_start || !b->values || !b->hap_off || !b->hap_bases || !b->hap_cigar_off ||
+        !b->hap_cigars || !b->hap_start_wrt_ref || !b->read_off || !b->read_bases || !b->read_cigar_off || !b->read_cigars ||
+        !b->read_orig_len || !b->reference_start || !best_allele || !cigar_ops || !n_ops || !pos)
+        return lk_fail(ctx, LK_ERR_INVALID, "null realign arrays");
+    const int64_t n_reads = b->region_read_start[b->n_regions];
+    const double thr = b->informative_threshold > 0.0 ? b->informative_threshold : 0.2;  // LOG_10_INFORMATIVE_THRESHOLD
+    // ---- best haplotype per read (host) ----
+    std::vector<uint8_t> info((size_t)n_reads, 0);
+    std::vector<int64_t> pair_of((size_t)n_reads, -1);
+    int64_t vbase = 0;
+    std::vector<int64_t> ro(1, 0), ao(1, 0);
+    std::vector<int64_t> todo;
+    for (int64_t g = 0; g < b->n_regions; g++) {
+        const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
+        const int64_t h0 = b->region_hap_start[g], h1 = b->region_hap_start[g + 1];
+        const int64_t A = h1 - h0, R = r1 - r0;
+        if (A < 0 || R < 0) return lk_fail(ctx, LK_ERR_INVALID, "decreasing region offsets");
+        const int64_t n_ev = b->region_n_evidence ? b->region_n_evidence[g] : R;
+        if (n_ev < 0 || n_ev > R) return lk_fail(ctx, LK_ERR_INVALID, "bad evidence count");
+        // haplotype_alignment_tiebreaking_priority: (is_ref ? 1 : 0) + 1 - cigar elements
+        std::vector<int32_t> prio((size_t)A);
+        for (int64_t a = 0; a < A; a++) {
+            const int32_t n_el = (int32_t)(b->hap_cigar_off[h0 + a + 1] - b->hap_cigar_off[h0 + a]);
+            const bool is_ref = b->ref_allele_index ? (b->ref_allele_index[g] == a) : (a == 0);
+            prio[(size_t)a] = (is_ref ? 1 : 0) + 1 - n_el;
+        }
+        lk_status st = lk_best_alleles_breaking_ties(b->values + vbase, A, R, n_ev, prio.data(), thr, best_allele + r0, nullptr,
+                                                     info.data() + r0);
+        if (st != LK_OK) return lk_fail(ctx, st, "best_alleles failed");
+        for (int64_t r = r0; r < r1; r++) {
+            if (r - r0 >= n_ev || best_allele[r] < 0) { best_allele[r] = -1; n_ops[r] = -1; pos[r] = 0; continue; }
+            const int64_t h = h0 + best_allele[r];
+            pair_of[(size_t)r] = (int64_t)todo.size();
+            todo.push_back(r);
+            ro.push_back(ro.back() + (b->hap_off[h + 1] - b->hap_off[h]));
+            ao.push_back(ao.back() + (b->read_off[r + 1] - b->read_off[r]));
+        }
+        vbase += A * R;
+    }
+    if (informative) memcpy(informative, info.data(), (size_t)n_reads);
+    if (todo.empty()) return LK_OK;
+    // ---- one SW batch: reference = best haplotype, alternate = read without soft clips ----
+    std::vector<uint8_t> refs((size_t)ro.back()), alts((size_t)ao.back());
+    int64_t longest = 0;
+    for (size_t i = 0; i < todo.size(); i++) {
+        const int64_t r = todo[i];
+        const int64_t rl = b->read_off[r + 1] - b->read_off[r];
+        memcpy(alts.data() + ao[i], b->read_bases + b->read_off[r], (size_t)rl);
+        longest = std::max(longest, rl);
+    }
+    {
+        size_t i = 0;
+        for (int64_t g = 0; g < b->n_regions; g++) {
+            const int64_t h0 = b->region_hap_start[g];
+            for (int64_t r = b->region_read_start[g]; r < b->region_read_start[g + 1]; r++) {
+                if (pair_of[(size_t)r] < 0) continue;
+                const int64_t h = h0 + best_allele[r];
+                memcpy(refs.data() + ro[i], b->hap_bases + b->hap_off[h], (size_t)(b->hap_off[h + 1] - b->hap_off[h]));
+                i++;
+            }
+        }
+    }
+    const lk_sw_params prm = { 10, -15, -30, -5 };  // ALIGNMENT_TO_BEST_HAPLOTYPE_SW_PARAMETERS, smith_waterman_aligner.rs:22-25
+    const int32_t sw_max_ops = std::max<int32_t>(max_ops, 64);
+    std::vector<uint32_t> sw_ops(todo.size() * (size_t)sw_max_ops);
+    std::vector<int32_t> sw_n(todo.size()), sw_off(todo.size());
+    lk_status st = lk_sw_batch_host(ctx, (int64_t)todo.size(), ro.data(), refs.data(), ao.data(), alts.data(), &prm, LK_SW_SOFTCLIP,
+                                    sw_max_ops, sw_ops.data(), sw_n.data(), sw_off.data());
+    if (st != LK_OK) return st;
+    // ---- CIGAR composition per read (host) ----
+    size_t i = 0;
+    for (int64_t g = 0; g < b->n_regions; g++) {
+        const int64_t h0 = b->region_hap_start[g];
+        const int64_t href = h0 + (b->ref_allele_index ? b->ref_allele_index[g] : 0);
+        for (int64_t r = b->region_read_start[g]; r < b->region_read_start[g + 1]; r++) {
+            if (pair_of[(size_t)r] < 0) continue;
+            const int64_t h = h0 + best_allele[r];
+            if (sw_n[i] == -2) { n_ops[r] = -2; i++; continue; }
+            st = lk_realign_finish(b->read_bases + b->read_off[r], b->read_off[r + 1] - b->read_off[r],
+                                   b->read_cigars + b->read_cigar_off[r], (int32_t)(b->read_cigar_off[r + 1] - b->read_cigar_off[r]),
+                                   b->read_orig_len[r], sw_ops.data() + i * (size_t)sw_max_ops, sw_n[i], sw_off[i],
+                                   b->hap_cigars + b->hap_cigar_off[h], (int32_t)(b->hap_cigar_off[h + 1] - b->hap_cigar_off[h]),
+                                   b->hap_start_wrt_ref[h], b->hap_bases + b->hap_off[href], b->hap_off[href + 1] - b->hap_off[href],
+                                   b->reference_start[g], max_ops, cigar_ops + r * (int64_t)max_ops, &n_ops[r], &pos[r]);
+            if (st != LK_OK) return lk_fail(ctx, st, "realign_finish failed");
+            i++;
+        }
     }
     return LK_OK;
 }

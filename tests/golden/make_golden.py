@@ -10,6 +10,9 @@ reference code is copied.  Sources:
   * tests/smith_waterman_aligner_unit_tests.rs:229-400 -> sw_known_answers.json
   * tests/smith_waterman_aligner_unit_tests.rs:403-1000 (ref_N/read_N/cigar_N) -> sw_long_pairs.json
   * tests/cigar_utils_unit_tests.rs:36-110          -> calculate_cigar_cases.json
+  * tests/alignment_utils_unit_tests.rs:155-340 (create_read_aligned_to_ref known answers), :840-878
+    (apply_cigar_to_cigar), :902-916 (append_clipped_elements...), :1017-1024 (read_start_on_reference_haplotype)
+                                                     -> realign_cases.json
 """
 import argparse
 import json
@@ -63,6 +66,53 @@ def calculate_cigar_cases(path):
     return [dict(ref=a, alt=b, cigar=c) for a, b, c in cases]
 
 
+def realign_cases(path):
+    """Known answers of the reference's create_read_aligned_to_ref tests.  The data provider
+    (make_read_aligned_to_ref_data, tests/alignment_utils_unit_tests.rs:155-340) builds most cases in loops from the
+    literals below; the loops are replayed here, the three long literal examples are pulled out of the file."""
+    src = open(path).read()
+    out = {"aligned_to_ref": [], "apply_cigar_to_cigar": [], "append_clipped": [], "read_start": []}
+    hap = re.search(r'let hap_bases = "([ACGT]+)";', src).group(1)
+    allm = "%dM" % len(hap)
+
+    def case(read, hap_bases, hap_cigar, hap_start, ref_bases, ref_start, pos, cigar, line):
+        out["aligned_to_ref"].append(dict(read=read, hap=hap_bases, hap_cigar=hap_cigar, hap_start=hap_start, ref=ref_bases,
+                                          ref_start=ref_start, expected_pos=pos, expected_cigar=cigar, read_cigar="10M",
+                                          source="tests/alignment_utils_unit_tests.rs:%d" % line))
+    for i in range(-1, len(hap)):   # :160-180 one substitution to 'A' anywhere: still all-M
+        b = list(hap)
+        if i != -1:
+            b[i] = "A"
+        case("".join(b), hap, allm, 0, hap, 10, 10, allm, 160)
+    for pad in range(1, 10):        # :183-199 insertions at the front
+        case("N" * pad + hap, hap, allm, 0, hap, 10, 10, "%dI%s" % (pad, allm), 183)
+    for pad in range(1, 10):        # :202-217 insertions at the back
+        case(hap + "N" * pad, hap, allm, 0, hap, 10, 10, "%s%dI" % (allm, pad), 202)
+    for ref_start in range(1, 10):  # :220-238 ref_start and hap_start are respected
+        for hap_start in range(ref_start, 10 + ref_start):
+            case(hap, hap, allm, hap_start, hap, ref_start, ref_start + hap_start, allm, 220)
+    # :241-262 SW does not left-align: 31M6D211M must come out as 28M6D214M
+    m = re.search(r'let hap = "([ACGT]+)";\s*let hap_cigar = format!\("\{\}M", hap.len\(\)\);\s*let read_bases = "([ACGT]+)";', src)
+    case(m.group(2), m.group(1), "%dM" % len(m.group(1)), 500, m.group(1), 10130100, 10130740, "28M6D214M", 241)
+    # :265-296 left-align generates a leading deletion; :299-335 haplotype with an indel relative to the reference
+    for m in re.finditer(r'let reference = "([ACGT]+)";.*?let haplotype = "([ACGT]+)";.*?let read_bases = "([ACGT]+)";\s*'
+                         r'let hap_cigar = ([^;]+);.*?let ref_start = (\d+);\s*let hap_start = (\d+);\s*'
+                         r'let alignment_offset = (\d+);\s*let good_cigar = "(\w+)";', src, re.S):
+        ref, h, rd, hc, rs, hs, ao, good = m.groups()
+        hc = hc.strip()
+        hap_cigar = "%dM" % len(h) if hc.startswith("format!") else hc.strip('"')
+        case(rd, h, hap_cigar, int(hs), ref, int(rs), int(rs) + int(hs) + int(ao), good, src[:m.start()].count("\n") + 1)
+    for i in range(1, 5):  # :840-846
+        out["apply_cigar_to_cigar"].append(dict(first="%dM" % i, second="%dM" % i, expected="%dM" % i))
+    for a, b, c in re.findall(r'test_apply_cigar_to_cigar\("(\w+)", "(\w+)", "(\w+)"\);', src):
+        out["apply_cigar_to_cigar"].append(dict(first=a, second=b, expected=c))
+    for a, b, c in re.findall(r'test_append_clipped_elements_from_original_cigar\(\s*"(\w+)",\s*"(\w+)",\s*"(\w+)",?\s*\)', src):
+        out["append_clipped"].append(dict(original=a, shifted=b, expected=c))
+    for a, b, c in re.findall(r'test_read_start_on_reference_haplotype\("(\w+)", (\d+), (\d+)\);', src):
+        out["read_start"].append(dict(cigar=a, read_start_on_haplotype=int(b), expected=int(c)))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -74,6 +124,9 @@ def main():
               open(os.path.join(HERE, "sw_long_pairs.json"), "w"), indent=1)
     cc = calculate_cigar_cases(os.path.join(t, "cigar_utils_unit_tests.rs"))
     json.dump(cc, open(os.path.join(HERE, "calculate_cigar_cases.json"), "w"), indent=1)
+    rc = realign_cases(os.path.join(t, "alignment_utils_unit_tests.rs"))
+    json.dump(rc, open(os.path.join(HERE, "realign_cases.json"), "w"), indent=1)
+    print("realign cases:", {k: len(v) for k, v in rc.items()})
     print("pairhmm rows:", sum(1 for l in open(os.path.join(HERE, "pairhmm-testdata.txt")) if not l.startswith("#")))
     print("calculate_cigar cases:", len(cc))
 
