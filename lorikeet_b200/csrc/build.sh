@@ -5,10 +5,10 @@ cd "$(dirname "$0")"
 OUT=${LK_OUT:-../liblorikeet_b200.so}
 BUILD=${LK_BUILD_DIR:-../_build}
 NVCC=${NVCC:-nvcc}
-FLAGS="${LK_EXTRA_FLAGS} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function"
+FLAGS="${LK_EXTRA_FLAGS} -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-Wno-unused-function,-Wno-unknown-pragmas"
 mkdir -p $BUILD
 pids=()
-for f in pairhmm_kernels.cu sw_kernels.cu lk_api.cu lk_sw_api.cu tools_kernels.cu; do
+for f in pairhmm_kernels.cu sw_kernels.cu engine_kernels.cu lk_api.cu lk_sw_api.cu tools_kernels.cu; do
   [ -f "$f" ] || continue
   o=$BUILD/${f%.cu}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$o" -print -quit)" ] || [ ../../include/lorikeet_b200.h -nt "$o" ]; then
@@ -19,7 +19,7 @@ for f in host_model.cpp host_prep.cpp host_engine.cpp host_synth.cpp host_cigar.
   [ -f "$f" ] || continue
   o=$BUILD/${f%.cpp}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 -name '*.h' -newer "$o" -print -quit)" ] || [ ../../include/lorikeet_b200.h -nt "$o" ]; then
-    g++ -O3 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c "$f" -o "$o" & pids+=($!)
+    g++ -O3 -std=c++17 -fPIC -Wall -Wno-unknown-pragmas -I/usr/local/cuda/include -c "$f" -o "$o" & pids+=($!)
   fi
 done
 for p in "${pids[@]}"; do wait $p; done

@@ -1,0 +1,223 @@
+// engine_kernels.cu — device side of PairHMMLikelihoodCalculationEngine's pre- and post-ops, so the
+// region driver takes raw reads and returns normalised, filtered [allele][read] matrices without host passes.
+//
+//   engine_modify_reads_kernel   modify_read_qualities        pair_hmm_likelihood_calculation_engine.rs:352-426
+//                                  apply_pcr_error_model        :502-526, find_tandem_repeat_units :528-611,
+//                                  find_number_of_repetitions   variant_context_utils.rs:276-337
+//                                  cap_minimum_read_qualities   :428-466
+//   engine_epilogue_kernel       [r*A + h] -> [a][r]            pair_hmm.rs:247-266
+//                                  normalize_likelihoods        allele_likelihoods.rs:378-444 (search_best_allele :457-554)
+//                                  thresholds                   ...engine.rs:244-319 (table :23-39), from the ORIGINAL qualities
+//                                  filter_poorly_modeled_evidence / remove_evidence_by_index   allele_likelihoods.rs:925-1018
+//
+// All byte / f64 compare work, HBM-bound and tiny next to the PairHMM kernels; the f64 arithmetic uses explicit
+// un-fused operations so every threshold rounds exactly like the reference's.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "lk_internal.h"
+
+namespace lk {
+
+namespace {
+
+constexpr int kMaxStrUnitLength = 20;   // ...engine.rs:98
+constexpr int kMaxRepeatLength = 100;   // :99
+constexpr uint8_t kMinUsableQ = 6;      // quality_utils.rs:23
+
+__device__ __forceinline__ bool same_bytes(const uint8_t *a, const uint8_t *b, int n) {
+    for (int i = 0; i < n; i++)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+// VariantContextUtils::find_number_of_repetitions_main (variant_context_utils.rs:276-337)
+__device__ int count_repeats(const uint8_t *unit, int unit_len, const uint8_t *test, int test_len, bool leading) {
+    if (test_len == 0) return 0;
+    const int diff = test_len - unit_len;
+    int reps = 0;
+    if (leading) {
+        for (int s = 0; s <= diff; s += unit_len) {
+            if (!same_bytes(test + s, unit, unit_len)) break;
+            reps++;
+        }
+    } else {
+        for (int s = diff; s >= 0; s -= unit_len) {
+            if (!same_bytes(test + s, unit, unit_len)) break;
+            reps++;
+        }
+    }
+    return reps;
+}
+
+// find_tandem_repeat_units(...).1 (...engine.rs:528-611)
+__device__ int tandem_repeat_length(const uint8_t *bases, int len, int offset) {
+    int max_bw = 0;
+    const uint8_t *best_bw = bases + offset;
+    int best_bw_len = 1;
+    for (int str = 1; str <= kMaxStrUnitLength; str++) {
+        if (offset + 1 < str) break;
+        const uint8_t *unit = bases + offset + 1 - str;
+        max_bw = count_repeats(unit, str, bases, offset + 1, false);
+        if (max_bw > 1) { best_bw = unit; best_bw_len = str; break; }
+    }
+    int max_rl = max_bw;
+    if (offset < len - 1) {
+        const uint8_t *best_fw = bases + offset + 1;
+        int best_fw_len = 1, max_fw = 0;
+        for (int str = 1; str <= kMaxStrUnitLength; str++) {
+            if (offset + str + 1 > len) break;
+            const uint8_t *unit = bases + offset + 1;
+            max_fw = count_repeats(unit, str, bases + offset + 1, len - offset - 1, true);
+            if (max_fw > 1) { best_fw = unit; best_fw_len = str; break; }
+        }
+        if (best_fw_len == best_bw_len && same_bytes(best_fw, best_bw, best_fw_len)) {
+            max_rl = max_bw + max_fw;
+        } else {
+            max_bw = count_repeats(best_fw, best_fw_len, bases, offset + 1, false);
+            max_rl = max_fw + max_bw;
+        }
+    }
+    return max_rl < kMaxRepeatLength ? max_rl : kMaxRepeatLength;
+}
+
+// ...engine.rs:23-39, (mean, variance) for baseQ 1..40
+__constant__ double kDynMean[40] = {
+    5.996842844, 5.870018422, 5.401558531, 4.818940919, 4.218758304, 3.646319832, 3.122346753, 2.654731979, 2.244479156, 1.88893867,
+    1.583645342, 1.3233807, 1.102785365, 0.916703025, 0.760361881, 0.629457387, 0.520175654, 0.42918208, 0.353590663, 0.290923699,
+    0.23906788, 0.196230431, 0.160897421, 0.131795374, 0.1078567, 0.088189063, 0.072048567, 0.058816518, 0.047979438, 0.039111985,
+    0.031862437, 0.025940415, 0.021106532, 0.017163711, 0.013949904, 0.011332027, 0.009200898, 0.007467036, 0.006057179, 0.004911394 };
+__constant__ double kDynVar[40] = {
+    0.196616587, 1.388545569, 5.641990128, 10.33176216, 14.25799688, 17.02880749, 18.64537883, 19.27521677, 19.13584613, 18.43922003,
+    17.36842261, 16.07088712, 14.65952563, 13.21718577, 11.80207947, 10.45304833, 9.194183767, 8.038657241, 6.991779595, 6.053379213,
+    5.219610436, 4.484302033, 3.839943445, 3.27839108, 2.791361596, 2.370765375, 2.008921719, 1.698687797, 1.433525748, 1.207526336,
+    1.015402928, 0.852465956, 0.714585285, 0.598145851, 0.500000349, 0.41742159, 0.348056286, 0.289881373, 0.241163527, 0.200422214 };
+
+}  // namespace
+
+// one warp per read, lanes over its bases; in place on the staged copies
+__global__ void engine_modify_reads_kernel(EngineDevArgs E, int64_t n_reads) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n_reads; r += n_warps) {
+        const int64_t o = E.read_off[r];
+        const int len = (int)(E.read_off[r + 1] - o);
+        const uint8_t *bases = E.read_bases + o;
+        const uint8_t mapq = E.cap_to_mapq ? E.read_mapq[r] : 255;
+        for (int j = lane; j < len; j += 32) {
+            uint8_t q = E.read_qual[o + j], qi = E.read_ins[o + j], qd = E.read_del[o + j];
+            if (E.use_pcr && j < len - 1) {  // apply_pcr_error_model writes i-1 for i in 1..len: the last base is never touched
+                const uint8_t c = E.pcr_cache[tandem_repeat_length(bases, len, j)];
+                qi = qi < c ? qi : c;
+                qd = qd < c ? qd : c;
+            }
+            if (E.cap_to_mapq) q = q < mapq ? q : mapq;     // cap_minimum_read_qualities :428-458
+            if (q < E.bq_threshold) q = kMinUsableQ;
+            if (qi < kMinUsableQ) qi = kMinUsableQ;
+            if (qd < kMinUsableQ) qd = kMinUsableQ;
+            E.read_qual[o + j] = q; E.read_ins[o + j] = qi; E.read_del[o + j] = qd;
+        }
+    }
+}
+
+// one warp per region
+__global__ void engine_epilogue_kernel(EngineDevArgs E, int64_t n_regions) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double ninf = -INFINITY;
+    for (int64_t g = warp; g < n_regions; g += n_warps) {
+        const int64_t r0 = E.region_read_start[g];
+        const int R = (int)(E.region_read_start[g + 1] - r0);
+        const int A = (int)(E.region_hap_start[g + 1] - E.region_hap_start[g]);
+        if (R == 0 || A == 0) continue;
+        const int64_t base = E.read_out_base[r0];  // pairs before this region (chunk-local)
+        const double *src = E.lk + base;            // [r*A + a]
+        double *v = E.values + base;                // [a*R + r]
+        const int ref_idx = E.ref_allele_index ? E.ref_allele_index[g] : 0;
+        const bool normalise = !(E.cap_diff == ninf) && A >= 2;
+        int kept_before = 0;
+        for (int rb = 0; rb < R; rb += 32) {
+            const int r = rb + lane;
+            bool keep = false;
+            double worst = ninf;
+            if (r < R) {
+                // search_best_allele(.., can_be_reference = symmetric, None): only the best likelihood is needed
+                int first = (E.symmetric || ref_idx != 0) ? 0 : 1;
+                double best = src[(int64_t)r * A + first];
+                for (int a = first + 1; a < A; a++) {
+                    if (!E.symmetric && a == ref_idx) continue;
+                    const double c = src[(int64_t)r * A + a];
+                    if (c > best) best = c;
+                }
+                if (normalise) worst = __dadd_rn(best, E.cap_diff);
+                // maximum over ALL alleles after normalisation (filter_poorly_modeled_evidence)
+                double mx = ninf;
+                for (int a = 0; a < A; a++) {
+                    double c = src[(int64_t)r * A + a];
+                    if (normalise && c < worst) c = worst;
+                    if (c > mx) mx = c;
+                }
+                // threshold from the ORIGINAL qualities / length (the "HMMQuals" key quirk)
+                const int64_t o = E.read_off[r0 + r];
+                const int len = (int)(E.read_off[r0 + r + 1] - o);
+                double e = ceil(__dmul_rn((double)len, E.expected_error_rate));
+                double thr;
+                if (E.dynamic_disq) {
+                    double mean = 0.0, var = 0.0;
+                    for (int i = 0; i < len; i++) {
+                        const int bq = E.qual_orig[o + i];
+                        const int entry = bq <= 1 ? 0 : (bq < 40 ? bq : 40) - 1;
+                        mean = __dadd_rn(mean, kDynMean[entry]);
+                        var = __dadd_rn(var, kDynVar[entry]);
+                    }
+                    const double dyn = __dmul_rn(__dadd_rn(mean, __dmul_rn(E.disq_scale, sqrt(var))), -0.1);
+                    const double stat = __dmul_rn(e, -4.0);
+                    thr = dyn < stat ? dyn : stat;
+                } else {
+                    thr = __dmul_rn(e < 2.0 ? e : 2.0, -4.0);
+                }
+                keep = !(mx < thr);
+                if (E.keep) E.keep[r0 + r] = keep ? 1 : 0;
+            }
+            const unsigned kb = __ballot_sync(0xffffffffu, keep);
+            if (keep) {  // compacted column of this read
+                const int col = kept_before + __popc(kb & ((1u << lane) - 1u));
+                for (int a = 0; a < A; a++) {
+                    double c = src[(int64_t)r * A + a];
+                    if (normalise && c < worst) c = worst;
+                    v[(int64_t)a * R + col] = c;
+                }
+            }
+            kept_before += __popc(kb);
+        }
+        // tail of every row: NaN (allele_likelihoods.rs:996-1009)
+        const int tail = R - kept_before;
+        for (int t = lane; t < tail * A; t += 32) {
+            const int a = t / tail, c = kept_before + t % tail;
+            v[(int64_t)a * R + c] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
+}
+
+cudaError_t launch_engine_modify(const EngineDevArgs &E, int64_t n_reads, cudaStream_t st) {
+    if (n_reads == 0) return cudaSuccess;
+    const int threads = 128;
+    int64_t blocks = (n_reads * 32 + threads - 1) / threads;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    engine_modify_reads_kernel<<<(unsigned)blocks, threads, 0, st>>>(E, n_reads);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_engine_epilogue(const EngineDevArgs &E, int64_t n_regions, cudaStream_t st) {
+    if (n_regions == 0) return cudaSuccess;
+    const int threads = 128;
+    int64_t blocks = (n_regions * 32 + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    engine_epilogue_kernel<<<(unsigned)blocks, threads, 0, st>>>(E, n_regions);
+    return cudaGetLastError();
+}
+
+}  // namespace lk

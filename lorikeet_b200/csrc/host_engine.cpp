@@ -10,8 +10,8 @@
 // and src/model/allele_likelihoods.rs normalize_likelihoods :378-444, search_best_allele :457-554,
 // filter_poorly_modeled_evidence :925-1018; src/model/variant_context_utils.rs:240-348.
 //
-// Kept on the host on purpose (SURVEY 8a/a2,a7): the work is O(reads * R * 20) byte compares with side effects on
-// the caller's read lists; the GPU part is the (read x haplotype) likelihood block in between.
+// lk_engine_modify_read_qualities is the stand-alone host utility (in place on the caller's arrays); the region driver
+// lk_engine_compute_read_likelihoods runs the same pre-ops and the post-ops on the device (engine_kernels.cu, N3).
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -110,43 +110,6 @@ void modify_one_read(const uint8_t *cache, bool use_pcr, const uint8_t *bases, u
     }
 }
 
-// :23-39, rows (baseQ, mean, variance) for baseQ 1..40
-const double kDynTable[] = {
-    1.0, 5.996842844, 0.196616587, 2.0, 5.870018422, 1.388545569, 3.0, 5.401558531, 5.641990128,
-    4.0, 4.818940919, 10.33176216, 5.0, 4.218758304, 14.25799688, 6.0, 3.646319832, 17.02880749,
-    7.0, 3.122346753, 18.64537883, 8.0, 2.654731979, 19.27521677, 9.0, 2.244479156, 19.13584613,
-    10.0, 1.88893867, 18.43922003, 11.0, 1.583645342, 17.36842261, 12.0, 1.3233807, 16.07088712,
-    13.0, 1.102785365, 14.65952563, 14.0, 0.916703025, 13.21718577, 15.0, 0.760361881, 11.80207947,
-    16.0, 0.629457387, 10.45304833, 17.0, 0.520175654, 9.194183767, 18.0, 0.42918208, 8.038657241,
-    19.0, 0.353590663, 6.991779595, 20.0, 0.290923699, 6.053379213, 21.0, 0.23906788, 5.219610436,
-    22.0, 0.196230431, 4.484302033, 23.0, 0.160897421, 3.839943445, 24.0, 0.131795374, 3.27839108,
-    25.0, 0.1078567, 2.791361596, 26.0, 0.088189063, 2.370765375, 27.0, 0.072048567, 2.008921719,
-    28.0, 0.058816518, 1.698687797, 29.0, 0.047979438, 1.433525748, 30.0, 0.039111985, 1.207526336,
-    31.0, 0.031862437, 1.015402928, 32.0, 0.025940415, 0.852465956, 33.0, 0.021106532, 0.714585285,
-    34.0, 0.017163711, 0.598145851, 35.0, 0.013949904, 0.500000349, 36.0, 0.011332027, 0.41742159,
-    37.0, 0.009200898, 0.348056286, 38.0, 0.007467036, 0.289881373, 39.0, 0.006057179, 0.241163527,
-    40.0, 0.004911394, 0.200422214
-};
-
-// calculate_log10_dynamic_read_qual_threshold :261-291
-double dynamic_threshold(const uint8_t *qual, int len, double k) {
-    double mean = 0.0, var = 0.0;
-    for (int i = 0; i < len; i++) {
-        const int bq = qual[i];
-        const int entry = bq <= 1 ? 0 : std::min(40, bq) - 1;
-        mean += kDynTable[entry * 3 + 1];
-        var += kDynTable[entry * 3 + 2];
-    }
-    return (mean + k * std::sqrt(var)) * -0.1;
-}
-
-// log10_min_true_likelihood :293-319
-double min_true_likelihood(int len, double max_error_per_base, bool cap) {
-    double e = std::ceil((double)len * max_error_per_base);
-    if (cap) e = std::min(2.0, e);
-    return e * -4.0;
-}
-
 template <class F>
 void parallel_for(int64_t n, int n_threads, F f) {
     if (n_threads <= 1 || n < 2) { for (int64_t i = 0; i < n; i++) f(i); return; }
@@ -188,43 +151,11 @@ extern "C" lk_status lk_engine_modify_read_qualities(const lk_engine_args *args,
     return LK_OK;
 }
 
-// normalize_likelihoods for one [A x R] block (allele_likelihoods.rs:378-444; search_best_allele :457-554 with priorities None)
-static void normalize_block(double *v, int A, int R, double cap_diff, bool symmetric, int ref_idx) {
-    if (cap_diff == -std::numeric_limits<double>::infinity() || A < 2) return;
-    for (int r = 0; r < R; r++) {
-        const bool can_be_ref = symmetric;
-        int best = (can_be_ref || ref_idx != 0) ? 0 : 1;
-        double best_lk = v[(size_t)best * R + r];
-        for (int a = best + 1; a < A; a++) {
-            if (!can_be_ref && a == ref_idx) continue;
-            if (v[(size_t)a * R + r] > best_lk) { best = a; best_lk = v[(size_t)a * R + r]; }
-        }
-        const double worst = best_lk + cap_diff;
-        for (int a = 0; a < A; a++)
-            if (v[(size_t)a * R + r] < worst) v[(size_t)a * R + r] = worst;
-    }
-}
-
-// filter_poorly_modeled_evidence + remove_evidence_by_index for one block (:925-1018)
-static int filter_block(double *v, int A, int R, const double *thr, uint8_t *keep) {
-    int kept = 0;
-    for (int r = 0; r < R; r++) {
-        double best = -std::numeric_limits<double>::infinity();
-        for (int a = 0; a < A; a++) best = std::max(best, v[(size_t)a * R + r]);
-        const bool remove = best < thr[r];
-        if (keep) keep[r] = remove ? 0 : 1;
-        if (!remove) {
-            if (kept != r)
-                for (int a = 0; a < A; a++) v[(size_t)a * R + kept] = v[(size_t)a * R + r];
-            kept++;
-        }
-    }
-    if (kept < R)
-        for (int a = 0; a < A; a++)
-            for (int r = kept; r < R; r++) v[(size_t)a * R + r] = std::numeric_limits<double>::quiet_NaN();
-    return kept;
-}
-
+// Region driver.  Everything runs on the device inside the PairHMM chunk pipeline (lk_api.cu: lk_pairhmm_pipeline with a
+// hook): engine_modify_reads_kernel on the staged copies (the caller's arrays stay untouched), the PairHMM kernels,
+// engine_epilogue_kernel (transpose to [allele][read], normalise, thresholds from the ORIGINAL qualities and lengths --
+// the "HMMQuals" key quirk: the capped qualities are stored under a key nobody reads, so :268,299 fall back to the
+// original quals / length -- filter, compact, NaN tail).  See engine_kernels.cu.
 extern "C" lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_engine_args *args, const lk_pairhmm_batch *batch,
                                                         const uint8_t *read_mapq, const int32_t *ref_allele_index,
                                                         double *values, uint8_t *keep) {
@@ -233,51 +164,20 @@ extern "C" lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_en
     lk_status st = lk_pairhmm_batch_dims(batch, &n_pairs, nullptr);
     if (st != LK_OK) return lk_fail(ctx, st, "invalid batch");
     if (n_pairs > 0 && !values) return lk_fail(ctx, LK_ERR_INVALID, "null values");
-    const int64_t n_reads = batch->region_read_start[batch->n_regions];
-    const int64_t nbytes = n_reads ? batch->read_off[n_reads] : 0;
-    // processed copies; the originals stay untouched for the thresholds (the "HMMQuals" key quirk: the capped
-    // qualities are stored under a key nobody reads, so :268,299 fall back to the ORIGINAL quals / length)
-    std::vector<uint8_t> q(batch->read_qual, batch->read_qual + nbytes), qi(batch->read_ins, batch->read_ins + nbytes),
-        qd(batch->read_del, batch->read_del + nbytes);
-    st = lk_engine_modify_read_qualities(args, n_reads, batch->read_off, batch->read_bases, q.data(), qi.data(), qd.data(),
-                                         read_mapq, 0);
-    if (st != LK_OK) return lk_fail(ctx, st, "modify_read_qualities failed");
+    if (!args->disable_cap_read_qualities_to_mapq && !read_mapq && batch->region_read_start[batch->n_regions] > 0)
+        return lk_fail(ctx, LK_ERR_INVALID, "read_mapq is required unless capping to MAPQ is disabled");
+    if (args->pcr_error_model < 0 || args->pcr_error_model > 3) return lk_fail(ctx, LK_ERR_INVALID, "bad PCR error model");
+    lk_engine_hook hook;
+    memset(&hook, 0, sizeof hook);
+    hook.args = args;
+    hook.read_mapq = args->disable_cap_read_qualities_to_mapq ? nullptr : read_mapq;
+    hook.ref_allele_index = ref_allele_index;
+    hook.values = values;
+    hook.keep = keep;
+    if (args->pcr_error_model != LK_PCR_NONE)  // initialize_pcr_error_model :169-184
+        for (int i = 0; i <= kMaxRepeatLength; i++) hook.pcr_cache[i] = adjusted_qual(i, (double)args->pcr_error_model);
     lk_pairhmm_batch pb = *batch;
-    pb.read_qual = q.data(); pb.read_ins = qi.data(); pb.read_del = qd.data();
     pb.read_gcp = nullptr;  // gap_continuation_penalties is vec![constant_gcp; len] (:649-651)
     pb.gcp_constant = args->constant_gcp;
-    std::vector<double> lk((size_t)n_pairs);
-    st = lk_pairhmm_batch_host(ctx, &pb, lk.data(), nullptr);
-    if (st != LK_OK) return st;
-    // per region: [r*A + h] -> [a][r] (pair_hmm.rs:247-266), normalise, filter
-    std::vector<int64_t> base((size_t)batch->n_regions + 1, 0);
-    for (int64_t g = 0; g < batch->n_regions; g++)
-        base[(size_t)g + 1] = base[(size_t)g] + (batch->region_read_start[g + 1] - batch->region_read_start[g]) *
-                                                    (batch->region_hap_start[g + 1] - batch->region_hap_start[g]);
-    parallel_for(batch->n_regions, (int)std::max(1u, std::thread::hardware_concurrency()), [&](int64_t g) {
-        const int64_t r0 = batch->region_read_start[g];
-        const int R = (int)(batch->region_read_start[g + 1] - r0);
-        const int A = (int)(batch->region_hap_start[g + 1] - batch->region_hap_start[g]);
-        if (R == 0 || A == 0) return;
-        double *v = values + base[(size_t)g];
-        const double *src = lk.data() + base[(size_t)g];
-        for (int r = 0; r < R; r++)
-            for (int a = 0; a < A; a++) v[(size_t)a * R + r] = src[(size_t)r * A + a];
-        normalize_block(v, A, R, args->log10_global_read_mismapping_rate,
-                        args->symmetrically_normalize_alleles_to_reference != 0, ref_allele_index ? ref_allele_index[g] : 0);
-        std::vector<double> thr((size_t)R);
-        for (int r = 0; r < R; r++) {
-            const int64_t o = batch->read_off[r0 + r];
-            const int len = (int)(batch->read_off[r0 + r + 1] - o);
-            if (args->dynamic_read_disqualification) {  // dynamic_log10_min_likelihood_model :244-259
-                const double dyn = dynamic_threshold(batch->read_qual + o, len, args->read_disqualification_scale);
-                const double stat = min_true_likelihood(len, args->expected_error_rate_per_base, false);
-                thr[(size_t)r] = dyn < stat ? dyn : stat;
-            } else {
-                thr[(size_t)r] = min_true_likelihood(len, args->expected_error_rate_per_base, true);
-            }
-        }
-        filter_block(v, A, R, thr.data(), keep ? keep + r0 : nullptr);
-    });
-    return LK_OK;
+    return lk_pairhmm_pipeline(ctx, &pb, nullptr, nullptr, &hook);
 }

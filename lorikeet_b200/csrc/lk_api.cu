@@ -223,7 +223,7 @@ static GcpMode resolve_gcp(const lk_pairhmm_batch *b, int64_t n_reads) {
 // metadata to the device on stream st.  Asynchronous: returns once the copies are queued (metadata goes through
 // the workspace's pinned arena; `ev_staged` marks the point where that arena may be reused).
 static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0, int64_t g1, const GcpMode &gcp,
-                             lk_resident *R, cudaStream_t st) {
+                             lk_resident *R, cudaStream_t st, const lk_engine_hook *hook = nullptr) {
     cudaError_t e;
     if (R->ev_staged) {
         if ((e = cudaEventSynchronize(R->ev_staged)) != cudaSuccess) return lk_cuda_fail(ctx, e, "wait staging");
@@ -250,12 +250,22 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
     R->hap_byte0 = n_haps ? b->hap_off[hbase] : 0;
     const int64_t read_bytes = n_reads ? b->read_off[rbase + n_reads] - R->read_byte0 : 0;
     const int64_t hap_bytes = n_haps ? b->hap_off[hbase + n_haps] - R->hap_byte0 : 0;
+    R->read_bytes_staged = read_bytes;
 
     // ---- metadata through the pinned arena ----
     struct Piece { DevBuf *dst; const void *src; size_t bytes; };
     std::vector<int64_t> local_rhs((size_t)n_regions + 1);
     for (int64_t g = 0; g <= n_regions; g++) local_rhs[(size_t)g] = b->region_hap_start[g0 + g] - hbase;
+    std::vector<int64_t> local_rrs;
+    if (hook) {
+        local_rrs.resize((size_t)n_regions + 1);
+        for (int64_t g = 0; g <= n_regions; g++) local_rrs[(size_t)g] = b->region_read_start[g0 + g] - rbase;
+    }
     const Piece pieces[] = {
+        { &R->region_read_start, hook ? local_rrs.data() : nullptr, hook ? (size_t)(n_regions + 1) * 8 : 0 },
+        { &R->read_mapq, hook && hook->read_mapq ? hook->read_mapq + rbase : nullptr, hook && hook->read_mapq ? (size_t)n_reads : 0 },
+        { &R->ref_allele_index, hook && hook->ref_allele_index ? hook->ref_allele_index + g0 : nullptr,
+          hook && hook->ref_allele_index ? (size_t)n_regions * 4 : 0 },
         { &R->read_off, b->read_off + rbase, (size_t)(n_reads + 1) * 8 },
         { &R->read_region, P.read_region.data(), (size_t)n_reads * 4 },
         { &R->read_out_base, P.read_out_base.data(), (size_t)n_reads * 8 },
@@ -278,6 +288,7 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
     RS(read_flags, n_reads); RS(hap_flags, n_haps);
     RS(hidx, P.henc_words);
     RS(out, P.n_pairs * 8); RS(flags, P.n_pairs);
+    if (hook) { RS(values, P.n_pairs * 8); RS(keep, n_reads); if (hook->args->dynamic_read_disqualification) { RS(qual_orig, read_bytes); } }
     RS(counters, 64);
     RS(rescue_pairs, std::max<int64_t>(P.n_pairs, 1) * (int64_t)sizeof(RescuePair));
     R->plain_blocks = ctx->n_sm * 2;
@@ -335,10 +346,47 @@ static void fill_args(lk_ctx *ctx, lk_resident *R, PairHmmArgs &A) {
 }
 
 // Queue every kernel of one staged workspace on st (no synchronisation).
-static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, bool timed) {
+static void fill_engine_args(const lk_engine_hook *hook, lk_resident *R, const PairHmmArgs &A, EngineDevArgs &E) {
+    memset(&E, 0, sizeof E);
+    const lk_engine_args *a = hook->args;
+    E.read_bases = A.read_bases;
+    E.read_qual = (uint8_t *)A.read_qual; E.read_ins = (uint8_t *)A.read_ins; E.read_del = (uint8_t *)A.read_del;
+    E.qual_orig = a->dynamic_read_disqualification ? (const uint8_t *)R->qual_orig.p - R->read_byte0 : nullptr;
+    E.read_off = A.read_off;
+    E.read_mapq = hook->read_mapq ? (const uint8_t *)R->read_mapq.p : nullptr;
+    E.read_out_base = A.read_out_base;
+    E.region_read_start = (const int64_t *)R->region_read_start.p;
+    E.region_hap_start = A.region_hap_start;
+    E.ref_allele_index = hook->ref_allele_index ? (const int32_t *)R->ref_allele_index.p : nullptr;
+    E.lk = A.out;
+    E.values = (double *)R->values.p;
+    E.keep = (uint8_t *)R->keep.p;
+    E.cap_diff = a->log10_global_read_mismapping_rate;
+    E.expected_error_rate = a->expected_error_rate_per_base;
+    E.disq_scale = a->read_disqualification_scale;
+    E.use_pcr = a->pcr_error_model != LK_PCR_NONE;
+    E.cap_to_mapq = !a->disable_cap_read_qualities_to_mapq;
+    E.symmetric = a->symmetrically_normalize_alleles_to_reference != 0;
+    E.dynamic_disq = a->dynamic_read_disqualification != 0;
+    E.bq_threshold = a->base_quality_score_threshold;
+    memcpy(E.pcr_cache, hook->pcr_cache, sizeof E.pcr_cache);
+}
+
+static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, bool timed, const lk_engine_hook *hook = nullptr) {
     cudaError_t e;
     PairHmmArgs A;
     fill_args(ctx, R, A);
+    EngineDevArgs E;
+    if (hook) {
+        fill_engine_args(hook, R, A, E);
+        if (R->n_reads > 0) {
+            if (E.dynamic_disq) {  // thresholds use the ORIGINAL qualities: keep a copy before they are rewritten in place
+                if ((e = cudaMemcpyAsync(R->qual_orig.p, R->read_qual.p, R->read_bytes_staged, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+                    return lk_cuda_fail(ctx, e, "copy original qualities");
+            }
+            if ((e = launch_engine_modify(E, R->n_reads, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "engine_modify_reads");
+        }
+    }
     R->counter_init[0] = R->all_f64 ? (int32_t)R->n_pairs : R->n_direct;
     R->counter_init[1] = 0;
     R->counter_init[2] = 0;
@@ -371,6 +419,10 @@ static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, b
     }
     if ((e = launch_plain(A, R->plain_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_plain");
     R->launch_count++;
+    if (hook) {
+        if ((e = launch_engine_epilogue(E, R->n_regions, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "engine_epilogue");
+        R->launch_count += 2;  // modify_reads + epilogue
+    }
     return LK_OK;
 }
 
@@ -450,6 +502,7 @@ extern "C" lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *
 static void release_buffers(lk_resident *R) {
     DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
                        &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
+                       &R->region_read_start, &R->read_mapq, &R->ref_allele_index, &R->qual_orig, &R->values, &R->keep,
                        &R->hap_bases, &R->hidx, &R->henc_off, &R->hap_flags, &R->tasks, &R->groups, &R->out,
                        &R->flags, &R->counters, &R->rescue_pairs, &R->scratch, &R->band_pairs, &R->band_scratch,
                        &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,
@@ -469,8 +522,14 @@ extern "C" void lk_resident_free(lk_ctx *ctx, lk_resident *R) {
 // Host-buffer entry point: regions are cut into chunks that flow through two workspaces / two streams, so the
 // H2D copy and task building of chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i.
 extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags) {
+    return lk_pairhmm_pipeline(ctx, batch, out, flags, nullptr);
+}
+
+// With a hook the pipeline is the region driver: out / flags are ignored, hook->values / hook->keep are filled.
+lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags, const lk_engine_hook *hook) {
     if (!ctx) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
+    if (hook) { out = hook->values; flags = nullptr; }
     int64_t n_reads = 0, n_haps = 0;
     lk_status vs = validate_batch(ctx, batch, &n_reads, &n_haps);
     if (vs != LK_OK) return vs;
@@ -506,7 +565,9 @@ extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *
         lk_resident *R = ctx->ws[i & 1];
         cudaStream_t s = ctx->stream[i & 1];
         if (R->n_pairs == 0) return LK_OK;
-        cudaError_t ce = cudaMemcpyAsync(out + pair_base[(size_t)i], R->out.p, (size_t)R->n_pairs * 8, cudaMemcpyDeviceToHost, s);
+        cudaError_t ce = cudaMemcpyAsync(out + pair_base[(size_t)i], hook ? R->values.p : R->out.p, (size_t)R->n_pairs * 8, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess && hook && hook->keep && R->n_reads > 0)
+            ce = cudaMemcpyAsync(hook->keep + batch->region_read_start[cut[(size_t)i]], R->keep.p, (size_t)R->n_reads, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && flags) ce = cudaMemcpyAsync(flags + pair_base[(size_t)i], R->flags.p, (size_t)R->n_pairs, cudaMemcpyDeviceToHost, s);
         if (ce != cudaSuccess) return lk_cuda_fail(ctx, ce, "D2H");
         return LK_OK;
@@ -518,9 +579,9 @@ extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *
         lk_resident *R = ctx->ws[i & 1];
         cudaStream_t s = ctx->stream[i & 1];
         const double t0 = now_ms();
-        st = stage_range(ctx, batch, cut[(size_t)i], cut[(size_t)i + 1], gcp, R, s);
+        st = stage_range(ctx, batch, cut[(size_t)i], cut[(size_t)i + 1], gcp, R, s, hook);
         const double t1 = now_ms();
-        if (st == LK_OK) st = enqueue_kernels(ctx, R, s, false);
+        if (st == LK_OK) st = enqueue_kernels(ctx, R, s, false, hook);
         launches += R->launch_count;
         const double t2 = now_ms();
         if (st == LK_OK && i >= 1) st = collect(i - 1);  // may block on a pageable destination: chunk i is already queued

@@ -61,10 +61,13 @@ struct lk_resident {
     lk::HostPrep prep;
     PinnedBuf pinned;                 // metadata staging (so its H2D copies are truly asynchronous)
     cudaEvent_t ev_staged = nullptr;  // pinned arena may be rewritten once this has fired
+    int64_t read_bytes_staged = 0;
     int64_t read_byte0 = 0, hap_byte0 = 0;  // first arena byte staged: device pointers are biased by these
     DevBuf read_bases, read_qual, read_ins, read_del, read_gcp, read_off, read_region, read_out_base, read_flags;
     DevBuf region_hap_start, hap_off, hap_bases, hidx, henc_off, hap_flags;
     DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch, band_pairs, band_scratch;
+    // engine pre/post-ops on the device (N3)
+    DevBuf region_read_start, read_mapq, ref_allele_index, qual_orig, values, keep;
     // ---- Smith-Waterman ----
     struct SwLaunch { int K; int32_t first; int32_t count; };
     std::vector<SwLaunch> sw_launches;
@@ -75,6 +78,17 @@ struct lk_resident {
     lk_sw_params sw_params = { 0, 0, 0, 0 };
     DevBuf sw_refs, sw_alts, sw_ref_off, sw_alt_off, sw_bt, sw_bt_off, sw_ops, sw_nops, sw_offsets, sw_order;
 };
+
+// Region driver hook of the PairHMM chunk pipeline: modify_read_qualities before, normalise / filter after, on the device.
+struct lk_engine_hook {
+    const lk_engine_args *args;
+    const uint8_t *read_mapq;          // per read of the whole batch (may be null when capping is disabled)
+    const int32_t *ref_allele_index;   // per region of the whole batch, may be null
+    double *values;                    // out, pair-indexed like `out` of lk_pairhmm_batch_host
+    uint8_t *keep;                     // out, per read, may be null
+    uint8_t pcr_cache[101];
+};
+lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags, const lk_engine_hook *hook);
 
 lk_status lk_fail(lk_ctx *ctx, lk_status st, const std::string &msg);
 lk_status lk_cuda_fail(lk_ctx *ctx, cudaError_t e, const char *what);

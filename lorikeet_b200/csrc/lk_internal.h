@@ -18,6 +18,28 @@ cudaError_t launch_list_all_pairs(const PairHmmArgs &A, int64_t n_reads, cudaStr
 cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t st);
 cudaError_t launch_band(const PairHmmArgs &A, int n_blocks, cudaStream_t st);
 cudaError_t launch_plain(const PairHmmArgs &A, int n_blocks, cudaStream_t st);
+// engine pre/post-ops on the device (engine_kernels.cu)
+struct EngineDevArgs {
+    // reads of the staged chunk (arena pointers biased like PairHmmArgs)
+    const uint8_t *read_bases;
+    uint8_t *read_qual, *read_ins, *read_del;
+    const uint8_t *qual_orig;          // untouched copy of read_qual (dynamic disqualification only)
+    const int64_t *read_off;
+    const uint8_t *read_mapq;          // per read (chunk-local index)
+    const int64_t *read_out_base;      // per read: first pair of (read, haplotype 0)
+    const int64_t *region_read_start;  // chunk-local
+    const int64_t *region_hap_start;   // chunk-local
+    const int32_t *ref_allele_index;   // per region, may be null
+    const double *lk;                  // PairHMM result [r*A + h] per region
+    double *values;                    // out: [a*R + r] per region
+    uint8_t *keep;                     // out: per read, may be null
+    double cap_diff, expected_error_rate, disq_scale;
+    int32_t use_pcr, cap_to_mapq, symmetric, dynamic_disq;
+    uint8_t bq_threshold;
+    uint8_t pcr_cache[101];
+};
+cudaError_t launch_engine_modify(const EngineDevArgs &E, int64_t n_reads, cudaStream_t st);
+cudaError_t launch_engine_epilogue(const EngineDevArgs &E, int64_t n_regions, cudaStream_t st);
 cudaError_t launch_sw(int K, const SwArgs &A, int n_blocks, cudaStream_t st);
 
 }  // namespace lk

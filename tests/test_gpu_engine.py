@@ -100,3 +100,53 @@ def test_reference_engine_unit_test(ctx):
     eng = PairHMMLikelihoodCalculationEngine(ctx, 93, -4.5, PCRErrorModel.CONSERVATIVE, 16, False, 1.0, 0.02, True, False, False)
     values, keep = eng.compute_read_likelihoods(b, np.array([60], np.uint8), np.array([0], np.int32))
     assert keep[0] == 1 and values[0] > values[1]
+
+
+@pytest.mark.parametrize("pcr,no_mapq_cap,bq_thr", [(0, False, 18), (1, False, 6), (2, True, 18), (3, True, 30)])
+def test_pre_ops_variants_match_oracle(ctx, pcr, no_mapq_cap, bq_thr):
+    # every PCRErrorModel (None / Hostile / Aggressive / Conservative), with and without the MAPQ cap, several thresholds:
+    # the device pre-ops (engine_modify_reads_kernel) against the oracle's apply_pcr_error_model + cap_minimum_read_qualities
+    from lorikeet_b200 import synth
+    from lorikeet_b200.engine import PairHMMLikelihoodCalculationEngine
+    b = synth.pairhmm_regions(10, first_region=4242 + pcr, pcr_model=0, base_quality_score_threshold=0)
+    rng = np.random.default_rng(pcr)
+    # plant homopolymers / short tandem repeats so the PCR model has repeats of many lengths to cap
+    for r in rng.choice(b.n_reads, 80, replace=False):
+        a, e = int(b.read_off[r]), int(b.read_off[r + 1])
+        unit = rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(1, 5)))
+        k = int(rng.integers(a, e - 40))
+        b.read_bases[k:k + 36] = np.resize(unit, 36)
+    mapq = rng.integers(5, 61, b.n_reads).astype(np.uint8)
+    ref_idx = np.zeros(b.n_regions, np.int32)
+    eng = PairHMMLikelihoodCalculationEngine(ctx, 10, -4.5, pcr, bq_thr, False, 1.0, 0.02, True, no_mapq_cap, False)
+    values, keep = eng.compute_read_likelihoods(b, mapq, ref_idx)
+    evalues, ekeep = _oracle_engine(b, mapq, ref_idx, 10, -4.5, pcr, bq_thr, False, 1.0, 0.02, True, 1 if no_mapq_cap else 0)
+    assert np.array_equal(keep, ekeep)
+    nan = np.isnan(evalues)
+    assert np.array_equal(np.isnan(values), nan)
+    rel = np.abs(values[~nan] - evalues[~nan]) / np.maximum(np.abs(evalues[~nan]), 1e-3)
+    assert rel.max() < 1e-4
+
+
+def test_region_driver_is_chunk_invariant(ctx):
+    # 2600 regions = 2.66 M pairs -> the host pipeline cuts the batch into 2 chunks (two workspaces, two streams); the
+    # result must equal the concatenation of independent calls on thirds of the batch, bit for bit
+    from lorikeet_b200 import synth
+    from lorikeet_b200.engine import PairHMMLikelihoodCalculationEngine, PCRErrorModel
+    n = 2600
+    b = synth.pairhmm_regions(n, first_region=90000, pcr_model=0, base_quality_score_threshold=0)
+    rng = np.random.default_rng(3)
+    mapq = rng.integers(20, 61, b.n_reads).astype(np.uint8)
+    ref_idx = rng.integers(0, 2, b.n_regions).astype(np.int32)
+    eng = PairHMMLikelihoodCalculationEngine(ctx, 10, -4.5, PCRErrorModel.CONSERVATIVE, 18, True, 1.0, 0.02, True, False, False)
+    values, keep = eng.compute_read_likelihoods(b, mapq, ref_idx)
+    parts_v, parts_k = [], []
+    for g0, g1 in ((0, 900), (900, 1800), (1800, n)):
+        sb = b.region_slice(g0, g1)
+        r0, r1 = int(b.region_read_start[g0]), int(b.region_read_start[g1])
+        v, k = eng.compute_read_likelihoods(sb, mapq[r0:r1], ref_idx[g0:g1])
+        parts_v.append(v); parts_k.append(k)
+    assert np.array_equal(keep, np.concatenate(parts_k))
+    pv = np.concatenate(parts_v)
+    assert np.array_equal(np.isnan(values), np.isnan(pv))
+    assert np.array_equal(values[~np.isnan(values)], pv[~np.isnan(pv)])
