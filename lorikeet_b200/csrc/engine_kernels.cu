@@ -32,19 +32,20 @@ __device__ __forceinline__ bool same_bytes(const uint8_t *a, const uint8_t *b, i
     return true;
 }
 
-// VariantContextUtils::find_number_of_repetitions_main (variant_context_utils.rs:276-337)
+// VariantContextUtils::find_number_of_repetitions_main (variant_context_utils.rs:276-337).  A window that IS the unit
+// (the unit is a slice of the same read: its own position is the first window of every scan here) counts without a compare.
 __device__ int count_repeats(const uint8_t *unit, int unit_len, const uint8_t *test, int test_len, bool leading) {
     if (test_len == 0) return 0;
     const int diff = test_len - unit_len;
     int reps = 0;
     if (leading) {
         for (int s = 0; s <= diff; s += unit_len) {
-            if (!same_bytes(test + s, unit, unit_len)) break;
+            if (test + s != unit && !same_bytes(test + s, unit, unit_len)) break;
             reps++;
         }
     } else {
         for (int s = diff; s >= 0; s -= unit_len) {
-            if (!same_bytes(test + s, unit, unit_len)) break;
+            if (test + s != unit && !same_bytes(test + s, unit, unit_len)) break;
             reps++;
         }
     }
@@ -96,15 +97,25 @@ __constant__ double kDynVar[40] = {
 
 }  // namespace
 
-// one warp per read, lanes over its bases; in place on the staged copies
-__global__ void engine_modify_reads_kernel(EngineDevArgs E, int64_t n_reads) {
+// one warp per read, lanes over its bases; in place on the staged copies.  The read's bases are staged in shared memory
+// (the repeat search reads every base ~40 times); reads longer than the slab are scanned in global memory.
+constexpr int kEngineSlab = 1024;
+__global__ void __launch_bounds__(128) engine_modify_reads_kernel(EngineDevArgs E, int64_t n_reads) {
+    __shared__ uint8_t slab[4][kEngineSlab];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    uint8_t *mine = slab[threadIdx.x >> 5];
     for (int64_t r = warp; r < n_reads; r += n_warps) {
         const int64_t o = E.read_off[r];
         const int len = (int)(E.read_off[r + 1] - o);
         const uint8_t *bases = E.read_bases + o;
+        if (E.use_pcr && len <= kEngineSlab) {
+            __syncwarp();
+            for (int j = lane; j < len; j += 32) mine[j] = bases[j];
+            __syncwarp();
+            bases = mine;
+        }
         const uint8_t mapq = E.cap_to_mapq ? E.read_mapq[r] : 255;
         for (int j = lane; j < len; j += 32) {
             uint8_t q = E.read_qual[o + j], qi = E.read_ins[o + j], qd = E.read_del[o + j];

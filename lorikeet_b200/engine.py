@@ -39,14 +39,17 @@ class PairHMMLikelihoodCalculationEngine:
                                     1 if symmetrically_normalize_alleles_to_reference else 0,
                                     1 if disable_cap_read_qualities_to_mapq else 0, 1 if modify_soft_clipped_bases else 0)
 
-    def compute_read_likelihoods(self, batch, read_mapq, ref_allele_index=None):
+    def compute_read_likelihoods(self, batch, read_mapq, ref_allele_index=None, values=None, keep=None):
         """compute_read_likelihoods (:195-242) for a batch of single-sample regions.
         Returns (values, keep): values holds per region an [A x R] row-major block ([allele][read], the reference's
         AlleleLikelihoods layout) at the pair offsets of the batch, normalised and filtered; keep[r] = read survived."""
         L = _lib.load()
         n = batch.n_pairs
-        values = np.empty(n, dtype=np.float64)
-        keep = np.ones(batch.n_reads, dtype=np.uint8)
+        if values is None:
+            values = np.empty(n, dtype=np.float64)
+        if keep is None:
+            keep = np.ones(batch.n_reads, dtype=np.uint8)
+        assert values.dtype == np.float64 and values.size == n and keep.dtype == np.uint8 and keep.size == batch.n_reads
         mapq = np.ascontiguousarray(read_mapq, dtype=np.uint8)
         assert mapq.size == batch.n_reads
         ref = None

@@ -20,7 +20,7 @@ def ctx():
     c.close()
 
 
-def _oracle_engine(batch, mapq, ref_idx, gcp, mismap, pcr, bq_thr, dynamic, scale, err_rate, symmetric, no_mapq_cap):
+def _oracle_engine(batch, mapq, ref_idx, gcp, mismap, pcr, bq_thr, dynamic, scale, err_rate, symmetric, no_mapq_cap, rescaled=False):
     L = O.lib()
     p = lambda a, t: a.ctypes.data_as(t)
     q, ins, dele = batch.read_qual.copy(), batch.read_ins.copy(), batch.read_del.copy()
@@ -34,7 +34,7 @@ def _oracle_engine(batch, mapq, ref_idx, gcp, mismap, pcr, bq_thr, dynamic, scal
     d = dict(region_read_start=batch.region_read_start, region_hap_start=batch.region_hap_start, read_off=batch.read_off,
              hap_off=batch.hap_off, read_bases=batch.read_bases, read_qual=q, read_ins=ins, read_del=dele,
              read_gcp=np.full(batch.read_bases.shape, gcp, np.uint8), hap_bases=batch.hap_bases)
-    lk = O.pairhmm_batch(d)
+    lk = O.pairhmm_batch(d, rescaled=rescaled)
     values = np.empty_like(lk)
     keep = np.ones(batch.n_reads, np.uint8)
     base = 0
@@ -150,3 +150,30 @@ def test_region_driver_is_chunk_invariant(ctx):
     pv = np.concatenate(parts_v)
     assert np.array_equal(np.isnan(values), np.isnan(pv))
     assert np.array_equal(values[~np.isnan(values)], pv[~np.isnan(pv)])
+
+
+def test_region_driver_on_long_reads(ctx):
+    # reads longer than the modify kernel's shared-memory slab (1024 bases) and than the fast kernel's 32*K rows: the
+    # pre-ops scan global memory and the likelihoods come from the fp32 band kernel; oracle = rescaled f64 restatement
+    from lorikeet_b200 import synth
+    from lorikeet_b200.engine import PairHMMLikelihoodCalculationEngine, PCRErrorModel
+    b = synth.pairhmm_regions(3, **dict(synth.CFG3, read_len=1500, hap_len=1800, n_reads=4, n_haps=3, pcr_model=0,
+                                         base_quality_score_threshold=0))
+    rng = np.random.default_rng(9)
+    for r in range(b.n_reads):  # plant a long homopolymer and a dinucleotide repeat in every read
+        a = int(b.read_off[r])
+        b.read_bases[a + 1100:a + 1140] = ord("A")
+        b.read_bases[a + 300:a + 340] = np.resize(np.frombuffer(b"CA", np.uint8), 40)
+    mapq = np.full(b.n_reads, 50, np.uint8)
+    ref_idx = np.zeros(b.n_regions, np.int32)
+    # dynamic disqualification: with the static -8 every noisy 1.5 kbp read would be filtered and nothing would be compared
+    eng = PairHMMLikelihoodCalculationEngine(ctx, 10, -4.5, PCRErrorModel.CONSERVATIVE, 18, True, 4.0, 0.3, True, False, False)
+    values, keep = eng.compute_read_likelihoods(b, mapq, ref_idx)
+    # oracle composition with the rescaled forward (the un-rescaled f64 underflows on long noisy reads)
+    evalues, ekeep = _oracle_engine(b, mapq, ref_idx, 10, -4.5, 3, 18, True, 4.0, 0.3, True, 0, rescaled=True)
+    assert np.array_equal(keep, ekeep)
+    assert keep.sum() > 0
+    nan = np.isnan(evalues)
+    assert np.array_equal(np.isnan(values), nan)
+    rel = np.abs(values[~nan] - evalues[~nan]) / np.maximum(np.abs(evalues[~nan]), 1e-3)
+    assert rel.max() < 1e-4
