@@ -172,10 +172,23 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 during the run (NCCL's version banner,
+    library chatter) has been diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -385,7 +398,7 @@ def main():
             "wall_s_timed_region": t_wall,
             "other_configs": extras,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     res.free()
     ctx.close()
     if world > 1:
