@@ -507,21 +507,12 @@ LK_UNROLL_N(LK_BAND_UNROLL)
                 }
             }
             // ---- bring what the row above sent into my exponent ----
-            // A lane that has not started adopts the sender's exponent.  If the incoming values would exceed 2^60 in my
-            // scale (I had scaled up while only tiny far-off-diagonal values were around), I scale myself down first:
-            // whatever I hold is negligible next to what is arriving.
+            // A lane that has not started adopts the sender's exponent.  Afterwards the lane's scale is chosen at its
+            // checkpoints (below) from its own strip AND what is arriving, so incoming values sit in range: the top row of
+            // a strip is never more than ~1/tMI below the row that feeds it, and 16 columns cannot move either side by
+            // the 2^107 of headroom above the 2^20 centre.  (Should a value overflow all the same, the sum comes out
+            // inf / NaN and the pair is redone in f64.)
             if (s <= lane + 1) xi = xi_up;
-            {
-                const int eb = (__float_as_int_hd(fmaxf(Mu, fmaxf(Iu, Du))) >> 23) & 0xFF;  // biased exponent of the largest
-                const int over = (eb - 127) + (xi - xi_up) - 60;
-                if (over > 0 && eb != 0) {
-                    const float f = pow2i(-over);
-#pragma unroll
-                    for (int k = 0; k < K; k++) { M[k] *= f; I[k] *= f; D[k] *= f; }
-                    Md *= f; Id *= f; Dd *= f; acc *= f; kinit *= f;
-                    xi -= over;
-                }
-            }
             const float al = pow2i(xi - xi_up);
             Mu *= al; Iu *= al; Du *= al;
             // ---- one column of the strip, rows top to bottom.  Row k reads row k-1 of the previous column (pm, pi, pd)
@@ -550,7 +541,7 @@ LK_UNROLL_N(LK_BAND_UNROLL)
             }
             // ---- block-floating-point upkeep: at the lane's first column and every 16 columns re-centre the strip ----
             if ((s & 15) == 0 || s == lane + 1) {
-                float m = acc;  // the running column sum must stay in range too: never scale up past it
+                float m = fmaxf(acc, fmaxf(Mu, fmaxf(Iu, Du)));  // the running sum and what is arriving must stay in range too
 #pragma unroll
                 for (int k = 0; k < K; k++) m = fmaxf(m, fmaxf(M[k], I[k]));
                 if (m > 0.f && (m < 9.5367431640625e-07f || m > 1.152921504606847e18f)) {  // outside [2^-20, 2^60]
