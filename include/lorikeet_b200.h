@@ -296,6 +296,24 @@ lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_engine_args *
                                              const uint8_t *read_mapq, const int32_t *ref_allele_index,
                                              double *values, uint8_t *keep);
 
+/* ---------------------------------------------------------------- cross-thread batching front-end (N4) */
+
+/*
+ * Lorikeet calls the engine from Rayon workers, one region per task (src/assembly/assembly_region_walker.rs:140-277).
+ * A batcher keeps those call sites unchanged: lk_batcher_submit blocks the calling thread, a dispatcher thread
+ * concatenates the regions pending from all threads (at most max_regions, waiting at most max_wait_us for more) and
+ * runs ONE launch for them.  args != NULL: the region driver (lk_engine_compute_read_likelihoods; values = [A x R]
+ * block, keep_or_flags = keep mask per read); args == NULL: lk_pairhmm_batch_host ([r*A + h], flags per pair).
+ * `region` must describe exactly one region (n_regions == 1).
+ */
+typedef struct lk_batcher lk_batcher;
+lk_status lk_batcher_create(lk_ctx *ctx, const lk_engine_args *args /* may be NULL */, int32_t max_regions,
+                            int32_t max_wait_us, lk_batcher **out);
+void lk_batcher_destroy(lk_batcher *b);
+lk_status lk_batcher_submit(lk_batcher *b, const lk_pairhmm_batch *region, const uint8_t *read_mapq,
+                            int32_t ref_allele_index, double *values, uint8_t *keep_or_flags /* may be NULL */);
+void lk_batcher_stats(lk_batcher *b, int64_t *n_batches, int64_t *n_regions);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "lk_engine_modify_read_qualities", "lk_engine_compute_read_likelihoods",
     "lk_realign_reads_batch", "lk_best_alleles_breaking_ties", "lk_realign_finish", "lk_cigar_apply_to_cigar",
     "lk_cigar_append_clipped_elements", "lk_read_start_on_reference_haplotype",
+    "lk_batcher_create", "lk_batcher_destroy", "lk_batcher_submit", "lk_batcher_stats",
 ]
 
 
@@ -172,6 +173,14 @@ def load():
     L.lk_cigar_append_clipped_elements.argtypes = [u32p, C.c_int32, u32p, C.c_int32, C.c_int32, u32p, i32p]
     L.lk_read_start_on_reference_haplotype.restype = C.c_int64
     L.lk_read_start_on_reference_haplotype.argtypes = [u32p, C.c_int32, C.c_uint32]
+    L.lk_batcher_create.restype = C.c_int
+    L.lk_batcher_create.argtypes = [vp, ep, C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.lk_batcher_destroy.restype = None
+    L.lk_batcher_destroy.argtypes = [vp]
+    L.lk_batcher_submit.restype = C.c_int
+    L.lk_batcher_submit.argtypes = [vp, bp, u8p, C.c_int32, f64p, u8p]
+    L.lk_batcher_stats.restype = None
+    L.lk_batcher_stats.argtypes = [vp, i64p, i64p]
     # introspection helpers (not part of the public header)
     L.lk_resident_launch_count.restype = C.c_int32
     L.lk_resident_launch_count.argtypes = [vp]

@@ -15,7 +15,7 @@ for f in pairhmm_kernels.cu sw_kernels.cu engine_kernels.cu lk_api.cu lk_sw_api.
     $NVCC $FLAGS -c "$f" -o "$o" & pids+=($!)
   fi
 done
-for f in host_model.cpp host_prep.cpp host_engine.cpp host_synth.cpp host_cigar.cpp; do
+for f in host_model.cpp host_prep.cpp host_engine.cpp host_synth.cpp host_cigar.cpp host_batcher.cpp; do
   [ -f "$f" ] || continue
   o=$BUILD/${f%.cpp}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 -name '*.h' -newer "$o" -print -quit)" ] || [ ../../include/lorikeet_b200.h -nt "$o" ]; then

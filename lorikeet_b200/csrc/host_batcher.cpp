@@ -1,0 +1,193 @@
+// host_batcher.cpp — cross-thread batching front-end (SURVEY.md 8(b) "Threading", 8(f) N4).
+//
+// Lorikeet calls the likelihood engine from Rayon workers, ONE region per task
+// (src/assembly/assembly_region_walker.rs:140-277: `par_iter` over assembly regions, an engine clone per region), and a
+// single region of 64 x 16 pairs keeps well under 1 % of a B200 busy.  The batcher lets those call sites stay as they
+// are: every worker thread submits its region through a blocking call; a dispatcher thread concatenates whatever is
+// pending (up to max_regions, waiting at most max_wait_us for stragglers) into one batch, runs the region driver
+// (lk_engine_compute_read_likelihoods, or the bare lk_pairhmm_batch_host when no engine arguments were given) once, and
+// hands every caller its own slice of the result.
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "../../include/lorikeet_b200.h"
+#include "lk_api_internal.h"
+
+namespace {
+
+struct Request {
+    const lk_pairhmm_batch *region;  // n_regions == 1, the caller's arrays (valid until the call returns)
+    const uint8_t *read_mapq;
+    int32_t ref_allele_index;
+    double *values;
+    uint8_t *keep_or_flags;
+    lk_status status = LK_OK;
+    bool done = false;
+};
+
+}  // namespace
+
+struct lk_batcher {
+    lk_ctx *ctx = nullptr;
+    bool engine = false;
+    lk_engine_args args;
+    int32_t max_regions = 256;
+    int64_t max_wait_us = 200;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<Request *> queue;
+    bool stop = false;
+    std::thread worker;
+    // statistics
+    int64_t n_batches = 0, n_regions = 0;
+
+    void run();
+    void process(std::vector<Request *> &reqs);
+};
+
+void lk_batcher::process(std::vector<Request *> &reqs) {
+    // concatenate the regions into one batch (host copies of a few KB per region)
+    const size_t G = reqs.size();
+    std::vector<int64_t> rrs(G + 1, 0), rhs(G + 1, 0), read_off(1, 0), hap_off(1, 0);
+    std::vector<uint8_t> bases, qual, ins, del, gcp, haps, mapq;
+    std::vector<int32_t> ref_idx(G, 0);
+    bool any_gcp = false, need_mapq = engine && !args.disable_cap_read_qualities_to_mapq;
+    for (Request *q : reqs) any_gcp |= (q->region->read_gcp != nullptr);
+    lk_status bad = LK_OK;
+    for (size_t g = 0; g < G; g++) {
+        const lk_pairhmm_batch *b = reqs[g]->region;
+        const int64_t nr = b->region_read_start[1], nh = b->region_hap_start[1];
+        rrs[g + 1] = rrs[g] + nr;
+        rhs[g + 1] = rhs[g] + nh;
+        const int64_t rb0 = nr ? b->read_off[0] : 0, rb1 = nr ? b->read_off[nr] : 0;
+        const int64_t hb0 = nh ? b->hap_off[0] : 0, hb1 = nh ? b->hap_off[nh] : 0;
+        for (int64_t r = 0; r < nr; r++) read_off.push_back(read_off.back() + (b->read_off[r + 1] - b->read_off[r]));
+        for (int64_t h = 0; h < nh; h++) hap_off.push_back(hap_off.back() + (b->hap_off[h + 1] - b->hap_off[h]));
+        bases.insert(bases.end(), b->read_bases + rb0, b->read_bases + rb1);
+        qual.insert(qual.end(), b->read_qual + rb0, b->read_qual + rb1);
+        ins.insert(ins.end(), b->read_ins + rb0, b->read_ins + rb1);
+        del.insert(del.end(), b->read_del + rb0, b->read_del + rb1);
+        if (any_gcp) {
+            if (b->read_gcp) gcp.insert(gcp.end(), b->read_gcp + rb0, b->read_gcp + rb1);
+            else gcp.insert(gcp.end(), (size_t)(rb1 - rb0), b->gcp_constant);
+        }
+        haps.insert(haps.end(), b->hap_bases + hb0, b->hap_bases + hb1);
+        if (need_mapq) {
+            if (!reqs[g]->read_mapq && nr > 0) { bad = LK_ERR_INVALID; break; }
+            mapq.insert(mapq.end(), reqs[g]->read_mapq, reqs[g]->read_mapq + nr);
+        }
+        ref_idx[g] = reqs[g]->ref_allele_index;
+    }
+    lk_pairhmm_batch big;
+    memset(&big, 0, sizeof big);
+    big.n_regions = (int64_t)G;
+    big.region_read_start = rrs.data(); big.region_hap_start = rhs.data();
+    big.read_off = read_off.data();
+    big.read_bases = bases.data(); big.read_qual = qual.data(); big.read_ins = ins.data(); big.read_del = del.data();
+    big.read_gcp = any_gcp ? gcp.data() : nullptr;
+    big.gcp_constant = reqs[0]->region->gcp_constant;
+    big.hap_off = hap_off.data(); big.hap_bases = haps.data();
+    int64_t n_pairs = 0;
+    for (size_t g = 0; g < G; g++) n_pairs += (rrs[g + 1] - rrs[g]) * (rhs[g + 1] - rhs[g]);
+    std::vector<double> out((size_t)n_pairs);
+    std::vector<uint8_t> aux((size_t)(engine ? rrs[G] : n_pairs));
+    lk_status st = bad;
+    if (st == LK_OK) {
+        if (engine) st = lk_engine_compute_read_likelihoods(ctx, &args, &big, need_mapq ? mapq.data() : nullptr, ref_idx.data(), out.data(), aux.data());
+        else st = lk_pairhmm_batch_host(ctx, &big, out.data(), aux.data());
+    }
+    int64_t pbase = 0;
+    for (size_t g = 0; g < G; g++) {
+        Request *q = reqs[g];
+        const int64_t nr = rrs[g + 1] - rrs[g], np = nr * (rhs[g + 1] - rhs[g]);
+        if (st == LK_OK) {
+            if (np && q->values) memcpy(q->values, out.data() + pbase, (size_t)np * 8);
+            if (q->keep_or_flags) {
+                if (engine) { if (nr) memcpy(q->keep_or_flags, aux.data() + rrs[g], (size_t)nr); }
+                else if (np) memcpy(q->keep_or_flags, aux.data() + pbase, (size_t)np);
+            }
+        }
+        q->status = st;
+        pbase += np;
+    }
+}
+
+void lk_batcher::run() {
+    std::unique_lock<std::mutex> lock(mu);
+    for (;;) {
+        cv_work.wait(lock, [&] { return stop || !queue.empty(); });
+        if (stop && queue.empty()) return;
+        // give stragglers a moment: a fuller batch uses the GPU better than a prompt one
+        if ((int32_t)queue.size() < max_regions && max_wait_us > 0 && !stop)
+            cv_work.wait_for(lock, std::chrono::microseconds(max_wait_us), [&] { return stop || (int32_t)queue.size() >= max_regions; });
+        std::vector<Request *> reqs;
+        while (!queue.empty() && (int32_t)reqs.size() < max_regions) { reqs.push_back(queue.front()); queue.pop_front(); }
+        lock.unlock();
+        process(reqs);
+        lock.lock();
+        n_batches++;
+        n_regions += (int64_t)reqs.size();
+        for (Request *q : reqs) q->done = true;
+        cv_done.notify_all();
+    }
+}
+
+extern "C" lk_status lk_batcher_create(lk_ctx *ctx, const lk_engine_args *args, int32_t max_regions, int32_t max_wait_us,
+                                       lk_batcher **out) {
+    if (!ctx || !out) return LK_ERR_INVALID;
+    *out = nullptr;
+    if (max_regions < 1 || max_wait_us < 0) return lk_fail(ctx, LK_ERR_INVALID, "bad batcher arguments");
+    lk_batcher *b = new (std::nothrow) lk_batcher();
+    if (!b) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    b->ctx = ctx;
+    b->engine = args != nullptr;
+    if (args) b->args = *args;
+    b->max_regions = max_regions;
+    b->max_wait_us = max_wait_us;
+    b->worker = std::thread([b] { b->run(); });
+    *out = b;
+    return LK_OK;
+}
+
+extern "C" void lk_batcher_destroy(lk_batcher *b) {
+    if (!b) return;
+    {
+        std::lock_guard<std::mutex> g(b->mu);
+        b->stop = true;
+    }
+    b->cv_work.notify_all();
+    if (b->worker.joinable()) b->worker.join();
+    delete b;
+}
+
+extern "C" lk_status lk_batcher_submit(lk_batcher *b, const lk_pairhmm_batch *region, const uint8_t *read_mapq,
+                                       int32_t ref_allele_index, double *values, uint8_t *keep_or_flags) {
+    if (!b || !region) return LK_ERR_INVALID;
+    if (region->n_regions != 1 || !region->region_read_start || !region->region_hap_start || region->region_read_start[0] != 0 ||
+        region->region_hap_start[0] != 0)
+        return LK_ERR_INVALID;
+    int64_t np = 0;
+    if (lk_pairhmm_batch_dims(region, &np, nullptr) != LK_OK) return LK_ERR_INVALID;
+    if (np > 0 && !values) return LK_ERR_INVALID;
+    Request q;
+    q.region = region; q.read_mapq = read_mapq; q.ref_allele_index = ref_allele_index; q.values = values; q.keep_or_flags = keep_or_flags;
+    std::unique_lock<std::mutex> lock(b->mu);
+    if (b->stop) return LK_ERR_INVALID;
+    b->queue.push_back(&q);
+    b->cv_work.notify_one();
+    b->cv_done.wait(lock, [&] { return q.done; });
+    return q.status;
+}
+
+extern "C" void lk_batcher_stats(lk_batcher *b, int64_t *n_batches, int64_t *n_regions) {
+    if (!b) return;
+    std::lock_guard<std::mutex> g(b->mu);
+    if (n_batches) *n_batches = b->n_batches;
+    if (n_regions) *n_regions = b->n_regions;
+}

@@ -96,3 +96,45 @@ class SmithWatermanAligner:
     def align(self, reference, alternate, parameters, overhang_strategy):
         off, cigar = self.ctx.sw_align(reference, alternate, parameters, overhang_strategy)
         return cigar, off
+
+
+class RegionBatcher:
+    """Cross-thread batching front-end (lk_batcher, include/lorikeet_b200.h): worker threads submit ONE region each, as
+    Lorikeet's Rayon tasks do (assembly_region_walker.rs:140-277); a dispatcher thread inside the library runs one launch
+    for everything pending.  engine=None batches bare PairHMM calls."""
+
+    def __init__(self, ctx, engine=None, max_regions=256, max_wait_us=200):
+        self.ctx = ctx
+        self.engine = engine
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        args = C.byref(engine.args) if engine is not None else None
+        ctx._check(self._L.lk_batcher_create(ctx._h, args, int(max_regions), int(max_wait_us), C.byref(self._h)))
+
+    def submit(self, region, read_mapq=None, ref_allele_index=0):
+        """Blocking; returns (values, keep) for an engine batcher, (log10 likelihoods [r*A + h], flags) otherwise."""
+        assert region.n_regions == 1
+        values = np.empty(region.n_pairs, dtype=np.float64)
+        aux = np.zeros(region.n_reads if self.engine is not None else region.n_pairs, dtype=np.uint8)
+        mapq = None if read_mapq is None else np.ascontiguousarray(read_mapq, dtype=np.uint8)
+        s = region.as_struct()
+        st = self._L.lk_batcher_submit(self._h, C.byref(s), mapq.ctypes.data_as(_lib.u8p) if mapq is not None else None,
+                                       int(ref_allele_index), values.ctypes.data_as(_lib.f64p), aux.ctypes.data_as(_lib.u8p))
+        self.ctx._check(st)
+        return values, aux
+
+    def stats(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._L.lk_batcher_stats(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def close(self):
+        if self._h:
+            self._L.lk_batcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
