@@ -281,6 +281,12 @@ lk_status lk_engine_modify_read_qualities(const lk_engine_args *args, int64_t n_
                                           const uint8_t *read_bases, uint8_t *read_qual, uint8_t *read_ins,
                                           uint8_t *read_del, const uint8_t *read_mapq, int n_threads);
 
+/* The same pre-ops as one device launch (the kernel the region driver runs on its staged copies): upload, launch,
+ * download, in place on the caller's arrays.  Byte-identical to lk_engine_modify_read_qualities. */
+lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const lk_engine_args *args, int64_t n_reads,
+                                                 const int64_t *read_off, const uint8_t *read_bases, uint8_t *read_qual,
+                                                 uint8_t *read_ins, uint8_t *read_del, const uint8_t *read_mapq);
+
 /*
  * Region driver = compute_read_likelihoods (:195-242) for a batch of single-sample regions:
  * modify_read_qualities on copies -> PairHMM on the GPU -> transpose into the reference's

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "lk_pairhmm_download", "lk_resident_free", "lk_pairhmm_forward",
     "lk_sw_batch_host", "lk_sw_upload", "lk_sw_run_resident", "lk_sw_download", "lk_sw_align",
     "lk_calculate_cigar_batch", "lk_calculate_cigar_shortcut", "lk_calculate_cigar_finish",
-    "lk_engine_modify_read_qualities", "lk_engine_compute_read_likelihoods",
+    "lk_engine_modify_read_qualities", "lk_engine_modify_read_qualities_device", "lk_engine_compute_read_likelihoods",
     "lk_realign_reads_batch", "lk_best_alleles_breaking_ties", "lk_realign_finish", "lk_cigar_apply_to_cigar",
     "lk_cigar_append_clipped_elements", "lk_read_start_on_reference_haplotype",
     "lk_batcher_create", "lk_batcher_destroy", "lk_batcher_submit", "lk_batcher_stats",
@@ -158,6 +158,8 @@ def load():
     ep = C.POINTER(EngineArgs)
     L.lk_engine_modify_read_qualities.restype = C.c_int
     L.lk_engine_modify_read_qualities.argtypes = [ep, C.c_int64, i64p, u8p, u8p, u8p, u8p, u8p, C.c_int]
+    L.lk_engine_modify_read_qualities_device.restype = C.c_int
+    L.lk_engine_modify_read_qualities_device.argtypes = [vp, ep, C.c_int64, i64p, u8p, u8p, u8p, u8p, u8p]
     L.lk_engine_compute_read_likelihoods.restype = C.c_int
     L.lk_engine_compute_read_likelihoods.argtypes = [vp, ep, bp, u8p, i32p, f64p, u8p]
     L.lk_realign_reads_batch.restype = C.c_int

@@ -151,6 +151,12 @@ extern "C" lk_status lk_engine_modify_read_qualities(const lk_engine_args *args,
     return LK_OK;
 }
 
+void lk_engine_fill_pcr_cache(const lk_engine_args *args, uint8_t cache[101]) {  // initialize_pcr_error_model :169-184
+    memset(cache, 0, 101);
+    if (args->pcr_error_model != LK_PCR_NONE)
+        for (int i = 0; i <= kMaxRepeatLength; i++) cache[i] = adjusted_qual(i, (double)args->pcr_error_model);
+}
+
 // Region driver.  Everything runs on the device inside the PairHMM chunk pipeline (lk_api.cu: lk_pairhmm_pipeline with a
 // hook): engine_modify_reads_kernel on the staged copies (the caller's arrays stay untouched), the PairHMM kernels,
 // engine_epilogue_kernel (transpose to [allele][read], normalise, thresholds from the ORIGINAL qualities and lengths --
@@ -174,8 +180,7 @@ extern "C" lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_en
     hook.ref_allele_index = ref_allele_index;
     hook.values = values;
     hook.keep = keep;
-    if (args->pcr_error_model != LK_PCR_NONE)  // initialize_pcr_error_model :169-184
-        for (int i = 0; i <= kMaxRepeatLength; i++) hook.pcr_cache[i] = adjusted_qual(i, (double)args->pcr_error_model);
+    lk_engine_fill_pcr_cache(args, hook.pcr_cache);
     lk_pairhmm_batch pb = *batch;
     pb.read_gcp = nullptr;  // gap_continuation_penalties is vec![constant_gcp; len] (:649-651)
     pb.gcp_constant = args->constant_gcp;

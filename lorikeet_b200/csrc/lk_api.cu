@@ -620,3 +620,53 @@ extern "C" int64_t lk_resident_pairs(const lk_resident *r) { return r ? r->n_pai
 extern "C" void *lk_resident_out_device_ptr(const lk_resident *r) { return r ? r->out.p : nullptr; }
 // duration of the fast-path (dominant) kernel launches inside the last timed lk_pairhmm_run_resident
 extern "C" float lk_resident_last_fast_ms(const lk_resident *r) { return r ? r->last_fast_ms : -1.f; }
+
+// modify_read_qualities on the device, stand-alone: the kernel the region driver runs on its staged copies, applied in
+// place to the caller's arrays (upload, one launch, download).  Same contract as the host utility
+// lk_engine_modify_read_qualities; exists so the device pre-ops can be compared byte for byte with it.
+extern "C" lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const lk_engine_args *args, int64_t n_reads,
+                                                            const int64_t *read_off, const uint8_t *read_bases, uint8_t *read_qual,
+                                                            uint8_t *read_ins, uint8_t *read_del, const uint8_t *read_mapq) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (!args || n_reads < 0) return lk_fail(ctx, LK_ERR_INVALID, "bad arguments");
+    if (n_reads == 0) return LK_OK;
+    if (!read_off || !read_bases || !read_qual || !read_ins || !read_del) return lk_fail(ctx, LK_ERR_INVALID, "null read arrays");
+    if (!args->disable_cap_read_qualities_to_mapq && !read_mapq) return lk_fail(ctx, LK_ERR_INVALID, "read_mapq required");
+    if (args->pcr_error_model < 0 || args->pcr_error_model > 3) return lk_fail(ctx, LK_ERR_INVALID, "bad PCR error model");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    const int64_t b0 = read_off[0], nb = read_off[n_reads] - b0;
+    DevBuf d_off, d_b, d_q, d_i, d_d, d_m;
+    cudaStream_t st = ctx->stream[0];
+    auto fail = [&](const char *what) { d_off.release(); d_b.release(); d_q.release(); d_i.release(); d_d.release(); d_m.release(); return lk_cuda_fail(ctx, e, what); };
+    if ((e = d_off.reserve((size_t)(n_reads + 1) * 8)) != cudaSuccess || (e = d_b.reserve((size_t)std::max<int64_t>(nb, 16))) != cudaSuccess ||
+        (e = d_q.reserve((size_t)std::max<int64_t>(nb, 16))) != cudaSuccess || (e = d_i.reserve((size_t)std::max<int64_t>(nb, 16))) != cudaSuccess ||
+        (e = d_d.reserve((size_t)std::max<int64_t>(nb, 16))) != cudaSuccess || (e = d_m.reserve((size_t)n_reads)) != cudaSuccess)
+        return fail("alloc");
+    if ((e = cudaMemcpyAsync(d_off.p, read_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_b.p, read_bases + b0, (size_t)nb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_q.p, read_qual + b0, (size_t)nb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_i.p, read_ins + b0, (size_t)nb, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_d.p, read_del + b0, (size_t)nb, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return fail("H2D");
+    if (read_mapq && (e = cudaMemcpyAsync(d_m.p, read_mapq, (size_t)n_reads, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D mapq");
+    EngineDevArgs E;
+    memset(&E, 0, sizeof E);
+    E.read_bases = (const uint8_t *)d_b.p - b0;
+    E.read_qual = (uint8_t *)d_q.p - b0; E.read_ins = (uint8_t *)d_i.p - b0; E.read_del = (uint8_t *)d_d.p - b0;
+    E.read_off = (const int64_t *)d_off.p;
+    E.read_mapq = read_mapq ? (const uint8_t *)d_m.p : nullptr;
+    E.use_pcr = args->pcr_error_model != LK_PCR_NONE;
+    E.cap_to_mapq = !args->disable_cap_read_qualities_to_mapq;
+    E.bq_threshold = args->base_quality_score_threshold;
+    lk_engine_fill_pcr_cache(args, E.pcr_cache);
+    if ((e = launch_engine_modify(E, n_reads, st)) != cudaSuccess) return fail("engine_modify_reads");
+    if ((e = cudaMemcpyAsync(read_qual + b0, d_q.p, (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(read_ins + b0, d_i.p, (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(read_del + b0, d_d.p, (size_t)nb, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return fail("D2H");
+    d_off.release(); d_b.release(); d_q.release(); d_i.release(); d_d.release(); d_m.release();
+    return LK_OK;
+}

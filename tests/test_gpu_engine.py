@@ -177,3 +177,47 @@ def test_region_driver_on_long_reads(ctx):
     assert np.array_equal(np.isnan(values), nan)
     rel = np.abs(values[~nan] - evalues[~nan]) / np.maximum(np.abs(evalues[~nan]), 1e-3)
     assert rel.max() < 1e-4
+
+
+def test_device_pre_ops_are_byte_identical_to_the_host_utility(ctx):
+    # engine_modify_reads_kernel (shared-memory path up to 1024 bases, global-memory scan above) against
+    # lk_engine_modify_read_qualities on reads built to be hard: homopolymers, tandem repeats of every unit length 1..22,
+    # repeats touching either end, reads of length 1..3, lengths around the 1024-base path switch
+    from lorikeet_b200 import _lib
+    from lorikeet_b200.engine import PairHMMLikelihoodCalculationEngine
+    L = _lib.load()
+    rng = np.random.default_rng(123)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    reads = []
+    for length in [1, 2, 3, 5, 31, 32, 33, 64, 100, 150, 151, 255, 256, 257, 300, 1023, 1024, 1025, 1500] + list(rng.integers(20, 260, 300)):
+        length = int(length)
+        r = rng.choice(acgt, length)
+        for _ in range(int(rng.integers(0, 5))):
+            u = int(rng.integers(1, 23))
+            reps = int(rng.integers(2, 30))
+            unit = rng.choice(acgt, u)
+            k = int(rng.integers(-u, max(1, length)))
+            seg = np.resize(unit, u * reps)
+            a, e = max(k, 0), min(k + len(seg), length)
+            if e > a:
+                r[a:e] = seg[a - k:e - k]
+        reads.append(r)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    bases = np.ascontiguousarray(np.concatenate(reads))
+    n = len(reads)
+    for pcr, no_cap, thr in ((3, 0, 18), (1, 1, 6), (2, 0, 30), (0, 0, 18)):
+        q = rng.integers(2, 42, bases.size).astype(np.uint8)
+        ins = rng.integers(3, 50, bases.size).astype(np.uint8)
+        dele = rng.integers(3, 50, bases.size).astype(np.uint8)
+        mapq = rng.integers(0, 61, n).astype(np.uint8)
+        eng = PairHMMLikelihoodCalculationEngine(ctx, 10, -4.5, pcr, thr, False, 1.0, 0.02, True, bool(no_cap), False)
+        hq, hi, hd = q.copy(), ins.copy(), dele.copy()
+        p = lambda a, t: a.ctypes.data_as(t)
+        assert L.lk_engine_modify_read_qualities(C.byref(eng.args), n, p(off, _lib.i64p), p(bases, _lib.u8p), p(hq, _lib.u8p),
+                                                 p(hi, _lib.u8p), p(hd, _lib.u8p), p(mapq, _lib.u8p), 4) == 0
+        dq, di, dd = q.copy(), ins.copy(), dele.copy()
+        ctx._check(L.lk_engine_modify_read_qualities_device(ctx._h, C.byref(eng.args), n, p(off, _lib.i64p), p(bases, _lib.u8p),
+                                                            p(dq, _lib.u8p), p(di, _lib.u8p), p(dd, _lib.u8p), p(mapq, _lib.u8p)))
+        assert np.array_equal(dq, hq)
+        bad = np.nonzero((di != hi) | (dd != hd))[0]
+        assert bad.size == 0, (pcr, bad[:5], di[bad[:5]], hi[bad[:5]])
