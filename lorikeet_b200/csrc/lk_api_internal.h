@@ -69,7 +69,7 @@ struct lk_resident {
     // engine pre/post-ops on the device (N3)
     DevBuf region_read_start, read_mapq, ref_allele_index, qual_orig, values, keep;
     // ---- Smith-Waterman ----
-    struct SwLaunch { int K; int32_t first; int32_t count; };
+    struct SwLaunch { int K; int32_t first; int32_t count; bool clamp; };
     std::vector<SwLaunch> sw_launches;
     int sw_blocks = 0;
     int64_t sw_scratch_words = 0;

@@ -40,6 +40,6 @@ struct EngineDevArgs {
 };
 cudaError_t launch_engine_modify(const EngineDevArgs &E, int64_t n_reads, cudaStream_t st);
 cudaError_t launch_engine_epilogue(const EngineDevArgs &E, int64_t n_regions, cudaStream_t st);
-cudaError_t launch_sw(int K, const SwArgs &A, int n_blocks, cudaStream_t st);
+cudaError_t launch_sw(int K, bool clamp, const SwArgs &A, int n_blocks, cudaStream_t st);
 
 }  // namespace lk

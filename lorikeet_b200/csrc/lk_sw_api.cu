@@ -60,16 +60,19 @@ lk_status sw_upload_locked(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off,
     for (int ki = 0; ki < kNumSwKs; ki++) {
         const int K = kSwKs[ki];
         const size_t first = order.size();
+        int64_t nm_max = 0;
         for (int64_t p = 0; p < n_pairs; p++) {
             const int n = (int)(ref_off[p + 1] - ref_off[p]), m = (int)(alt_off[p + 1] - alt_off[p]);
             if (sw_choose_k(n) != K) continue;
             order.push_back((int32_t)p);
-            if (n > 0 && m > 0) max_words = std::max(max_words, sw_bt_words(n, m, K) + 2 * ((int64_t)m + 1) + 32);
+            nm_max = std::max<int64_t>(nm_max, (int64_t)n + m);
+            if (n > 0 && m > 0) max_words = std::max(max_words, sw_scratch_words(n, m, K));
         }
         std::stable_sort(order.begin() + (long)first, order.end(), [&](int32_t a, int32_t b) {
             return (ref_off[a + 1] - ref_off[a]) * (alt_off[a + 1] - alt_off[a]) > (ref_off[b + 1] - ref_off[b]) * (alt_off[b + 1] - alt_off[b]);
         });
-        if (order.size() > first) R->sw_launches.push_back(lk_resident::SwLaunch{ K, (int32_t)first, (int32_t)(order.size() - first) });
+        if (order.size() > first) R->sw_launches.push_back(lk_resident::SwLaunch{ K, (int32_t)first, (int32_t)(order.size() - first),
+                !sw_clamp_inactive(nm_max, params->match_value, params->mismatch_penalty, params->gap_open_penalty, params->gap_extend_penalty) });
     }
     for (int64_t p = 0; p < n_pairs; p++) R->sw_cells += (ref_off[p + 1] - ref_off[p]) * (alt_off[p + 1] - alt_off[p]);
     // persistent grid: up to 16 warps per SM, fewer if the per-warp backtrack scratch would exceed ~12 GB
@@ -123,7 +126,7 @@ lk_status sw_run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
         A.order = (const int32_t *)R->sw_order.p + L.first;
         A.n_order = L.count;
         A.cursor = (int32_t *)R->counters.p + li++;
-        if ((e = launch_sw(L.K, A, R->sw_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
+        if ((e = launch_sw(L.K, L.clamp, A, R->sw_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
         R->launch_count++;
     }
     if (kernel_ms) cudaEventRecord(ev1, st);

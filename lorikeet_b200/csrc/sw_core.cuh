@@ -81,6 +81,26 @@ LK_DEV uint32_t sw_push_sign(uint32_t plane, int32_t d) {      // (plane << 1) |
     return (plane << 1) | ((uint32_t)d >> 31);
 #endif
 }
+// ---- substitution-weight table --------------------------------------------------------------
+// The match / mismatch weight of a cell, (ref[i] == alt[j]) ? w_match : w_mismatch, costs a compare and a select per cell
+// on the 16-lane ALU pipe.  Instead each lane keeps, in per-warp shared memory, the weight of each of its K rows against
+// each base an alternate column can hold: tab[class][k/4][lane] is an int4, so a step fetches its K weights with
+// ceil(K/4) conflict-free LDS.128 at an address picked by the column's byte.  Classes are the exact bytes 'A' 'C' 'G' 'T'
+// 'N' (the reference compares raw bytes, smith_waterman_aligner.rs:197-202); a pair whose alternate holds any other byte
+// takes the compare-and-select path (decided once per pair, warp-uniform), so nothing is assumed about the alphabet.
+constexpr int SW_N_CLASSES = 5;
+LK_DEV int sw_byte_class(uint32_t b) {  // 0..4, or SW_N_CLASSES for "some other byte"
+    switch (b) {
+        case 'A': return 0;
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        case 'N': return 4;
+        default: return SW_N_CLASSES;
+    }
+}
+template <int K> struct SwTable { static constexpr int words = SW_N_CLASSES * ((K + 3) / 4) * 32 * 4; };
+
 // H[k] for a warp-uniform runtime k (a switch keeps it to one branch instead of a K-long select chain)
 template <int K>
 LK_DEV int32_t sw_pick(const int32_t (&H)[K], int k) {
@@ -104,8 +124,22 @@ LK_HD int64_t sw_bt_words(int n, int m, int K) {
     return (int64_t)n_bands * (int64_t)(m + 32) * 4 * 32;  // one uint4 of bit-planes per (step, lane)
 }
 
-template <class Wp, int K>
-LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
+// CLAMP = false drops the max(-1e8, .) of smith_waterman_aligner.rs:31,248-260 from the cell: the host proves per launch
+// that no score can get that low ((n + m + 2) * max|weight| < 1e8, sw_clamp_inactive), which is every realistic input.
+LK_HD bool sw_clamp_inactive(int64_t nm_max, int32_t wm, int32_t wx, int32_t wo, int32_t we) {
+    int64_t a = wm < 0 ? -(int64_t)wm : wm, b = wx < 0 ? -(int64_t)wx : wx, c = wo < 0 ? -(int64_t)wo : wo, d = we < 0 ? -(int64_t)we : we;
+    int64_t mx = a > b ? a : b;
+    mx = mx > c ? mx : c;
+    mx = mx > d ? mx : d;
+    return (nm_max + 2) * mx < 100000000LL;
+}
+
+// words of per-warp scratch one pair needs: backtrack planes, two band-boundary rows, one class byte per alternate base
+LK_HD int64_t sw_scratch_words(int n, int m, int K) { return sw_bt_words(n, m, K) + 2 * ((int64_t)m + 1) + ((int64_t)m + 3) / 4 + 36; }
+
+template <class Wp, int K, bool CLAMP = true>
+LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, int32_t *wtab) {
+    constexpr int KQ = (K + 3) / 4;
     const int lane = w.lane();
     const uint8_t *ref = A.refs + A.ref_off[pair];
     const uint8_t *alt = A.alts + A.alt_off[pair];
@@ -152,6 +186,19 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
     uint32_t *bt = scratch;                                         // [band][step][lane] x uint4 {pd, pr, ho, vo}
     int32_t *bndH = (int32_t *)(scratch + sw_bt_words(n, m, K));    // two boundary rows: H then F
     int32_t *bndF = bndH + (m + 1);
+    // class of every alternate base, once per pair; the weight table is used when all of them are A C G T N (warp-uniform)
+    uint8_t *acls = (uint8_t *)(bndF + (m + 1));
+    bool use_table;
+    {
+        bool other = false;
+        for (int j = lane; j < m; j += 32) {
+            const int cl = sw_byte_class(alt[j]);
+            other |= (cl == SW_N_CLASSES);
+            acls[j] = (uint8_t)(cl == SW_N_CLASSES ? 0 : cl);
+        }
+        use_table = w.ballot(other) == 0u;
+        w.sync();
+    }
     // best cell of the last column (scan top->bottom with >=, :301-307) and bottom-row summary
     int32_t col_max = (int32_t)(-2147483647 - 1);
     int col_p1 = 0;
@@ -171,6 +218,15 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
             H[k] = edge_gaps ? (wo + (i - 1) * we) : 0;  // sw[i][0]
             E[k] = SW_LOW_INIT;                           // best_gap_h[i]
         }
+        // substitution weights of this lane's rows against each alternate class (rows past the reference never match)
+        w.sync();
+#pragma unroll
+        for (int k = 0; k < KQ * 4; k++) {
+            const int cls_of_row = (k < K) ? sw_byte_class(rb[k < K ? k : 0]) : SW_N_CLASSES;
+#pragma unroll
+            for (int c = 0; c < SW_N_CLASSES; c++) wtab[((c * KQ + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = (cls_of_row == c) ? wm : wx;
+        }
+        w.sync();
         // column 0 of the row above this lane's strip
         const int i_above = row0 + lane * K;  // matrix row index of the row above (0 = top row)
         int32_t Hd = (i_above == 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
@@ -180,6 +236,7 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
         const int bottom_lane = (rows - 1) / K, bottom_k = (rows - 1) % K;
         const int n_steps = m + lanes - 1;
 
+        int cls_ahead = (use_table && lane == 0) ? (int)acls[0] : 0;  // column of step 1 (only lane 0 is active then)
         for (int s = 1; s <= n_steps; s++) {
             const int c = s - lane;
             if (lane == 0) {  // row above comes from the matrix top row or from the previous band
@@ -187,27 +244,48 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch) {
                 else if (c <= m) { Hu = bndH[c]; Fu = bndF[c]; }
             }
             const bool active = (c >= 1) && (c <= m) && (lane < lanes);
+            // class of the NEXT step's column, fetched one step ahead so its latency hides behind this step's cells
+            const int cls_next = cls_ahead;
+            if (use_table) cls_ahead = (c >= 0 && c < m) ? (int)acls[c] : 0;
             int32_t h_last = 0, f_last = SW_LOW_INIT;
             if (active) {
-                const uint32_t ab = w.ldg(alt + c - 1);
+                int32_t wt[KQ * 4];
+                if (use_table) {
+                    const int cls = cls_next;
+#pragma unroll
+                    for (int q = 0; q < KQ; q++) w.lds4i(wt + 4 * q, wtab + ((cls * KQ + q) * 32 + lane) * 4);
+                } else {  // some alternate byte is outside ACGTN: raw byte compare for this pair, as the reference does everywhere
+                    const uint32_t ab = w.ldg(alt + c - 1);
+#pragma unroll
+                    for (int k = 0; k < K; k++) wt[k] = (rb[k] == ab) ? wm : wx;
+                }
                 int32_t hdiag = Hd, hup = Hu, fup = Fu;
                 uint32_t pl_d = 0u, pl_r = 0u, pl_h = 0u, pl_v = 0u;
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const int32_t hold = H[k];
-                    const int32_t step_diag = hdiag + ((rb[k] == ab) ? wm : wx);     // :197-202
+                    const int32_t step_diag = hdiag + wt[k];                         // :197-202
                     const int32_t ext_v = fup + we;                                  // :210-222
                     const int32_t step_down = sw_addmax(hup, wo, ext_v);             // max(hup + wo, ext_v)
                     const int32_t ext_h = E[k] + we;                                 // :232-245
                     const int32_t step_right = sw_addmax(hold, wo, ext_h);
-                    const int32_t gap = step_right > step_down ? step_right : step_down;
+                    // choice: diagonal if >= both gaps, else the larger gap (:248-260).  Without the clamp one 3-input max gives
+                    // the cell and "not diagonal" is best > step_diag; with it the 2-input max of the gaps is needed as well.
+                    int32_t best, not_diag;
+                    if (CLAMP) {
+                        const int32_t gap = step_right > step_down ? step_right : step_down;
+                        best = sw_max3(step_diag, gap, SW_MATRIX_MIN_CUTOFF);
+                        not_diag = step_diag - gap;
+                    } else {
+                        best = sw_max3(step_diag, step_right, step_down);
+                        not_diag = step_diag - best;
+                    }
                     // each plane shifts in the SIGN BIT of a difference (one funnel shift per bit; the subtractions can
-                    // issue on the otherwise idle FMA pipe): row k ends up at bit K-1-k
+                    // issue on the FMA pipe): row k ends up at bit K-1-k
                     pl_v = sw_push_sign(pl_v, ext_v - step_down);      // set: opened (hup + wo > fup + we)
                     pl_h = sw_push_sign(pl_h, ext_h - step_right);     // set: opened
-                    pl_d = sw_push_sign(pl_d, step_diag - gap);        // set: NOT diagonal (:248-252 wants diag >= both)
+                    pl_d = sw_push_sign(pl_d, not_diag);               // set: NOT diagonal (:248-252 wants diag >= both)
                     pl_r = sw_push_sign(pl_r, step_right - step_down); // set: vertical (right < down), clear: horizontal
-                    const int32_t best = sw_max3(step_diag, gap, SW_MATRIX_MIN_CUTOFF);
                     E[k] = step_right;
                     H[k] = best;
                     hdiag = hold; hup = best; fup = step_down;

@@ -19,14 +19,20 @@ struct SwDevWarp {
     __device__ __forceinline__ void store4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
         *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
     }
+    __device__ __forceinline__ void lds4i(int32_t *dst, const int32_t *src) const {
+        const int4 v = *reinterpret_cast<const int4 *>(src);
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
     __device__ __forceinline__ void load4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const {
         const uint4 v = *reinterpret_cast<const uint4 *>(p);
         a = v.x; b = v.y; c = v.z; d = v.w;
     }
 };
 
-template <int K>
+template <int K, bool CLAMP>
 __global__ void __launch_bounds__(LK_SW_THREADS) sw_kernel(const SwArgs A) {
+    extern __shared__ int4 lk_sw_smem[];  // per-warp substitution-weight tables
+    int32_t *wtab = reinterpret_cast<int32_t *>(lk_sw_smem) + (threadIdx.x >> 5) * SwTable<K>::words;
     SwDevWarp w;
     const int warp_in_grid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     uint32_t *scratch = A.scratch + (int64_t)warp_in_grid * A.scratch_words;
@@ -35,15 +41,29 @@ __global__ void __launch_bounds__(LK_SW_THREADS) sw_kernel(const SwArgs A) {
         if (w.lane() == 0) idx = atomicAdd(A.cursor, 1);
         idx = w.shfl(idx, 0);
         if (idx >= A.n_order) break;
-        sw_align_pair<SwDevWarp, K>(w, A, A.order[idx], scratch);
+        sw_align_pair<SwDevWarp, K, CLAMP>(w, A, A.order[idx], scratch, wtab);
         __syncwarp();
     }
 }
 
-cudaError_t launch_sw(int K, const SwArgs &A, int n_blocks, cudaStream_t st) {
+template <int K, bool CLAMP>
+static cudaError_t launch_sw_k(const SwArgs &A, int n_blocks, cudaStream_t st) {
+    const int smem = (LK_SW_THREADS / 32) * SwTable<K>::words * (int)sizeof(int32_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sw_kernel<K, CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    sw_kernel<K, CLAMP><<<n_blocks, LK_SW_THREADS, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+// clamp: false when the host has proved the -1e8 clamp inactive for every pair of the launch (sw_clamp_inactive)
+cudaError_t launch_sw(int K, bool clamp, const SwArgs &A, int n_blocks, cudaStream_t st) {
     if (A.n_order == 0) return cudaSuccess;
     switch (K) {
-#define LK_CASE(KV) case KV: sw_kernel<KV><<<n_blocks, LK_SW_THREADS, 0, st>>>(A); break;
+#define LK_CASE(KV) case KV: return clamp ? launch_sw_k<KV, true>(A, n_blocks, st) : launch_sw_k<KV, false>(A, n_blocks, st);
         LK_SW_K_TABLE(LK_CASE)
 #undef LK_CASE
         default: return cudaErrorInvalidValue;

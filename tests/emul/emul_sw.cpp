@@ -45,6 +45,7 @@ struct SwEmulWarp {
     template <class T> T ldg(const T *p) const { return *p; }
     void sync() { sh->bar.arrive_and_wait(); }
     void store4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+    void lds4i(int32_t *dst, const int32_t *src) const { memcpy(dst, src, 16); }
     void load4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const { a = p[0]; b = p[1]; c = p[2]; d = p[3]; }
 };
 
@@ -67,13 +68,17 @@ extern "C" int emul_sw_batch(int64_t n_pairs, const int64_t *ref_off, const uint
     for (int64_t p = 0; p < n_pairs; p++) {
         const int n = (int)(ref_off[p + 1] - ref_off[p]), m = (int)(alt_off[p + 1] - alt_off[p]);
         const int K = choose_k(n, force_k);
-        std::vector<uint32_t> scratch((size_t)(n > 0 && m > 0 ? sw_bt_words(n, m, K) + 2 * (m + 1) + 32 : 64));
+        // same rule as the host launcher; odd pairs take the clamped form so both instantiations are exercised
+        const bool clamp = !sw_clamp_inactive((int64_t)n + m, params[0], params[1], params[2], params[3]) || (p & 1);
+        std::vector<int32_t> wtab((size_t)SwTable<17>::words);
+        std::vector<uint32_t> scratch((size_t)(n > 0 && m > 0 ? sw_scratch_words(n, m, K) : 64));
         std::vector<std::thread> th;
         for (int l = 0; l < 32; l++)
             th.emplace_back([&, l]() {
                 SwEmulWarp w{ l, &sh };
                 switch (K) {
-#define LK_CASE(KV) case KV: sw_align_pair<SwEmulWarp, KV>(w, A, (int)p, scratch.data()); break;
+#define LK_CASE(KV) case KV: if (clamp) sw_align_pair<SwEmulWarp, KV, true>(w, A, (int)p, scratch.data(), wtab.data()); \
+                             else sw_align_pair<SwEmulWarp, KV, false>(w, A, (int)p, scratch.data(), wtab.data()); break;
                     LK_SW_K_TABLE(LK_CASE)
 #undef LK_CASE
                 }

@@ -54,3 +54,11 @@ def test_capacity_and_empty():
     ro = np.array([0, 0, 4]); ao = np.array([0, 3, 3])
     ops, n_ops, offs = E.sw_batch(ro, np.frombuffer(b"ACGT", np.uint8), ao, np.frombuffer(b"ACG", np.uint8), SC.ORIGINAL_DEFAULT, "SoftClip")
     assert list(n_ops) == [-1, -1]
+
+
+def test_bytes_outside_acgtn_take_the_compare_path():
+    # the substitution-weight table covers the exact bytes A C G T N; any other byte in an alternate column (lower case,
+    # IUPAC codes, '-') must fall back to the reference's raw byte comparison for that column
+    pairs = SC.random_pairs(40, seed=17, alphabet=b"ACGTNacgtRY-")
+    for strategy in ("SoftClip", "InDel"):
+        _compare(pairs, SC.NEW_SW_PARAMETERS, strategy)

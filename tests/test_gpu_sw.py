@@ -120,3 +120,12 @@ def test_resident_repeatable_and_edge_cases(ctx):
     import lorikeet_b200 as lk
     with pytest.raises(lk.LorikeetError):
         ctx.sw_align(b"", b"ACGT", SC.ORIGINAL_DEFAULT, "SoftClip")
+
+
+def test_bytes_outside_acgtn_and_clamped_form(ctx):
+    # alternate columns holding bytes outside A C G T N use the raw byte compare instead of the weight table; weights large
+    # enough that (n + m) * max|w| >= 1e8 select the kernel that keeps the reference's -1e8 clamp
+    pairs = SC.random_pairs(400, seed=23, alphabet=b"ACGTNacgtRY-")
+    for params, strategy in ((SC.NEW_SW_PARAMETERS, "SoftClip"), (SC.STANDARD_NGS, "InDel"), ([900000, -700000, -800000, -100000], "SoftClip"),
+                             ([900000, -700000, -800000, -100000], "LeadingInDel")):
+        _compare(ctx, pairs, params, strategy)
