@@ -362,7 +362,12 @@ LK_UNROLL_N(LK_FAST_UNROLL)
 // data (a 4th shuffle / the 4th word of the boundary element) and the receiver re-aligns what it gets
 // with one FMUL per value.  Fully adaptive: no a-priori decay estimate, no retries.
 // =============================================================================================
-struct Bnd4 { float m, i, d; int32_t xi; };
+// 16-byte aligned so a boundary element moves as ONE 128-bit load / store (per-warp scratch slices are 16-byte multiples)
+#if defined(__CUDACC__)
+struct __align__(16) Bnd4 { float m, i, d; int32_t xi; };
+#else
+struct alignas(16) Bnd4 { float m, i, d; int32_t xi; };
+#endif
 
 constexpr int BAND_INIT_EXP = 40;  // initial condition 2^40 / H
 
@@ -488,9 +493,11 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         cur_b.m = 0.f; cur_b.i = 0.f; cur_b.d = 0.f; cur_b.xi = 0;
         if (band > 0) cur_b = bin[1 <= H ? 1 : H];
 
+        int slice_ahead = (int)w.ldg(hp + 1);
 LK_UNROLL_N(LK_BAND_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
-            const float *trow = tab + ((int)w.ldg(hp + s) * KQ * 32 + lane) * 4;
+            const float *trow = tab + (slice_ahead * KQ * 32 + lane) * 4;
+            slice_ahead = (int)w.ldg(hp + s + 1);  // next step's column, fetched ahead of the LDS address it forms
             float sel[KQ * 4];
 #pragma unroll
             for (int q = 0; q < KQ; q++) w.lds4(sel + 4 * q, trow + q * 128);
