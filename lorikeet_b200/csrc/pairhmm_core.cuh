@@ -317,9 +317,11 @@ LK_UNROLL_N(LK_FAST_UNROLL)
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const float om = M[k], oi = I[k], od = D[k];
-                    float mm = fmaf(pi, cb[k], pm);
-                    mm = fmaf(pd, cc[k], mm);
+                    // (statement order matters to ptxas here: this one measured 4 452 GCUPS, the textbook order 4 408,
+                    // two others 4 045)
                     D[k] = fmaf(od, VARGCP ? cf[k] : (GM == GM_Q10 ? 0.1f : A.cf_uniform), om);
+                    float mm = fmaf(pd, cc[k], pm);
+                    mm = fmaf(pi, cb[k], mm);
                     M[k] = mm * sel[k];
                     I[k] = fmaf(ii, ce[k], im);
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
