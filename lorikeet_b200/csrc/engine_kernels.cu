@@ -32,52 +32,47 @@ __device__ __forceinline__ bool same_bytes(const uint8_t *a, const uint8_t *b, i
     return true;
 }
 
-// VariantContextUtils::find_number_of_repetitions_main (variant_context_utils.rs:276-337).  A window that IS the unit
-// (the unit is a slice of the same read: its own position is the first window of every scan here) counts without a compare.
-__device__ int count_repeats(const uint8_t *unit, int unit_len, const uint8_t *test, int test_len, bool leading) {
-    if (test_len == 0) return 0;
-    const int diff = test_len - unit_len;
-    int reps = 0;
-    if (leading) {
-        for (int s = 0; s <= diff; s += unit_len) {
-            if (test + s != unit && !same_bytes(test + s, unit, unit_len)) break;
-            reps++;
-        }
-    } else {
-        for (int s = diff; s >= 0; s -= unit_len) {
-            if (test + s != unit && !same_bytes(test + s, unit, unit_len)) break;
-            reps++;
-        }
-    }
-    return reps;
+// find_tandem_repeat_units(...).1 (...engine.rs:528-611), by run lengths.  Consecutive copies of a unit of length s are
+// a run of positions with b[p] == b[p - s]: the reference's window-by-window counts are
+//   copies ending at `offset`        = 1 + RB / s,  RB = run of equalities ending at offset
+//   copies starting at `offset + 1`  = 1 + RF / s,  RF = run starting at offset + 1 + s
+//   copies of a forward unit (length L) that precede it = RB' / L,  RB' = run ending at offset + L
+// so each (offset, s) costs one short while loop instead of window compares behind a call -- which matters because the
+// lanes of a warp sit on different offsets: with the call, some lane was inside it at almost every s and the warp ran
+// at 8.7 active lanes of 32.
+__device__ __forceinline__ int run_back(const uint8_t *b, int q, int s) {  // run of b[p] == b[p - s] ending at q
+    int p = q;
+    while (p >= s && b[p] == b[p - s]) p--;
+    return q - p;
 }
-
-// find_tandem_repeat_units(...).1 (...engine.rs:528-611)
 __device__ int tandem_repeat_length(const uint8_t *bases, int len, int offset) {
-    int max_bw = 0;
-    const uint8_t *best_bw = bases + offset;
-    int best_bw_len = 1;
+    int max_bw = 0, bw_len = 1;
     for (int str = 1; str <= kMaxStrUnitLength; str++) {
         if (offset + 1 < str) break;
-        const uint8_t *unit = bases + offset + 1 - str;
-        max_bw = count_repeats(unit, str, bases, offset + 1, false);
-        if (max_bw > 1) { best_bw = unit; best_bw_len = str; break; }
+        const int run = run_back(bases, offset, str);
+        max_bw = run >= str ? 1 + run / str : 1;
+        if (max_bw > 1) { bw_len = str; break; }
     }
     int max_rl = max_bw;
     if (offset < len - 1) {
-        const uint8_t *best_fw = bases + offset + 1;
-        int best_fw_len = 1, max_fw = 0;
+        int fw_len = 1, max_fw = 0;
         for (int str = 1; str <= kMaxStrUnitLength; str++) {
             if (offset + str + 1 > len) break;
-            const uint8_t *unit = bases + offset + 1;
-            max_fw = count_repeats(unit, str, bases + offset + 1, len - offset - 1, true);
-            if (max_fw > 1) { best_fw = unit; best_fw_len = str; break; }
+            const int p0 = offset + 1 + str;
+            int p = p0;
+            while (p < len && bases[p] == bases[p - str]) p++;
+            max_fw = (p - p0) >= str ? 1 + (p - p0) / str : 1;
+            if (max_fw > 1) { fw_len = str; break; }
         }
-        if (best_fw_len == best_bw_len && same_bytes(best_fw, best_bw, best_fw_len)) {
+        if (fw_len == bw_len && same_bytes(bases + offset + 1, bases + offset + 1 - bw_len, fw_len)) {
             max_rl = max_bw + max_fw;
         } else {
-            max_bw = count_repeats(best_fw, best_fw_len, bases, offset + 1, false);
-            max_rl = max_fw + max_bw;
+            int before = 0;  // copies of the forward unit among the bases up to `offset`
+            if (offset + 1 >= fw_len) {
+                const int run = run_back(bases, offset + fw_len, fw_len);
+                before = run >= fw_len ? run / fw_len : 0;
+            }
+            max_rl = max_fw + before;
         }
     }
     return max_rl < kMaxRepeatLength ? max_rl : kMaxRepeatLength;
