@@ -239,10 +239,12 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
         int cls_ahead = (use_table && lane == 0) ? (int)acls[0] : 0;  // column of step 1 (only lane 0 is active then)
         for (int s = 1; s <= n_steps; s++) {
             const int c = s - lane;
-            if (lane == 0) {  // row above comes from the matrix top row or from the previous band
-                if (band == 0) { Hu = edge_gaps ? (wo + (c - 1) * we) : 0; Fu = SW_LOW_INIT; }
-                else if (c <= m) { Hu = bndH[c]; Fu = bndF[c]; }
-            }
+            // row above lane 0 comes from the matrix top row or from the previous band (selects, not a divergent branch)
+            if (band == 0) {
+                const int32_t top = edge_gaps ? (wo + (c - 1) * we) : 0;
+                Hu = lane == 0 ? top : Hu;
+                Fu = lane == 0 ? SW_LOW_INIT : Fu;
+            } else if (lane == 0 && c <= m) { Hu = bndH[c]; Fu = bndF[c]; }
             const bool active = (c >= 1) && (c <= m) && (lane < lanes);
             // class of the NEXT step's column, fetched one step ahead so its latency hides behind this step's cells
             const int cls_next = cls_ahead;
@@ -299,7 +301,8 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
                         if (i <= n && H[k] >= col_max) { col_max = H[k]; col_p1 = i; }
                     }
                 }
-                if (has_bottom && lane == bottom_lane) {  // bottom row summary (:316-329), see below
+                if (has_bottom) {  // bottom row summary (:316-329), see below.  Every lane keeps one for its row at register
+                    // bottom_k (warp-uniform index, no divergence); only bottom_lane's is read afterwards.
                     int32_t cur = sw_pick<K>(H, bottom_k);
                     const int dj = (n > c) ? (n - c) : (c - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
                     if (cur > bot_max || (cur == bot_max && dj < db)) { bot_max = cur; bot_j = c; }
