@@ -18,8 +18,8 @@ const int *fast_k_values(int *n) {
 // Pick rows-per-lane for a read of length R: maximise useful cell-updates per issue slot.
 //   lanes per read G = ceil(R/K); reads per warp p = floor(32/G);
 //   row efficiency = p*R / (32*K); skew efficiency ~ H/(H+G-1) with H ~ 2R;
-//   issue slots per cell ~ 7 + 10/K; a mild penalty for the lower occupancy of the big-K variants
-//   (measured on B200 for R = 150: K = 10 / 15 / 19 within 4 % of each other, profiles/).
+//   issued instructions per cell ~ 5.25 (FMUL + 4 FFMA + a quarter LDS.128) + 14/K of per-step bookkeeping
+//   (measured on B200 for R = 150: K = 19 -> 4 450 GCUPS, K = 20 -> 4 220, K = 15 -> 3 890, K = 16 -> 3 630).
 int choose_k(int R, int force_k) {
     int n = 0;
     const int *ks = fast_k_values(&n);
@@ -38,8 +38,7 @@ int choose_k(int R, int force_k) {
         const double row_eff = (double)(p * R) / (32.0 * K);
         const double H = std::max(2.0 * R, 64.0);
         const double skew = H / (H + G - 1);
-        const double occ = K <= 10 ? 1.0 : (K <= 15 ? 0.97 : 0.95);
-        const double score = row_eff * skew * occ / (7.0 + 10.0 / K);
+        const double score = row_eff * skew / (5.25 + 14.0 / K);
         if (score > best) { best = score; best_k = K; }
     }
     return best_k;  // 0: too long for the fast path
