@@ -178,7 +178,11 @@ static cudaError_t launch_fast_kg(const PairHmmArgs &A, cudaStream_t st) {
     const int warps_per_block = LK_FAST_THREADS / 32;
     const unsigned blocks = (unsigned)((A.n_tasks + warps_per_block - 1) / warps_per_block);
     const int smem = warps_per_block * FastTable<K>::floats * (int)sizeof(float);
-    static bool configured = false;  // per instantiation; the attribute is idempotent, so a race is harmless
+    // the opt-in is per function AND per device: one flag per device ordinal (idempotent, so a race is harmless)
+    static bool configured_on[64] = { false };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &configured = configured_on[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(pairhmm_fast_kernel<K, GM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
@@ -208,7 +212,10 @@ cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t s
 cudaError_t launch_band(const PairHmmArgs &A, int n_blocks, cudaStream_t st) {
     if (A.n_band == 0) return cudaSuccess;
     const int smem = (LK_BAND_THREADS / 32) * FastTable<LK_BAND_K>::floats * (int)sizeof(float);
-    static bool configured = false;
+    static bool configured_on[64] = { false };  // per device ordinal: the attribute is per function and device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &configured = configured_on[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(pairhmm_band_kernel<LK_BAND_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(pairhmm_band_kernel<LK_BAND_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

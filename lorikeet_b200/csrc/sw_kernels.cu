@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(LK_SW_THREADS) sw_kernel(const SwArgs A) {
 template <int K, bool CLAMP>
 static cudaError_t launch_sw_k(const SwArgs &A, int n_blocks, cudaStream_t st) {
     const int smem = (LK_SW_THREADS / 32) * SwTable<K>::words * (int)sizeof(int32_t);
-    static bool configured = false;
+    static bool configured_on[64] = { false };  // per device ordinal: the attribute is per function and device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &configured = configured_on[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(sw_kernel<K, CLAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

@@ -57,3 +57,23 @@ def test_dispatcher_world2_nccl():
     with lk.Context(0) as ctx:
         exp = ctx.pairhmm_batch(b)
     assert np.array_equal(results[0], exp) and np.array_equal(results[1], exp)
+
+
+def test_two_devices_in_one_process():
+    # the kernels' shared-memory opt-in is per function AND per device: a second context on another device in the same
+    # process must work (one host thread + lk_ctx per device is the layout SURVEY 8(e) describes)
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import lorikeet_b200 as lk
+    from lorikeet_b200 import synth
+    b = synth.pairhmm_regions(12, first_region=500)
+    ro, refs, ao, alts = synth.sw_pairs(200)
+    outs = []
+    for dev in (0, 1):
+        with lk.Context(dev) as ctx:
+            outs.append((ctx.pairhmm_batch(b), ctx.sw_batch(ro, refs, ao, alts, [200, -150, -260, -11], "SoftClip")))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    for a, c in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, c)
