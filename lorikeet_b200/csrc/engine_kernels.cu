@@ -45,7 +45,7 @@ __device__ __forceinline__ int run_back(const uint8_t *b, int q, int s) {  // ru
     while (p >= s && b[p] == b[p - s]) p--;
     return q - p;
 }
-__device__ int tandem_repeat_length(const uint8_t *bases, int len, int offset) {
+__device__ __noinline__ int tandem_repeat_length(const uint8_t *bases, int len, int offset) {
     int max_bw = 0, bw_len = 1;
     for (int str = 1; str <= kMaxStrUnitLength; str++) {
         if (offset + 1 < str) break;
@@ -78,6 +78,70 @@ __device__ int tandem_repeat_length(const uint8_t *bases, int len, int offset) {
     return max_rl < kMaxRepeatLength ? max_rl : kMaxRepeatLength;
 }
 
+// The same search for a read staged in shared memory (slab laid out as kEnginePad guard bytes, the read, guard bytes;
+// `b` points at the read's first byte, 4-byte aligned).  A unit length s can only repeat at `offset` if the single byte
+// pair b[offset] == b[offset - s] (backward) / b[offset + 1] == b[offset + 1 + s] (forward) matches, so all 20 pairs of
+// a direction are compared at once -- six aligned LDS.32, five funnel shifts, a SWAR zero-byte test per word (exact for
+// any byte value) and a multiply that gathers the four flags of a word -- and only the lengths whose bit survives (5 of
+// 20 on random sequence) enter the run-length loop.  Guard bytes are never trusted: the validity masks cut the lengths
+// that would reach outside the read.  Byte-identical to tandem_repeat_length (tests/test_gpu_engine.py).
+constexpr int kEnginePad = 24;
+__device__ __forceinline__ uint32_t zero_byte_flags(uint32_t x) {  // bit 8b+7 set iff byte b of x is 0
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+template <bool BACKWARD>
+__device__ __forceinline__ uint32_t window_eq_mask(const uint8_t *b, int first, uint32_t c) {
+    // 20 bytes b[first .. first+19] against byte c.  BACKWARD: byte t -> bit 19 - t (s = 20 - t); else byte t -> bit t (s = t + 1)
+    const int p0 = first + kEnginePad;  // >= 4: index from the slab's (aligned) start
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(b - kEnginePad) + (p0 >> 2);
+    const uint32_t sh = (uint32_t)(p0 & 3) * 8u, splat = c * 0x01010101u;
+    uint32_t lo = w[0], mask = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const uint32_t hi = w[k + 1];
+        const uint32_t z = zero_byte_flags(__funnelshift_r(lo, hi, sh) ^ splat);
+        lo = hi;
+        if (BACKWARD) mask |= (__umulhi(z, 0x10080402u) & 0xfu) << (16 - 4 * k);  // flags -> bits 3,2,1,0 of the high word
+        else          mask |= (__umulhi(z, 0x02040810u) & 0xfu) << (4 * k);       // flags -> bits 0,1,2,3
+    }
+    return mask;
+}
+__device__ __forceinline__ int tandem_repeat_length_staged(const uint8_t *b, int len, int offset) {
+    int max_bw = 1, bw_len = 1;
+    uint32_t m = window_eq_mask<true>(b, offset - 20, b[offset]) & (offset >= 20 ? 0xfffffu : (1u << offset) - 1u);
+    while (m) {
+        const int s = __ffs(m);
+        m &= m - 1;
+        const int run = 1 + run_back(b, offset - 1, s);
+        if (run >= s) { max_bw = 1 + run / s; bw_len = s; break; }
+    }
+    int max_rl = max_bw;
+    if (offset < len - 1) {
+        int fw_len = 1, max_fw = 1;
+        const int room = len - 2 - offset;  // s <= room keeps b[offset + 1 + s] inside the read
+        m = window_eq_mask<false>(b, offset + 2, b[offset + 1]) & (room >= 20 ? 0xfffffu : (1u << room) - 1u);
+        while (m) {
+            const int s = __ffs(m);
+            m &= m - 1;
+            const int p0 = offset + 1 + s;
+            int p = p0 + 1;
+            while (p < len && b[p] == b[p - s]) p++;
+            if (p - p0 >= s) { max_fw = 1 + (p - p0) / s; fw_len = s; break; }
+        }
+        if (fw_len == bw_len && same_bytes(b + offset + 1, b + offset + 1 - bw_len, fw_len)) {
+            max_rl = max_bw + max_fw;
+        } else {
+            int before = 0;
+            if (offset + 1 >= fw_len) {
+                const int run = run_back(b, offset + fw_len, fw_len);
+                before = run >= fw_len ? run / fw_len : 0;
+            }
+            max_rl = max_fw + before;
+        }
+    }
+    return max_rl < kMaxRepeatLength ? max_rl : kMaxRepeatLength;
+}
+
 // ...engine.rs:23-39, (mean, variance) for baseQ 1..40
 __constant__ double kDynMean[40] = {
     5.996842844, 5.870018422, 5.401558531, 4.818940919, 4.218758304, 3.646319832, 3.122346753, 2.654731979, 2.244479156, 1.88893867,
@@ -99,7 +163,7 @@ __constant__ double kDynVar[40] = {
 // per-base search, which stops at the first mismatching byte: 3.6 ms against 2.0 ms per 2 000 regions.  Dropped.)
 constexpr int kEngineSlab = 1024;
 __global__ void __launch_bounds__(128) engine_modify_reads_kernel(EngineDevArgs E, int64_t n_reads) {
-    __shared__ uint8_t slab[4][kEngineSlab];
+    __shared__ __align__(16) uint8_t slab[4][kEnginePad + kEngineSlab + kEnginePad + 4];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -109,16 +173,17 @@ __global__ void __launch_bounds__(128) engine_modify_reads_kernel(EngineDevArgs 
         const int len = (int)(E.read_off[r + 1] - o);
         const uint8_t *bases = E.read_bases + o;
         const uint8_t mapq = E.cap_to_mapq ? E.read_mapq[r] : 255;
-        if (E.use_pcr && len <= kEngineSlab) {
+        const bool staged = E.use_pcr && len <= kEngineSlab;
+        if (staged) {
             __syncwarp();
-            for (int j = lane; j < len; j += 32) mine[j] = bases[j];
+            for (int j = lane; j < len; j += 32) mine[kEnginePad + j] = bases[j];
             __syncwarp();
-            bases = mine;
+            bases = mine + kEnginePad;
         }
         for (int j = lane; j < len; j += 32) {
             uint8_t q = E.read_qual[o + j], qi = E.read_ins[o + j], qd = E.read_del[o + j];
             if (E.use_pcr && j < len - 1) {  // apply_pcr_error_model writes i-1 for i in 1..len: the last base is never touched
-                const uint8_t c = E.pcr_cache[tandem_repeat_length(bases, len, j)];
+                const uint8_t c = E.pcr_cache[staged ? tandem_repeat_length_staged(bases, len, j) : tandem_repeat_length(bases, len, j)];
                 qi = qi < c ? qi : c;
                 qd = qd < c ? qd : c;
             }
