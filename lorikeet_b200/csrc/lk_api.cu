@@ -112,7 +112,7 @@ extern "C" void lk_destroy(lk_ctx *ctx) {
     cudaSetDevice(ctx->device);
     for (int i = 0; i < 3; i++)
         if (ctx->stream[i]) { cudaStreamSynchronize(ctx->stream[i]); cudaStreamDestroy(ctx->stream[i]); }
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < LK_PIPE_DEPTH; i++)
         if (ctx->ws[i]) { lk_resident_free(nullptr, ctx->ws[i]); ctx->ws[i] = nullptr; }
     ctx->d_qerr_f.release(); ctx->d_qerr_d.release(); ctx->d_m2m.release();
     delete ctx;
@@ -529,6 +529,8 @@ extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *
 lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags, const lk_engine_hook *hook) {
     if (!ctx) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
+    timespec ts_entry; clock_gettime(CLOCK_MONOTONIC, &ts_entry);
+    const double t_entry = ts_entry.tv_sec * 1e3 + ts_entry.tv_nsec * 1e-6;
     if (hook) { out = hook->values; flags = nullptr; }
     int64_t n_reads = 0, n_haps = 0;
     lk_status vs = validate_batch(ctx, batch, &n_reads, &n_haps);
@@ -541,29 +543,40 @@ lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
     const GcpMode gcp = resolve_gcp(batch, n_reads);
-    // chunk boundaries: ~equal pair counts; ~1M pairs per chunk up to 8 chunks, then chunks of <= 4M pairs so the two
-    // workspaces stay bounded however large the batch is
+    // chunk boundaries by pair count.  Steady state: ~1M pairs per chunk up to 8 chunks, then chunks of <= 4M pairs so the
+    // two workspaces stay bounded however large the batch is.  Nothing overlaps the first chunk's task building and H2D,
+    // so the batch opens with a ramp (128K pairs, then x3 per chunk): the GPU starts after ~0.4 ms instead of ~3 ms and
+    // each chunk's kernels still cover the staging of the next, larger one.
     int64_t n_chunks = std::min<int64_t>(8, std::max<int64_t>(1, n_pairs / (1 << 20)));
     n_chunks = std::max<int64_t>(n_chunks, (n_pairs + (4 << 20) - 1) / (4 << 20));
-    n_chunks = std::min<int64_t>(n_chunks, batch->n_regions);
+    const int64_t steady = (n_pairs + n_chunks - 1) / n_chunks;
+    std::vector<int64_t> target;  // cumulative pair counts at which a chunk closes
+    {
+        int64_t acc = 0, size = 128 << 10;
+        while (size < steady && acc + size < n_pairs) { acc += size; target.push_back(acc); size *= 3; }
+        const int64_t rest = n_pairs - acc, k = std::max<int64_t>(1, (rest + steady - 1) / steady);
+        for (int64_t i = 1; i < k; i++) target.push_back(acc + rest * i / k);
+    }
     std::vector<int64_t> cut(1, 0), pair_base(1, 0);
     {
-        int64_t acc = 0, next = 1;
+        int64_t acc = 0;
+        size_t next = 0;
         for (int64_t r = 0; r < batch->n_regions; r++) {
             acc += (batch->region_read_start[r + 1] - batch->region_read_start[r]) * (batch->region_hap_start[r + 1] - batch->region_hap_start[r]);
-            if (r + 1 == batch->n_regions || (next < n_chunks && acc >= n_pairs * next / n_chunks)) {
-                cut.push_back(r + 1); pair_base.push_back(acc); next++;
+            if (r + 1 == batch->n_regions || (next < target.size() && acc >= target[next])) {
+                cut.push_back(r + 1); pair_base.push_back(acc);
+                while (next < target.size() && acc >= target[next]) next++;
             }
         }
     }
     const int C = (int)cut.size() - 1;
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < LK_PIPE_DEPTH; i++)
         if (!ctx->ws[i]) { ctx->ws[i] = new (std::nothrow) lk_resident(); if (!ctx->ws[i]) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"); }
     lk_status st = LK_OK;
     int32_t launches = 0;
     auto collect = [&](int i) -> lk_status {  // D2H of chunk i (queued behind its kernels on the same stream)
-        lk_resident *R = ctx->ws[i & 1];
-        cudaStream_t s = ctx->stream[i & 1];
+        lk_resident *R = ctx->ws[i % LK_PIPE_DEPTH];
+        cudaStream_t s = ctx->stream[i % LK_PIPE_DEPTH];
         if (R->n_pairs == 0) return LK_OK;
         cudaError_t ce = cudaMemcpyAsync(out + pair_base[(size_t)i], hook ? R->values.p : R->out.p, (size_t)R->n_pairs * 8, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && hook && hook->keep && R->n_reads > 0)
@@ -576,8 +589,8 @@ lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_begin = now_ms();
     for (int i = 0; i < C && st == LK_OK; i++) {
-        lk_resident *R = ctx->ws[i & 1];
-        cudaStream_t s = ctx->stream[i & 1];
+        lk_resident *R = ctx->ws[i % LK_PIPE_DEPTH];
+        cudaStream_t s = ctx->stream[i % LK_PIPE_DEPTH];
         const double t0 = now_ms();
         st = stage_range(ctx, batch, cut[(size_t)i], cut[(size_t)i + 1], gcp, R, s, hook);
         const double t1 = now_ms();
@@ -588,10 +601,12 @@ lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double
         if (trace) fprintf(stderr, "[lk] chunk %d/%d: stage %.2f ms, enqueue %.2f ms, collect %.2f ms (t=%.2f)\n", i, C, t1 - t0, t2 - t1, now_ms() - t2, now_ms() - t_begin);
     }
     if (st == LK_OK) st = collect(C - 1);
-    for (int i = 0; i < 2; i++) {
+    if (trace) fprintf(stderr, "[lk] all %d chunks queued (t=%.2f)\n", C, now_ms() - t_begin);
+    for (int i = 0; i < LK_PIPE_DEPTH; i++) {
         e = cudaStreamSynchronize(ctx->stream[i]);
         if (e != cudaSuccess && st == LK_OK) st = lk_cuda_fail(ctx, e, "pairhmm pipeline");
     }
+    if (trace) fprintf(stderr, "[lk] drained (t=%.2f; entry -> first chunk %.2f ms)\n", now_ms() - t_begin, t_begin - t_entry);
     ctx->last_launch_count = launches;
     return st;
 }

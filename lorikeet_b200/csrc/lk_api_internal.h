@@ -25,6 +25,7 @@ struct PinnedBuf {
 };
 
 struct lk_resident;
+constexpr int LK_PIPE_DEPTH = 3;  // == number of streams in lk_ctx
 
 struct lk_ctx {
     int device = 0;
@@ -37,7 +38,10 @@ struct lk_ctx {
     int force_k = 0;
     int32_t last_launch_count = 0;
     DevBuf d_qerr_f, d_qerr_d, d_m2m;
-    lk_resident *ws[2] = { nullptr, nullptr };  // reusable workspaces of lk_pairhmm_batch_host's chunk pipeline
+    // reusable workspaces of lk_pairhmm_batch_host's chunk pipeline, one per stream.  Three, not two: chunk i+2's H2D then
+    // waits on chunk i-1 (long finished) instead of chunk i, whose small f64 pass can be held back behind chunk i+1's
+    // main kernel and would otherwise delay the copy, and with it chunk i+2's kernels, past the end of chunk i+1.
+    lk_resident *ws[3] = { nullptr, nullptr, nullptr };
 };
 
 struct lk_resident {

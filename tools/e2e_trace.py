@@ -13,3 +13,13 @@ with lk.Context(0) as ctx:
         t = time.perf_counter(); ctx.pairhmm_batch(pb, out=out, flags=fl); print("e2e %.1f ms" % ((time.perf_counter() - t) * 1e3), flush=True)
     os.environ["LK_TRACE"] = "1"
     t = time.perf_counter(); ctx.pairhmm_batch(pb, out=out, flags=fl); print("e2e traced %.1f ms" % ((time.perf_counter() - t) * 1e3), flush=True)
+    # the region driver (bench.py's e2e path) on the same pinned batch
+    from lorikeet_b200.engine import PairHMMLikelihoodCalculationEngine
+    del os.environ["LK_TRACE"]
+    eng = PairHMMLikelihoodCalculationEngine(ctx)
+    mapq = pin(np.full(b.n_reads, 60, np.uint8)).numpy()
+    keepm = torch.empty(b.n_reads, dtype=torch.uint8).pin_memory().numpy()
+    for i in range(3):
+        t = time.perf_counter(); eng.compute_read_likelihoods(pb, mapq, values=out, keep=keepm); print("engine e2e %.1f ms" % ((time.perf_counter() - t) * 1e3), flush=True)
+    os.environ["LK_TRACE"] = "1"
+    t = time.perf_counter(); eng.compute_read_likelihoods(pb, mapq, values=out, keep=keepm); print("engine e2e traced %.1f ms" % ((time.perf_counter() - t) * 1e3), flush=True)
