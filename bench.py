@@ -122,7 +122,23 @@ def run_extras(ctx):
         ms = min(res.run() for _ in range(3))
         out["cfg4_smith_waterman"] = {"pairs": 100000, "cells": res.n_cells, "ms": ms, "gcups": res.n_cells / ms / 1e6,
                                       "note": "fill + in-kernel traceback, CIGARs bit-exact vs oracle (tests/test_gpu_sw.py)"}
+        n_cells = res.n_cells
         res.free()
+        # the same batch end to end through lk_sw_batch_host: pinned host buffers in, CIGARs + offsets in pinned host buffers out
+        import numpy as np
+        import torch
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        pro, prefs, pao, palts = pin(ro), pin(refs), pin(ao), pin(alts)
+        outs = (torch.empty((100000, 64), dtype=torch.int32).pin_memory().numpy().view(np.uint32),
+                torch.empty(100000, dtype=torch.int32).pin_memory().numpy(), torch.empty(100000, dtype=torch.int32).pin_memory().numpy())
+        ctx.sw_batch(pro, prefs, pao, palts, [200, -150, -260, -11], "SoftClip", max_ops=64, out=outs)
+        best = 1e30
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ctx.sw_batch(pro, prefs, pao, palts, [200, -150, -260, -11], "SoftClip", max_ops=64, out=outs)
+            best = min(best, time.perf_counter() - t0)
+        out["cfg4_smith_waterman"]["e2e"] = {"ms": best * 1e3, "gcups": n_cells / best / 1e9,
+                                             "api": "lk_sw_batch_host (the gkl::smithwaterman::align seam, batched), pinned host buffers"}
         b = synth.pairhmm_regions(111, **synth.CFG3)  # cfg3 slice: 111 of 2000 regions (8 reads x 10 kbp, 4 haps x 12 kbp);
         # 111 x 32 pairs = 2 full waves of the band kernel's 1776 resident warps, as the 36-wave full config is
         res = ctx.pairhmm_upload(b)

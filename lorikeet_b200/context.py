@@ -138,16 +138,22 @@ class Context:
         return ResidentPairHmm(self, batch)
 
     # ---------------------------------------------------------------- Smith-Waterman
-    def sw_batch(self, ref_off, refs, alt_off, alts, params, strategy, max_ops=64):
+    def sw_batch(self, ref_off, refs, alt_off, alts, params, strategy, max_ops=64, out=None):
+        """lk_sw_batch_host; out = (ops[n, max_ops] u32, n_ops[n] i32, offsets[n] i32) to reuse (e.g. pinned) buffers."""
         from .batch import _u8, _i64
         ref_off, alt_off, refs, alts = _i64(ref_off), _i64(alt_off), _u8(refs), _u8(alts)
         n = len(ref_off) - 1
         if isinstance(strategy, str):
             strategy = SW_STRATEGY[strategy]
         prm = _lib.SwParams(*[int(x) for x in params])
-        ops = np.zeros((n, max_ops), dtype=np.uint32)
-        n_ops = np.zeros(n, dtype=np.int32)
-        offs = np.zeros(n, dtype=np.int32)
+        if out is not None:
+            ops, n_ops, offs = out
+            assert ops.dtype == np.uint32 and ops.shape == (n, max_ops) and ops.flags.c_contiguous
+            assert n_ops.dtype == np.int32 and n_ops.size == n and offs.dtype == np.int32 and offs.size == n
+        else:
+            ops = np.zeros((n, max_ops), dtype=np.uint32)
+            n_ops = np.zeros(n, dtype=np.int32)
+            offs = np.zeros(n, dtype=np.int32)
         self._check(self._L.lk_sw_batch_host(self._h, n, ref_off.ctypes.data_as(_lib.i64p), refs.ctypes.data_as(_lib.u8p),
                                              alt_off.ctypes.data_as(_lib.i64p), alts.ctypes.data_as(_lib.u8p),
                                              C.byref(prm), int(strategy), int(max_ops), ops.ctypes.data_as(_lib.u32p),

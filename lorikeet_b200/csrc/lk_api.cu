@@ -114,6 +114,8 @@ extern "C" void lk_destroy(lk_ctx *ctx) {
         if (ctx->stream[i]) { cudaStreamSynchronize(ctx->stream[i]); cudaStreamDestroy(ctx->stream[i]); }
     for (int i = 0; i < LK_PIPE_DEPTH; i++)
         if (ctx->ws[i]) { lk_resident_free(nullptr, ctx->ws[i]); ctx->ws[i] = nullptr; }
+    for (int i = 0; i < LK_PIPE_DEPTH; i++)
+        if (ctx->sw_ws[i]) { lk_resident_free(nullptr, ctx->sw_ws[i]); ctx->sw_ws[i] = nullptr; }
     ctx->d_qerr_f.release(); ctx->d_qerr_d.release(); ctx->d_m2m.release();
     delete ctx;
 }

@@ -42,6 +42,7 @@ struct lk_ctx {
     // waits on chunk i-1 (long finished) instead of chunk i, whose small f64 pass can be held back behind chunk i+1's
     // main kernel and would otherwise delay the copy, and with it chunk i+2's kernels, past the end of chunk i+1.
     lk_resident *ws[3] = { nullptr, nullptr, nullptr };
+    lk_resident *sw_ws[3] = { nullptr, nullptr, nullptr };  // same for lk_sw_batch_host
 };
 
 struct lk_resident {
@@ -80,6 +81,8 @@ struct lk_resident {
     int64_t sw_n_pairs = 0, sw_cells = 0;
     int32_t sw_max_ops = 0, sw_strategy = 0;
     lk_sw_params sw_params = { 0, 0, 0, 0 };
+    int64_t sw_ref_byte0 = 0, sw_alt_byte0 = 0;  // first arena bytes staged: device base pointers are biased by these
+    std::vector<int32_t> sw_order_host;          // lives with the workspace so the queued H2D copy has a stable source
     DevBuf sw_refs, sw_alts, sw_ref_off, sw_alt_off, sw_bt, sw_bt_off, sw_ops, sw_nops, sw_offsets, sw_order;
 };
 

@@ -37,83 +37,120 @@ cudaError_t up(DevBuf &b, const T *src, size_t n, cudaStream_t st) {
     return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
 }
 
-lk_status sw_upload_locked(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
-                           const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
-                           lk_sw_overhang strategy, int32_t max_ops, lk_resident **out_res) {
+// Stage pairs [p0, p1) of the caller's arrays into workspace R on stream st: classify by K, order each class longest
+// first, queue the H2D copies.  Asynchronous (no stream sync); R may be a reused workspace whose earlier work on st
+// has completed.  Pair indices inside R are relative to p0; the byte arenas keep the caller's absolute offsets and
+// the device base pointers are biased instead (sw_fill_args).
+lk_status sw_stage_range(lk_ctx *ctx, lk_resident *R, int64_t p0, int64_t p1, const int64_t *ref_off, const uint8_t *refs,
+                         const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params, lk_sw_overhang strategy,
+                         int32_t max_ops, cudaStream_t st) {
+    const int64_t n_pairs = p1 - p0;
+    R->kind = 1;
+    R->sw_n_pairs = n_pairs; R->sw_max_ops = max_ops; R->sw_strategy = (int32_t)strategy; R->sw_params = *params;
+    R->sw_launches.clear();
+    R->sw_ref_byte0 = n_pairs ? ref_off[p0] : 0;
+    R->sw_alt_byte0 = n_pairs ? alt_off[p0] : 0;
+    // one pass: K class, cell count and scratch need of every pair
+    std::vector<int32_t> &order = R->sw_order_host;
+    order.resize((size_t)n_pairs);
+    std::vector<uint8_t> cls((size_t)n_pairs);
+    std::vector<int64_t> cells((size_t)n_pairs);
+    int64_t max_words = 64, nm_max[kNumSwKs], cells_max[kNumSwKs], count[kNumSwKs];
+    for (int ki = 0; ki < kNumSwKs; ki++) { nm_max[ki] = 0; cells_max[ki] = 1; count[ki] = 0; }
+    R->sw_cells = 0;
+    for (int64_t i = 0; i < n_pairs; i++) {
+        const int64_t p = p0 + i;
+        const int n = (int)(ref_off[p + 1] - ref_off[p]), m = (int)(alt_off[p + 1] - alt_off[p]);
+        const int K = sw_choose_k(n);
+        int ki = 0;
+        while (kSwKs[ki] != K) ki++;
+        cls[(size_t)i] = (uint8_t)ki;
+        cells[(size_t)i] = (int64_t)n * m;
+        R->sw_cells += cells[(size_t)i];
+        count[ki]++;
+        nm_max[ki] = std::max<int64_t>(nm_max[ki], (int64_t)n + m);
+        cells_max[ki] = std::max(cells_max[ki], cells[(size_t)i]);
+        if (n > 0 && m > 0) max_words = std::max(max_words, sw_scratch_words(n, m, K));
+    }
+    // order array: one contiguous run per K class, longest pairs first inside a class (better tail balance of the
+    // persistent grid).  A counting sort over 256 size buckets: the order only has to be roughly descending.
+    {
+        constexpr int NB = 256;
+        std::vector<int32_t> slot((size_t)kNumSwKs * NB + 1, 0);
+        auto bucket = [&](int64_t i) {
+            const int ki = cls[(size_t)i];
+            return ki * NB + (NB - 1 - (int)(cells[(size_t)i] * (NB - 1) / cells_max[ki]));
+        };
+        for (int64_t i = 0; i < n_pairs; i++) slot[(size_t)bucket(i) + 1]++;
+        for (size_t k = 1; k < slot.size(); k++) slot[k] += slot[k - 1];
+        for (int64_t i = 0; i < n_pairs; i++) order[(size_t)slot[(size_t)bucket(i)]++] = (int32_t)i;
+        int32_t first = 0;
+        for (int ki = 0; ki < kNumSwKs; ki++) {
+            if (count[ki] > 0)
+                R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)count[ki],
+                        !sw_clamp_inactive(nm_max[ki], params->match_value, params->mismatch_penalty, params->gap_open_penalty, params->gap_extend_penalty) });
+            first += (int32_t)count[ki];
+        }
+    }
+    // persistent grid: up to 16 warps per SM, fewer if the per-warp backtrack scratch would exceed ~12 GB
+    const int warps_per_block = LK_SW_THREADS / 32;
+    int64_t warps = (int64_t)ctx->n_sm * 16;
+    const int64_t budget_words = (12LL << 30) / 4;
+    max_words = (max_words + 3) & ~(int64_t)3;  // uint4 plane stores need 16-byte aligned per-warp slices
+    warps = std::max<int64_t>(warps_per_block, std::min(warps, budget_words / max_words));
+    warps = std::min<int64_t>(warps, std::max<int64_t>(warps_per_block, ((n_pairs + warps_per_block - 1) / warps_per_block) * warps_per_block));
+    R->sw_blocks = (int)(warps / warps_per_block);
+    R->sw_scratch_words = max_words;
+    const int64_t ref_bytes = n_pairs ? ref_off[p1] - R->sw_ref_byte0 : 0, alt_bytes = n_pairs ? alt_off[p1] - R->sw_alt_byte0 : 0;
+    cudaError_t e;
+    bool ok = (e = up(R->sw_refs, refs + R->sw_ref_byte0, (size_t)ref_bytes, st)) == cudaSuccess &&
+              (e = up(R->sw_alts, alts + R->sw_alt_byte0, (size_t)alt_bytes, st)) == cudaSuccess &&
+              (e = up(R->sw_ref_off, ref_off + p0, (size_t)n_pairs + 1, st)) == cudaSuccess &&
+              (e = up(R->sw_alt_off, alt_off + p0, (size_t)n_pairs + 1, st)) == cudaSuccess &&
+              (e = up(R->sw_order, order.data(), order.size(), st)) == cudaSuccess &&
+              (e = R->sw_ops.reserve((size_t)std::max<int64_t>(n_pairs * max_ops * 4, 16))) == cudaSuccess &&
+              (e = R->sw_nops.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
+              (e = R->sw_offsets.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
+              (e = R->counters.reserve(64)) == cudaSuccess &&
+              (e = R->sw_bt.reserve((size_t)((int64_t)R->sw_blocks * warps_per_block * max_words * 4))) == cudaSuccess;
+    if (!ok) return lk_cuda_fail(ctx, e, "SW upload");
+    return LK_OK;
+}
+
+lk_status sw_validate(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs, const int64_t *alt_off,
+                      const uint8_t *alts, const lk_sw_params *params, lk_sw_overhang strategy, int32_t max_ops) {
     if (n_pairs < 0 || !params || max_ops < 1) return lk_fail(ctx, LK_ERR_INVALID, "bad SW arguments");
     if ((int)strategy < 0 || (int)strategy > 3) return lk_fail(ctx, LK_ERR_INVALID, "bad overhang strategy");
     if (n_pairs > 0 && (!ref_off || !refs || !alt_off || !alts)) return lk_fail(ctx, LK_ERR_INVALID, "null SW arrays");
     if (n_pairs > 0x7fffffffLL / std::max(1, max_ops)) return lk_fail(ctx, LK_ERR_INVALID, "SW batch too large");
     for (int64_t p = 0; p < n_pairs; p++)
         if (ref_off[p + 1] < ref_off[p] || alt_off[p + 1] < alt_off[p]) return lk_fail(ctx, LK_ERR_INVALID, "decreasing SW offsets");
+    return LK_OK;
+}
+
+lk_status sw_upload_locked(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                           const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                           lk_sw_overhang strategy, int32_t max_ops, lk_resident **out_res) {
+    lk_status vs = sw_validate(ctx, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops);
+    if (vs != LK_OK) return vs;
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
     lk_resident *R = new (std::nothrow) lk_resident();
     if (!R) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
-    R->kind = 1;
-    R->sw_n_pairs = n_pairs; R->sw_max_ops = max_ops; R->sw_strategy = (int32_t)strategy; R->sw_params = *params;
-    // order arrays: one contiguous run per K class, longest pairs first inside a class (better tail balance)
-    std::vector<int32_t> order;
-    order.reserve((size_t)n_pairs);
-    int64_t max_words = 64;
-    R->sw_cells = 0;
-    for (int ki = 0; ki < kNumSwKs; ki++) {
-        const int K = kSwKs[ki];
-        const size_t first = order.size();
-        int64_t nm_max = 0;
-        for (int64_t p = 0; p < n_pairs; p++) {
-            const int n = (int)(ref_off[p + 1] - ref_off[p]), m = (int)(alt_off[p + 1] - alt_off[p]);
-            if (sw_choose_k(n) != K) continue;
-            order.push_back((int32_t)p);
-            nm_max = std::max<int64_t>(nm_max, (int64_t)n + m);
-            if (n > 0 && m > 0) max_words = std::max(max_words, sw_scratch_words(n, m, K));
-        }
-        std::stable_sort(order.begin() + (long)first, order.end(), [&](int32_t a, int32_t b) {
-            return (ref_off[a + 1] - ref_off[a]) * (alt_off[a + 1] - alt_off[a]) > (ref_off[b + 1] - ref_off[b]) * (alt_off[b + 1] - alt_off[b]);
-        });
-        if (order.size() > first) R->sw_launches.push_back(lk_resident::SwLaunch{ K, (int32_t)first, (int32_t)(order.size() - first),
-                !sw_clamp_inactive(nm_max, params->match_value, params->mismatch_penalty, params->gap_open_penalty, params->gap_extend_penalty) });
-    }
-    for (int64_t p = 0; p < n_pairs; p++) R->sw_cells += (ref_off[p + 1] - ref_off[p]) * (alt_off[p + 1] - alt_off[p]);
-    // persistent grid: up to 16 warps per SM, fewer if the per-warp backtrack scratch would exceed ~12 GB
-    const int warps_per_block = LK_SW_THREADS / 32;
-    int64_t warps = (int64_t)ctx->n_sm * 16;
-    const int64_t budget_words = (12LL << 30) / 4;
-    max_words = (max_words + 3) & ~(int64_t)3;
-    warps = std::max<int64_t>(warps_per_block, std::min(warps, budget_words / max_words));
-    warps = std::min<int64_t>(warps, std::max<int64_t>(warps_per_block, ((n_pairs + warps_per_block - 1) / warps_per_block) * warps_per_block));
-    R->sw_blocks = (int)(warps / warps_per_block);
-    max_words = (max_words + 3) & ~(int64_t)3;  // uint4 plane stores need 16-byte aligned per-warp slices
-    R->sw_scratch_words = max_words;
-    cudaStream_t st = ctx->stream[0];
-    const int64_t ref_bytes = n_pairs ? ref_off[n_pairs] : 0, alt_bytes = n_pairs ? alt_off[n_pairs] : 0;
-    bool ok = (e = up(R->sw_refs, refs, (size_t)ref_bytes, st)) == cudaSuccess &&
-              (e = up(R->sw_alts, alts, (size_t)alt_bytes, st)) == cudaSuccess &&
-              (e = up(R->sw_ref_off, ref_off, (size_t)n_pairs + 1, st)) == cudaSuccess &&
-              (e = up(R->sw_alt_off, alt_off, (size_t)n_pairs + 1, st)) == cudaSuccess &&
-              (e = up(R->sw_order, order.data(), order.size(), st)) == cudaSuccess &&
-              (e = R->sw_ops.reserve((size_t)std::max<int64_t>(n_pairs * max_ops * 4, 16))) == cudaSuccess &&
-              (e = R->sw_nops.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
-              (e = R->sw_offsets.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
-              (e = R->counters.reserve(64)) == cudaSuccess &&
-              (e = R->sw_bt.reserve((size_t)((int64_t)R->sw_blocks * warps_per_block * max_words * 4))) == cudaSuccess &&
-              (e = cudaStreamSynchronize(st)) == cudaSuccess;
-    if (!ok) { lk_resident_free(ctx, R); return lk_cuda_fail(ctx, e, "SW upload"); }
+    lk_status st = sw_stage_range(ctx, R, 0, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops, ctx->stream[0]);
+    if (st == LK_OK && (e = cudaStreamSynchronize(ctx->stream[0])) != cudaSuccess) st = lk_cuda_fail(ctx, e, "SW upload");
+    if (st != LK_OK) { lk_resident_free(ctx, R); return st; }
     *out_res = R;
     return LK_OK;
 }
 
-lk_status sw_run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
-    if (!R || R->kind != 1) return lk_fail(ctx, LK_ERR_INVALID, "not a Smith-Waterman resident batch");
-    cudaError_t e = cudaSetDevice(ctx->device);
-    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
-    cudaStream_t st = ctx->stream[0];
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (kernel_ms) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+// queue R's kernels on st (one launch per K class); no sync
+lk_status sw_enqueue(lk_ctx *ctx, lk_resident *R, cudaStream_t st) {
+    cudaError_t e;
     R->launch_count = 0;
     SwArgs A;
     memset(&A, 0, sizeof A);
-    A.refs = (const uint8_t *)R->sw_refs.p; A.alts = (const uint8_t *)R->sw_alts.p;
+    A.refs = (const uint8_t *)R->sw_refs.p - R->sw_ref_byte0; A.alts = (const uint8_t *)R->sw_alts.p - R->sw_alt_byte0;
     A.ref_off = (const int64_t *)R->sw_ref_off.p; A.alt_off = (const int64_t *)R->sw_alt_off.p;
     A.w_match = R->sw_params.match_value; A.w_mismatch = R->sw_params.mismatch_penalty;
     A.w_open = R->sw_params.gap_open_penalty; A.w_extend = R->sw_params.gap_extend_penalty;
@@ -129,12 +166,24 @@ lk_status sw_run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
         if ((e = launch_sw(L.K, L.clamp, A, R->sw_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
         R->launch_count++;
     }
+    return LK_OK;
+}
+
+lk_status sw_run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
+    if (!R || R->kind != 1) return lk_fail(ctx, LK_ERR_INVALID, "not a Smith-Waterman resident batch");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    cudaStream_t st = ctx->stream[0];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (kernel_ms) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, st); }
+    lk_status rs = sw_enqueue(ctx, R, st);
     if (kernel_ms) cudaEventRecord(ev1, st);
     e = cudaStreamSynchronize(st);
     if (kernel_ms) {
         if (e == cudaSuccess) cudaEventElapsedTime(kernel_ms, ev0, ev1);
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     }
+    if (rs != LK_OK) return rs;
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "sw kernels");
     return LK_OK;
 }
@@ -176,19 +225,64 @@ extern "C" lk_status lk_sw_download(lk_ctx *ctx, lk_resident *res, uint32_t *cig
     return sw_download_locked(ctx, res, cigar_ops, n_ops, offsets);
 }
 
+// Host-buffer entry point.  Pairs are cut into chunks of contiguous pair ranges (by cell count, with a short first
+// chunk so the GPU starts early) that flow through LK_PIPE_DEPTH context-owned, grow-only workspaces on as many
+// streams: host-side ordering and H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i, and no
+// device memory is allocated or freed per call once the workspaces have grown to the batch shape.
 extern "C" lk_status lk_sw_batch_host(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
                                       const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
                                       lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops,
                                       int32_t *alignment_offset) {
     if (!ctx) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
-    lk_resident *R = nullptr;
-    lk_status st = sw_upload_locked(ctx, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops, &R);
+    lk_status st = sw_validate(ctx, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops);
     if (st != LK_OK) return st;
-    st = sw_run_locked(ctx, R, nullptr);
-    if (st == LK_OK) st = sw_download_locked(ctx, R, cigar_ops, n_ops, alignment_offset);
-    ctx->last_launch_count = R->launch_count;
-    lk_resident_free(ctx, R);
+    ctx->last_launch_count = 0;
+    if (n_pairs == 0) return LK_OK;
+    if (!cigar_ops || !n_ops || !alignment_offset) return lk_fail(ctx, LK_ERR_INVALID, "null SW outputs");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    // chunk boundaries by cells: ramp 1e9, 3e9, ... up to the steady size max(total / 8, 5e9)
+    std::vector<int64_t> cut(1, 0);
+    {
+        double total = 0;
+        for (int64_t p = 0; p < n_pairs; p++) total += (double)(ref_off[p + 1] - ref_off[p]) * (double)(alt_off[p + 1] - alt_off[p]);
+        const double steady = std::max(total / 8.0, 5e9);
+        double size = 1e9, acc = 0, next = size;
+        for (int64_t p = 0; p < n_pairs; p++) {
+            acc += (double)(ref_off[p + 1] - ref_off[p]) * (double)(alt_off[p + 1] - alt_off[p]);
+            if (p + 1 == n_pairs) break;
+            if (acc >= next && total - acc > 0.5 * size) {
+                cut.push_back(p + 1);
+                size = std::min(size * 3.0, steady);
+                next = acc + size;
+            }
+        }
+        cut.push_back(n_pairs);
+    }
+    const int C = (int)cut.size() - 1;
+    int32_t launches = 0;
+    for (int i = 0; i < C && st == LK_OK; i++) {
+        const int w = i % LK_PIPE_DEPTH;
+        if (!ctx->sw_ws[w]) { ctx->sw_ws[w] = new (std::nothrow) lk_resident(); if (!ctx->sw_ws[w]) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"); }
+        lk_resident *R = ctx->sw_ws[w];
+        cudaStream_t s = ctx->stream[w];
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) { st = lk_cuda_fail(ctx, e, "SW pipeline"); break; }  // chunk i-3 done: R is free
+        const int64_t p0 = cut[(size_t)i], p1 = cut[(size_t)i + 1];
+        st = sw_stage_range(ctx, R, p0, p1, ref_off, refs, alt_off, alts, params, strategy, max_ops, s);
+        if (st == LK_OK) st = sw_enqueue(ctx, R, s);
+        if (st != LK_OK) break;
+        launches += R->launch_count;
+        e = cudaMemcpyAsync(cigar_ops + p0 * max_ops, R->sw_ops.p, (size_t)(p1 - p0) * max_ops * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(n_ops + p0, R->sw_nops.p, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(alignment_offset + p0, R->sw_offsets.p, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) st = lk_cuda_fail(ctx, e, "SW download");
+    }
+    for (int i = 0; i < LK_PIPE_DEPTH; i++) {
+        e = cudaStreamSynchronize(ctx->stream[i]);
+        if (e != cudaSuccess && st == LK_OK) st = lk_cuda_fail(ctx, e, "SW pipeline");
+    }
+    ctx->last_launch_count = launches;
     return st;
 }
 

@@ -18,7 +18,9 @@ with lk.Context(0) as ctx:
             res.run()
         ms = min(res.run() for _ in range(5))
         print("SW %s pairs=%d cells=%.3e best_ms=%.3f GCUPS=%.1f" % (strategy, n, res.n_cells, ms, res.n_cells / ms / 1e6), flush=True)
-        t = time.time()
-        ctx.sw_batch(ro, refs, ao, alts, [200, -150, -260, -11], strategy, max_ops=64)
-        print("   e2e host call %.1f ms" % ((time.time() - t) * 1e3))
+        outs = (np.zeros((n, 64), np.uint32), np.zeros(n, np.int32), np.zeros(n, np.int32))
+        for _ in range(3):
+            t = time.time()
+            ctx.sw_batch(ro, refs, ao, alts, [200, -150, -260, -11], strategy, max_ops=64, out=outs)
+            print("   e2e host call (pageable buffers) %.1f ms" % ((time.time() - t) * 1e3))
         res.free()
