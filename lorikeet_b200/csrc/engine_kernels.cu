@@ -109,6 +109,8 @@ __device__ __forceinline__ uint32_t window_eq_mask(const uint8_t *b, int first, 
 __device__ __forceinline__ int tandem_repeat_length_staged(const uint8_t *b, int len, int offset) {
     int max_bw = 1, bw_len = 1;
     uint32_t m = window_eq_mask<true>(b, offset - 20, b[offset]) & (offset >= 20 ? 0xfffffu : (1u << offset) - 1u);
+    // a unit of length >= 2 needs the neighbouring byte pair to match as well: second screen, same window one byte down
+    if (m & ~1u) m &= window_eq_mask<true>(b, offset - 21, b[offset - 1]) & (offset >= 21 ? 0xfffffu : (1u << (offset - 1)) - 1u) | 1u;
     while (m) {
         const int s = __ffs(m);
         m &= m - 1;
@@ -120,6 +122,7 @@ __device__ __forceinline__ int tandem_repeat_length_staged(const uint8_t *b, int
         int fw_len = 1, max_fw = 1;
         const int room = len - 2 - offset;  // s <= room keeps b[offset + 1 + s] inside the read
         m = window_eq_mask<false>(b, offset + 2, b[offset + 1]) & (room >= 20 ? 0xfffffu : (1u << room) - 1u);
+        if (m & ~1u) m &= window_eq_mask<false>(b, offset + 3, b[offset + 2]) & (room >= 21 ? 0xfffffu : (1u << (room - 1)) - 1u) | 1u;
         while (m) {
             const int s = __ffs(m);
             m &= m - 1;
@@ -163,7 +166,7 @@ __constant__ double kDynVar[40] = {
 // per-base search, which stops at the first mismatching byte: 3.6 ms against 2.0 ms per 2 000 regions.  Dropped.)
 constexpr int kEngineSlab = 1024;
 __global__ void __launch_bounds__(128) engine_modify_reads_kernel(EngineDevArgs E, int64_t n_reads) {
-    __shared__ __align__(16) uint8_t slab[4][kEnginePad + kEngineSlab + kEnginePad + 4];
+    __shared__ __align__(16) uint8_t slab[4][kEnginePad + kEngineSlab + kEnginePad + 8];
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
