@@ -11,11 +11,15 @@
 // ONE lk_sw batch; what remains here is O(n+m) CIGAR surgery per pair, kept on the host like the reference.
 // CIGAR elements are BAM-encoded u32 (len << 4 | op; M=0 I=1 D=2 N=3 S=4 H=5 P=6 '='=7 X=8).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <vector>
 
 #include "../../include/lorikeet_b200.h"
+#include "host_parallel.h"
 #include "lk_api_internal.h"
 
 namespace {
@@ -307,42 +311,58 @@ extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, cons
     if (n_pairs < 0 || !params || max_ops < 1) return lk_fail(ctx, LK_ERR_INVALID, "bad calculate_cigar arguments");
     if (n_pairs == 0) return LK_OK;
     if (!ref_off || !alt_off || !cigar_ops || !n_ops) return lk_fail(ctx, LK_ERR_INVALID, "null calculate_cigar arrays");
+    for (int64_t p = 0; p < n_pairs; p++)
+        if (ref_off[p + 1] < ref_off[p] || alt_off[p + 1] < alt_off[p]) return lk_fail(ctx, LK_ERR_INVALID, "decreasing offsets");
+    // the per-pair host work (shortcuts, padding, CIGAR surgery) is spread over the host cores for large batches
+    constexpr int64_t kGrain = 2048;
+    std::vector<uint8_t> need((size_t)n_pairs, 0);
+    lk::parallel_for(n_pairs, kGrain, [&](int64_t p_begin, int64_t p_end) {
+        for (int64_t p = p_begin; p < p_end; p++)
+            need[(size_t)p] = !lk_calculate_cigar_shortcut(refs + ref_off[p], ref_off[p + 1] - ref_off[p], alts + alt_off[p],
+                                                           alt_off[p + 1] - alt_off[p], max_ops, cigar_ops + p * max_ops, &n_ops[p]);
+    });
     std::vector<int64_t> todo;
-    for (int64_t p = 0; p < n_pairs; p++) {
-        const int64_t rl = ref_off[p + 1] - ref_off[p], al = alt_off[p + 1] - alt_off[p];
-        if (rl < 0 || al < 0) return lk_fail(ctx, LK_ERR_INVALID, "decreasing offsets");
-        if (!lk_calculate_cigar_shortcut(refs + ref_off[p], rl, alts + alt_off[p], al, max_ops, cigar_ops + p * max_ops, &n_ops[p]))
-            todo.push_back(p);
-    }
+    for (int64_t p = 0; p < n_pairs; p++)
+        if (need[(size_t)p]) todo.push_back(p);
     if (todo.empty()) return LK_OK;
     // padded copies (cigar_utils.rs:387-398)
-    std::vector<int64_t> pro(todo.size() + 1, 0), pao(todo.size() + 1, 0);
-    for (size_t i = 0; i < todo.size(); i++) {
-        const int64_t p = todo[i];
-        pro[i + 1] = pro[i] + (ref_off[p + 1] - ref_off[p]) + 2 * kSwPad;
-        pao[i + 1] = pao[i] + (alt_off[p + 1] - alt_off[p]) + 2 * kSwPad;
+    const int64_t T = (int64_t)todo.size();
+    std::vector<int64_t> pro((size_t)T + 1, 0), pao((size_t)T + 1, 0);
+    for (int64_t i = 0; i < T; i++) {
+        const int64_t p = todo[(size_t)i];
+        pro[(size_t)i + 1] = pro[(size_t)i] + (ref_off[p + 1] - ref_off[p]) + 2 * kSwPad;
+        pao[(size_t)i + 1] = pao[(size_t)i] + (alt_off[p + 1] - alt_off[p]) + 2 * kSwPad;
     }
-    std::vector<uint8_t> prefs((size_t)pro.back(), 'N'), palts((size_t)pao.back(), 'N');
-    int64_t sw_max_ops = 8;
-    for (size_t i = 0; i < todo.size(); i++) {
-        const int64_t p = todo[i];
-        memcpy(prefs.data() + pro[i] + kSwPad, refs + ref_off[p], (size_t)(ref_off[p + 1] - ref_off[p]));
-        memcpy(palts.data() + pao[i] + kSwPad, alts + alt_off[p], (size_t)(alt_off[p + 1] - alt_off[p]));
-        sw_max_ops = std::max<int64_t>(sw_max_ops, max_ops + 8);
-    }
-    std::vector<uint32_t> sw_ops(todo.size() * (size_t)sw_max_ops);
-    std::vector<int32_t> sw_n(todo.size()), sw_off(todo.size());
-    lk_status st = lk_sw_batch_host(ctx, (int64_t)todo.size(), pro.data(), prefs.data(), pao.data(), palts.data(), params, strategy,
-                                    (int32_t)sw_max_ops, sw_ops.data(), sw_n.data(), sw_off.data());
+    std::unique_ptr<uint8_t[]> prefs(new (std::nothrow) uint8_t[(size_t)pro.back()]), palts(new (std::nothrow) uint8_t[(size_t)pao.back()]);
+    if (!prefs || !palts) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    lk::parallel_for(T, kGrain, [&](int64_t i_begin, int64_t i_end) {
+        for (int64_t i = i_begin; i < i_end; i++) {
+            const int64_t p = todo[(size_t)i];
+            const int64_t rl = ref_off[p + 1] - ref_off[p], al = alt_off[p + 1] - alt_off[p];
+            uint8_t *r = prefs.get() + pro[(size_t)i], *a = palts.get() + pao[(size_t)i];
+            memset(r, 'N', (size_t)kSwPad); memcpy(r + kSwPad, refs + ref_off[p], (size_t)rl); memset(r + kSwPad + rl, 'N', (size_t)kSwPad);
+            memset(a, 'N', (size_t)kSwPad); memcpy(a + kSwPad, alts + alt_off[p], (size_t)al); memset(a + kSwPad + al, 'N', (size_t)kSwPad);
+        }
+    });
+    const int64_t sw_max_ops = std::max<int64_t>(8, (int64_t)max_ops + 8);
+    std::unique_ptr<uint32_t[]> sw_ops(new (std::nothrow) uint32_t[(size_t)T * (size_t)sw_max_ops]);
+    if (!sw_ops) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    std::vector<int32_t> sw_n((size_t)T), sw_off((size_t)T);
+    lk_status st = lk_sw_batch_host(ctx, T, pro.data(), prefs.get(), pao.data(), palts.get(), params, strategy,
+                                    (int32_t)sw_max_ops, sw_ops.get(), sw_n.data(), sw_off.data());
     if (st != LK_OK) return st;
-    for (size_t i = 0; i < todo.size(); i++) {
-        const int64_t p = todo[i];
-        if (sw_n[i] == -2) { n_ops[p] = -2; continue; }
-        st = lk_calculate_cigar_finish(refs + ref_off[p], ref_off[p + 1] - ref_off[p], alts + alt_off[p], alt_off[p + 1] - alt_off[p],
-                                       sw_ops.data() + i * (size_t)sw_max_ops, sw_n[i], sw_off[i], max_ops, cigar_ops + p * max_ops,
-                                       &n_ops[p]);
-        if (st != LK_OK) return lk_fail(ctx, st, "calculate_cigar_finish failed");
-    }
+    std::atomic<int> failed{ (int)LK_OK };
+    lk::parallel_for(T, kGrain, [&](int64_t i_begin, int64_t i_end) {
+        for (int64_t i = i_begin; i < i_end; i++) {
+            const int64_t p = todo[(size_t)i];
+            if (sw_n[(size_t)i] == -2) { n_ops[p] = -2; continue; }
+            const lk_status fs = lk_calculate_cigar_finish(refs + ref_off[p], ref_off[p + 1] - ref_off[p], alts + alt_off[p],
+                                                           alt_off[p + 1] - alt_off[p], sw_ops.get() + (size_t)i * (size_t)sw_max_ops,
+                                                           sw_n[(size_t)i], sw_off[(size_t)i], max_ops, cigar_ops + p * max_ops, &n_ops[p]);
+            if (fs != LK_OK) failed.store((int)fs);
+        }
+    });
+    if (failed.load() != (int)LK_OK) return lk_fail(ctx, (lk_status)failed.load(), "calculate_cigar_finish failed");
     return LK_OK;
 }
 
@@ -603,51 +623,55 @@ extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch 
     if (informative) memcpy(informative, info.data(), (size_t)n_reads);
     if (todo.empty()) return LK_OK;
     // ---- one SW batch: reference = best haplotype, alternate = read without soft clips ----
-    std::vector<uint8_t> refs((size_t)ro.back()), alts((size_t)ao.back());
-    int64_t longest = 0;
-    for (size_t i = 0; i < todo.size(); i++) {
-        const int64_t r = todo[i];
-        const int64_t rl = b->read_off[r + 1] - b->read_off[r];
-        memcpy(alts.data() + ao[i], b->read_bases + b->read_off[r], (size_t)rl);
-        longest = std::max(longest, rl);
-    }
+    const int64_t T = (int64_t)todo.size();
+    std::vector<int64_t> hap_of((size_t)T), href_of((size_t)T), region_of((size_t)T);
     {
         size_t i = 0;
         for (int64_t g = 0; g < b->n_regions; g++) {
             const int64_t h0 = b->region_hap_start[g];
             for (int64_t r = b->region_read_start[g]; r < b->region_read_start[g + 1]; r++) {
                 if (pair_of[(size_t)r] < 0) continue;
-                const int64_t h = h0 + best_allele[r];
-                memcpy(refs.data() + ro[i], b->hap_bases + b->hap_off[h], (size_t)(b->hap_off[h + 1] - b->hap_off[h]));
+                hap_of[i] = h0 + best_allele[r];
+                href_of[i] = h0 + (b->ref_allele_index ? b->ref_allele_index[g] : 0);
+                region_of[i] = g;
                 i++;
             }
         }
     }
+    constexpr int64_t kGrain = 2048;
+    std::unique_ptr<uint8_t[]> refs(new (std::nothrow) uint8_t[(size_t)std::max<int64_t>(ro.back(), 1)]),
+                               alts(new (std::nothrow) uint8_t[(size_t)std::max<int64_t>(ao.back(), 1)]);
+    if (!refs || !alts) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    lk::parallel_for(T, kGrain, [&](int64_t i_begin, int64_t i_end) {
+        for (int64_t i = i_begin; i < i_end; i++) {
+            const int64_t r = todo[(size_t)i], h = hap_of[(size_t)i];
+            memcpy(alts.get() + ao[(size_t)i], b->read_bases + b->read_off[r], (size_t)(b->read_off[r + 1] - b->read_off[r]));
+            memcpy(refs.get() + ro[(size_t)i], b->hap_bases + b->hap_off[h], (size_t)(b->hap_off[h + 1] - b->hap_off[h]));
+        }
+    });
     const lk_sw_params prm = { 10, -15, -30, -5 };  // ALIGNMENT_TO_BEST_HAPLOTYPE_SW_PARAMETERS, smith_waterman_aligner.rs:22-25
     const int32_t sw_max_ops = std::max<int32_t>(max_ops, 64);
-    std::vector<uint32_t> sw_ops(todo.size() * (size_t)sw_max_ops);
-    std::vector<int32_t> sw_n(todo.size()), sw_off(todo.size());
-    lk_status st = lk_sw_batch_host(ctx, (int64_t)todo.size(), ro.data(), refs.data(), ao.data(), alts.data(), &prm, LK_SW_SOFTCLIP,
-                                    sw_max_ops, sw_ops.data(), sw_n.data(), sw_off.data());
+    std::unique_ptr<uint32_t[]> sw_ops(new (std::nothrow) uint32_t[(size_t)T * (size_t)sw_max_ops]);
+    if (!sw_ops) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    std::vector<int32_t> sw_n((size_t)T), sw_off((size_t)T);
+    lk_status st = lk_sw_batch_host(ctx, T, ro.data(), refs.get(), ao.data(), alts.get(), &prm, LK_SW_SOFTCLIP,
+                                    sw_max_ops, sw_ops.get(), sw_n.data(), sw_off.data());
     if (st != LK_OK) return st;
-    // ---- CIGAR composition per read (host) ----
-    size_t i = 0;
-    for (int64_t g = 0; g < b->n_regions; g++) {
-        const int64_t h0 = b->region_hap_start[g];
-        const int64_t href = h0 + (b->ref_allele_index ? b->ref_allele_index[g] : 0);
-        for (int64_t r = b->region_read_start[g]; r < b->region_read_start[g + 1]; r++) {
-            if (pair_of[(size_t)r] < 0) continue;
-            const int64_t h = h0 + best_allele[r];
-            if (sw_n[i] == -2) { n_ops[r] = -2; i++; continue; }
-            st = lk_realign_finish(b->read_bases + b->read_off[r], b->read_off[r + 1] - b->read_off[r],
-                                   b->read_cigars + b->read_cigar_off[r], (int32_t)(b->read_cigar_off[r + 1] - b->read_cigar_off[r]),
-                                   b->read_orig_len[r], sw_ops.data() + i * (size_t)sw_max_ops, sw_n[i], sw_off[i],
-                                   b->hap_cigars + b->hap_cigar_off[h], (int32_t)(b->hap_cigar_off[h + 1] - b->hap_cigar_off[h]),
-                                   b->hap_start_wrt_ref[h], b->hap_bases + b->hap_off[href], b->hap_off[href + 1] - b->hap_off[href],
-                                   b->reference_start[g], max_ops, cigar_ops + r * (int64_t)max_ops, &n_ops[r], &pos[r]);
-            if (st != LK_OK) return lk_fail(ctx, st, "realign_finish failed");
-            i++;
+    // ---- CIGAR composition per read (host, spread over the cores for large batches) ----
+    std::atomic<int> failed{ (int)LK_OK };
+    lk::parallel_for(T, kGrain, [&](int64_t i_begin, int64_t i_end) {
+        for (int64_t i = i_begin; i < i_end; i++) {
+            const int64_t r = todo[(size_t)i], h = hap_of[(size_t)i], href = href_of[(size_t)i], g = region_of[(size_t)i];
+            if (sw_n[(size_t)i] == -2) { n_ops[r] = -2; continue; }
+            const lk_status fs = lk_realign_finish(
+                b->read_bases + b->read_off[r], b->read_off[r + 1] - b->read_off[r], b->read_cigars + b->read_cigar_off[r],
+                (int32_t)(b->read_cigar_off[r + 1] - b->read_cigar_off[r]), b->read_orig_len[r],
+                sw_ops.get() + (size_t)i * (size_t)sw_max_ops, sw_n[(size_t)i], sw_off[(size_t)i], b->hap_cigars + b->hap_cigar_off[h],
+                (int32_t)(b->hap_cigar_off[h + 1] - b->hap_cigar_off[h]), b->hap_start_wrt_ref[h], b->hap_bases + b->hap_off[href],
+                b->hap_off[href + 1] - b->hap_off[href], b->reference_start[g], max_ops, cigar_ops + r * (int64_t)max_ops, &n_ops[r], &pos[r]);
+            if (fs != LK_OK) failed.store((int)fs);
         }
-    }
+    });
+    if (failed.load() != (int)LK_OK) return lk_fail(ctx, (lk_status)failed.load(), "realign_finish failed");
     return LK_OK;
 }
