@@ -64,11 +64,57 @@ class PairHMMLikelihoodCalculationEngine:
 
 
 class PairHMM:
-    """PairHMM::initialize + compute_log10_likelihoods (pair_hmm.rs:63-341) on packed arrays."""
+    """PairHMM (pair_hmm.rs): initialize / quick_initialize (:63-168), compute_log10_likelihoods (:217-341) on packed
+    arrays, and the single-pair compute_read_likelihood_given_haplotype_log10 (:404-500) with the reference's argument
+    list, asserts and messages.  Haplotype-prefix caching (hap_start_index, recache_read_values, next_haplotype_bases)
+    is book-kept exactly as the reference does and, like its gkl arm, never used by the arithmetic."""
 
     def __init__(self, ctx):
         self.ctx = ctx
         self._log_likelihood_array = np.zeros(0)
+        self.initialized = False
+        self.max_read_length = 0
+        self.max_haplotype_length = 0
+        self.m_haplotype_data_array = []
+        self.haplotype_to_haplotype_list_index_map = {}
+        self.hap_start_index = None
+        self.previous_haplotype_length = None
+        self.do_exact_log10 = False
+        self.logless = True
+
+    @classmethod
+    def initialize(cls, ctx, haplotypes, per_sample_read_list):
+        """pair_hmm.rs:63-127.  haplotypes: list of byte strings in list order; per_sample_read_list: {sample: [read bases]}.
+        Keeps the haplotypes and the haplotype -> list index map (the AVX arm) and the maximum lengths (the scalar arm)."""
+        hmm = cls(ctx)
+        hmm.m_haplotype_data_array = [bytes(h) for h in haplotypes]
+        hmm.haplotype_to_haplotype_list_index_map = {h: i for i, h in enumerate(hmm.m_haplotype_data_array)}
+        max_read = max((len(r) for reads in per_sample_read_list.values() for r in reads), default=0)
+        max_hap = max((len(h) for h in hmm.m_haplotype_data_array), default=0)
+        hmm._set_sizes(max_read, max_hap)
+        hmm.initialized = True  # the AVX arm is initialised whatever the sizes (:88)
+        return hmm
+
+    @classmethod
+    def quick_initialize(cls, ctx, max_read_length, haplotype_max_length):  # pair_hmm.rs:130-168
+        hmm = cls(ctx)
+        hmm._set_sizes(max_read_length, haplotype_max_length)
+        return hmm
+
+    def _set_sizes(self, max_read_length, haplotype_max_length):
+        self.max_read_length = int(max_read_length)
+        self.max_haplotype_length = int(haplotype_max_length)
+        self.initialized = not (max_read_length == 0 and haplotype_max_length == 0)  # :138-141
+
+    def reinitialize(self, max_read_length, haplotype_max_length):  # pair_hmm.rs:193-207 (sizes only, as the reference)
+        self._set_sizes(max_read_length, haplotype_max_length)
+        self.initialized = True
+
+    def set_do_exact_log10(self, v):  # pair_hmm.rs:172-176, inert
+        self.do_exact_log10 = bool(v)
+
+    def set_logless(self, v):  # pair_hmm.rs:178-184, inert
+        self.logless = bool(v)
 
     def do_not_use_tristate_correction(self):  # pair_hmm.rs:189-191
         self.ctx.set_tristate_correction(False)
@@ -76,6 +122,28 @@ class PairHMM:
     def compute_log10_likelihoods(self, batch):
         self._log_likelihood_array = self.ctx.pairhmm_batch(batch)
         return self._log_likelihood_array
+
+    def compute_read_likelihood_given_haplotype_log10(self, haplotype_bases, read_bases, read_quals, insertion_gop,
+                                                      deletion_gop, overall_gcp, recache_read_values=True,
+                                                      next_haplotype_bases=None):
+        """pair_hmm.rs:404-500: one (read, haplotype) pair through lk_pairhmm_forward."""
+        assert self.initialized, "Must call initialize before calling compute_read_likelihood_given_haplotype_log10"
+        assert len(haplotype_bases) <= self.max_haplotype_length, "Haplotype bases is too long"
+        assert len(read_quals) == len(read_bases), "Read bases and read quals aren't the same size"
+        assert len(insertion_gop) == len(read_bases), "Read bases and insertion gcp aren't the same size"
+        assert len(deletion_gop) == len(read_bases), "Read bases and deletion gcp aren't the same size"
+        assert len(overall_gcp) == len(read_bases), "Read bases and overal GCP aren't the same size"
+        if recache_read_values:
+            self.hap_start_index = 0
+        next_start = 0
+        if next_haplotype_bases is not None and len(next_haplotype_bases) == len(haplotype_bases):
+            next_start = self.find_first_position_where_haplotypes_differ(haplotype_bases, next_haplotype_bases)
+        assert self.hap_start_index is not None  # the reference unwraps it (:468)
+        result = self.ctx.pairhmm_forward(haplotype_bases, read_bases, read_quals, insertion_gop, deletion_gop, overall_gcp)
+        assert result <= 0.0, "PairHmm Log Probability cannot be greater than 0.0"
+        self.hap_start_index = 0 if next_start < self.hap_start_index else next_start  # :487-496
+        self.previous_haplotype_length = len(haplotype_bases)
+        return result
 
     def get_log_likelihood_array(self):  # pair_hmm.rs:377-379
         return self._log_likelihood_array

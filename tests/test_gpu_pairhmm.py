@@ -51,6 +51,25 @@ def test_golden_rows_single_pair_entry_point(ctx):
         assert abs(got - r["expected"]) < 1e-5
 
 
+def test_golden_rows_through_the_pairhmm_type(ctx):
+    # the scalar arm's loop of PairHMM::compute_log10_likelihoods (pair_hmm.rs:290-333): for read { for allele { ... } } with
+    # recache on the first haplotype and the next haplotype passed for the prefix bookkeeping
+    from lorikeet_b200.engine import PairHMM
+    rows = load_pairhmm_golden()[:24]
+    hmm = PairHMM.initialize(ctx, [r["hap"] for r in rows], {0: [r["read"] for r in rows]})
+    assert hmm.initialized and hmm.max_haplotype_length == max(len(r["hap"]) for r in rows)
+    for r in rows[::6]:
+        first = True
+        for a, h in enumerate(rows[:6]):
+            nxt = rows[a + 1]["hap"] if a + 1 < 6 else None
+            got = hmm.compute_read_likelihood_given_haplotype_log10(h["hap"], r["read"], r["qual"], r["ins"], r["dele"], r["gcp"], first, nxt)
+            first = False
+            exp = O.pairhmm_forward(h["hap"], r["read"], r["qual"], r["ins"], r["dele"], r["gcp"])
+            assert got <= 0.0 and abs(got - exp) <= REL_TOL * max(abs(exp), 1e-3)
+            if h is r:
+                assert abs(got - r["expected"]) < 1e-5
+
+
 def test_golden_rows_forced_f64(ctx):
     rows = load_pairhmm_golden()
     cases = [dict(hap=r["hap"], read=r["read"], qual=r["qual"], ins=r["ins"], dele=r["dele"], gcp=r["gcp"]) for r in rows]

@@ -122,6 +122,42 @@ def test_resident_repeatable_and_edge_cases(ctx):
         ctx.sw_align(b"", b"ACGT", SC.ORIGINAL_DEFAULT, "SoftClip")
 
 
+def test_host_pipeline_matches_resident(ctx):
+    # lk_sw_batch_host cuts a large batch into contiguous pair ranges that flow through three workspaces / streams
+    # (8.2e9 cells -> 3 chunks here); every (n_ops, offset, ops[:n_ops]) must equal the single resident launch set, with
+    # short pairs of the other K classes mixed in so each chunk launches several kernels
+    from lorikeet_b200 import synth
+    rng = np.random.default_rng(77)
+    ro, refs, ao, alts = synth.sw_pairs(30000, first_pair=20000)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    parts_r, parts_a = [], []
+    for _ in range(600):
+        n = int(rng.integers(1, 260))
+        r = rng.choice(acgt, n)
+        a = r.copy()
+        if n > 8:
+            a = np.delete(a, slice(3, 3 + int(rng.integers(0, 4))))
+            a[int(rng.integers(0, a.size))] = ord("A")
+        parts_r.append(r); parts_a.append(a)
+    sro = np.concatenate([[0], np.cumsum([len(x) for x in parts_r])]).astype(np.int64)
+    sao = np.concatenate([[0], np.cumsum([len(x) for x in parts_a])]).astype(np.int64)
+    # short pairs first, then the long ones, then the short ones again
+    all_ro = np.concatenate([sro, sro[-1] + ro[1:], sro[-1] + ro[-1] + sro[1:]])
+    all_ao = np.concatenate([sao, sao[-1] + ao[1:], sao[-1] + ao[-1] + sao[1:]])
+    all_refs = np.concatenate(parts_r + [refs] + parts_r)
+    all_alts = np.concatenate(parts_a + [alts] + parts_a)
+    ops, n_ops, offs = ctx.sw_batch(all_ro, all_refs, all_ao, all_alts, SC.NEW_SW_PARAMETERS, "SoftClip", max_ops=64)
+    res = ctx.sw_upload(all_ro, all_refs, all_ao, all_alts, SC.NEW_SW_PARAMETERS, "SoftClip", max_ops=64)
+    res.run()
+    eops, en, eoffs = res.download()
+    res.free()
+    assert np.array_equal(n_ops, en) and np.array_equal(offs, eoffs) and (n_ops > 0).all()
+    valid = np.arange(64)[None, :] < n_ops[:, None]
+    assert np.array_equal(ops[valid], eops[valid])
+    # the two copies of the short pairs sit in different chunks and must agree with each other
+    assert np.array_equal(n_ops[:600], n_ops[-600:]) and np.array_equal(offs[:600], offs[-600:])
+
+
 def test_bytes_outside_acgtn_and_clamped_form(ctx):
     # alternate columns holding bytes outside A C G T N use the raw byte compare instead of the weight table; weights large
     # enough that (n + m) * max|w| >= 1e8 select the kernel that keeps the reference's -1e8 clamp
