@@ -9,6 +9,8 @@
 // hands every caller its own slice of the result.
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -46,17 +48,27 @@ struct lk_batcher {
     std::thread worker;
     // statistics
     int64_t n_batches = 0, n_regions = 0;
+    size_t last_batch = 1;  // callers released by the previous batch: once that many are back there is nobody left to wait for
+    // gather buffers of the dispatcher thread, kept across batches (fresh vectors cost more in page faults than the copies)
+    std::vector<int64_t> rrs, rhs, read_off, hap_off;
+    std::vector<uint8_t> bases, qual, ins, del, gcp, haps, mapq, aux;
+    std::vector<int32_t> ref_idx;
+    std::vector<double> out;
 
     void run();
     void process(std::vector<Request *> &reqs);
 };
 
+static double bt_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 void lk_batcher::process(std::vector<Request *> &reqs) {
+    static const bool trace = getenv("LK_TRACE") != nullptr;
+    const double t0 = bt_now_ms();
     // concatenate the regions into one batch (host copies of a few KB per region)
     const size_t G = reqs.size();
-    std::vector<int64_t> rrs(G + 1, 0), rhs(G + 1, 0), read_off(1, 0), hap_off(1, 0);
-    std::vector<uint8_t> bases, qual, ins, del, gcp, haps, mapq;
-    std::vector<int32_t> ref_idx(G, 0);
+    rrs.assign(G + 1, 0); rhs.assign(G + 1, 0); read_off.assign(1, 0); hap_off.assign(1, 0);
+    bases.clear(); qual.clear(); ins.clear(); del.clear(); gcp.clear(); haps.clear(); mapq.clear();
+    ref_idx.assign(G, 0);
     bool any_gcp = false, need_mapq = engine && !args.disable_cap_read_qualities_to_mapq;
     for (Request *q : reqs) any_gcp |= (q->region->read_gcp != nullptr);
     lk_status bad = LK_OK;
@@ -95,13 +107,15 @@ void lk_batcher::process(std::vector<Request *> &reqs) {
     big.hap_off = hap_off.data(); big.hap_bases = haps.data();
     int64_t n_pairs = 0;
     for (size_t g = 0; g < G; g++) n_pairs += (rrs[g + 1] - rrs[g]) * (rhs[g + 1] - rhs[g]);
-    std::vector<double> out((size_t)n_pairs);
-    std::vector<uint8_t> aux((size_t)(engine ? rrs[G] : n_pairs));
+    out.resize((size_t)n_pairs);
+    aux.resize((size_t)(engine ? rrs[G] : n_pairs));
     lk_status st = bad;
+    const double t1 = bt_now_ms();
     if (st == LK_OK) {
         if (engine) st = lk_engine_compute_read_likelihoods(ctx, &args, &big, need_mapq ? mapq.data() : nullptr, ref_idx.data(), out.data(), aux.data());
         else st = lk_pairhmm_batch_host(ctx, &big, out.data(), aux.data());
     }
+    const double t2 = bt_now_ms();
     int64_t pbase = 0;
     for (size_t g = 0; g < G; g++) {
         Request *q = reqs[g];
@@ -116,6 +130,7 @@ void lk_batcher::process(std::vector<Request *> &reqs) {
         q->status = st;
         pbase += np;
     }
+    if (trace) fprintf(stderr, "[lk] batcher: %zu regions, gather %.2f ms, device call %.2f ms, scatter %.2f ms\n", G, t1 - t0, t2 - t1, bt_now_ms() - t2);
 }
 
 void lk_batcher::run() {
@@ -125,7 +140,8 @@ void lk_batcher::run() {
         if (stop && queue.empty()) return;
         // give stragglers a moment: a fuller batch uses the GPU better than a prompt one
         if ((int32_t)queue.size() < max_regions && max_wait_us > 0 && !stop)
-            cv_work.wait_for(lock, std::chrono::microseconds(max_wait_us), [&] { return stop || (int32_t)queue.size() >= max_regions; });
+            cv_work.wait_for(lock, std::chrono::microseconds(max_wait_us),
+                             [&] { return stop || (int32_t)queue.size() >= max_regions || queue.size() >= last_batch; });
         std::vector<Request *> reqs;
         while (!queue.empty() && (int32_t)reqs.size() < max_regions) { reqs.push_back(queue.front()); queue.pop_front(); }
         lock.unlock();
@@ -133,6 +149,7 @@ void lk_batcher::run() {
         lock.lock();
         n_batches++;
         n_regions += (int64_t)reqs.size();
+        last_batch = reqs.size();
         for (Request *q : reqs) q->done = true;
         cv_done.notify_all();
     }

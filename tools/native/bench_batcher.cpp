@@ -1,0 +1,101 @@
+// bench_batcher.cpp — developer check of the drop-in call pattern: T host threads each submit ONE region at a time to
+// lk_batcher (what Lorikeet's Rayon workers would do through the Rust binding, assembly_region_walker.rs:140-277),
+// next to the same regions handed to lk_engine_compute_read_likelihoods in one call.
+//   g++ -O2 -std=c++17 -I include tools/native/bench_batcher.cpp -L lorikeet_b200 -llorikeet_b200 -lpthread -o bench_batcher
+//   LD_LIBRARY_PATH=lorikeet_b200 ./bench_batcher [regions=4000] [threads=32] [max_regions=512] [max_wait_us=200]
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "lorikeet_b200.h"
+#include "lorikeet_b200_synth.h"
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char **argv) {
+    const int64_t G = argc > 1 ? atoll(argv[1]) : 4000;
+    const int T = argc > 2 ? atoi(argv[2]) : 32;
+    const int max_regions = argc > 3 ? atoi(argv[3]) : 512;
+    const int max_wait_us = argc > 4 ? atoi(argv[4]) : 200;
+    lk_synth_params p;
+    memset(&p, 0, sizeof p);
+    p.seed_base = 0x4C4B0000; p.n_reads = 64; p.read_len = 150; p.n_haps = 16; p.hap_len = 300; p.min_edits = 1; p.max_edits = 4;
+    p.qual_profile = 0; p.pcr_model = 0 /* raw Q45: the engine applies the PCR model itself */; p.base_quality_score_threshold = 0; p.mapq = 60;
+    const int64_t R = G * p.n_reads, H = G * p.n_haps;
+    std::vector<int64_t> rrs(G + 1), rhs(G + 1), roff(R + 1), hoff(H + 1);
+    std::vector<uint8_t> rb(R * p.read_len), rq(rb.size()), ri(rb.size()), rd(rb.size()), hb(G * lk_synth_max_hap_bytes_per_region(&p));
+    if (lk_synth_pairhmm_regions(&p, 0, G, rrs.data(), rhs.data(), roff.data(), rb.data(), rq.data(), ri.data(), rd.data(), hoff.data(), hb.data(), 0) != LK_OK) return 1;
+    std::vector<uint8_t> mapq(R, 60);
+    lk_ctx *ctx = nullptr;
+    if (lk_create(0, &ctx) != LK_OK) { fprintf(stderr, "no CUDA device\n"); return 2; }
+    lk_engine_args args;
+    memset(&args, 0, sizeof args);
+    args.constant_gcp = 10; args.log10_global_read_mismapping_rate = -4.5; args.pcr_error_model = LK_PCR_CONSERVATIVE;
+    args.base_quality_score_threshold = 18; args.read_disqualification_scale = 1.0; args.expected_error_rate_per_base = 0.02;
+    args.symmetrically_normalize_alleles_to_reference = 1;
+    lk_pairhmm_batch all;
+    memset(&all, 0, sizeof all);
+    all.n_regions = G; all.region_read_start = rrs.data(); all.region_hap_start = rhs.data(); all.read_off = roff.data();
+    all.read_bases = rb.data(); all.read_qual = rq.data(); all.read_ins = ri.data(); all.read_del = rd.data(); all.gcp_constant = 10;
+    all.hap_off = hoff.data(); all.hap_bases = hb.data();
+    int64_t n_pairs = 0, n_cells = 0;
+    lk_pairhmm_batch_dims(&all, &n_pairs, &n_cells);
+    std::vector<double> direct(n_pairs), viab(n_pairs);
+    std::vector<uint8_t> keep_d(R), keep_b(R);
+    // ---- one call ----
+    double best = 1e30;
+    for (int it = 0; it < 3; it++) {
+        const double t0 = now_ms();
+        if (lk_engine_compute_read_likelihoods(ctx, &args, &all, mapq.data(), nullptr, direct.data(), keep_d.data()) != LK_OK) { fprintf(stderr, "%s\n", lk_last_error(ctx)); return 3; }
+        best = std::min(best, now_ms() - t0);
+    }
+    printf("one call            regions=%lld  %.1f ms  %.0f GCUPS\n", (long long)G, best, n_cells / best / 1e6);
+    // ---- T threads, one region per submit ----
+    lk_batcher *bt = nullptr;
+    if (lk_batcher_create(ctx, &args, max_regions, max_wait_us, &bt) != LK_OK) return 4;
+    std::vector<int64_t> pair_base(G + 1, 0);
+    for (int64_t g = 0; g < G; g++) pair_base[g + 1] = pair_base[g] + (rrs[g + 1] - rrs[g]) * (rhs[g + 1] - rhs[g]);
+    best = 1e30;
+    for (int it = 0; it < 3; it++) {
+        std::atomic<int64_t> next{ 0 };
+        std::atomic<int> bad{ 0 };
+        const double t0 = now_ms();
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; t++)
+            pool.emplace_back([&]() {
+                for (;;) {
+                    const int64_t g = next.fetch_add(1);
+                    if (g >= G) break;
+                    // a one-region view of the big arrays: offsets rebased to the region, arenas advanced to its first byte
+                    const int64_t r0 = rrs[g], nr = rrs[g + 1] - r0, h0 = rhs[g], nh = rhs[g + 1] - h0;
+                    int64_t rs1[2] = { 0, nr }, hs1[2] = { 0, nh };
+                    std::vector<int64_t> ro(nr + 1), ho(nh + 1);
+                    for (int64_t i = 0; i <= nr; i++) ro[i] = roff[r0 + i] - roff[r0];
+                    for (int64_t i = 0; i <= nh; i++) ho[i] = hoff[h0 + i] - hoff[h0];
+                    lk_pairhmm_batch one;
+                    memset(&one, 0, sizeof one);
+                    one.n_regions = 1; one.region_read_start = rs1; one.region_hap_start = hs1; one.read_off = ro.data();
+                    one.read_bases = rb.data() + roff[r0]; one.read_qual = rq.data() + roff[r0]; one.read_ins = ri.data() + roff[r0];
+                    one.read_del = rd.data() + roff[r0]; one.gcp_constant = 10; one.hap_off = ho.data(); one.hap_bases = hb.data() + hoff[h0];
+                    if (lk_batcher_submit(bt, &one, mapq.data() + r0, 0, viab.data() + pair_base[g], keep_b.data() + r0) != LK_OK) bad++;
+                }
+            });
+        for (auto &th : pool) th.join();
+        if (bad) { fprintf(stderr, "submit failed\n"); return 5; }
+        best = std::min(best, now_ms() - t0);
+    }
+    int64_t nb = 0, nr = 0;
+    lk_batcher_stats(bt, &nb, &nr);
+    printf("batcher %2d threads  regions=%lld  %.1f ms  %.0f GCUPS  (%.1f regions per launch)\n", T, (long long)G, best, n_cells / best / 1e6, (double)nr / (double)nb);
+    const bool same = memcmp(direct.data(), viab.data(), n_pairs * 8) == 0 && memcmp(keep_d.data(), keep_b.data(), R) == 0;
+    printf("batcher results %s the one-call results\n", same ? "are bit-identical to" : "DIFFER from");
+    lk_batcher_destroy(bt);
+    lk_destroy(ctx);
+    return same ? 0 : 6;
+}
