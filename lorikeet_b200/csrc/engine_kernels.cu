@@ -86,6 +86,9 @@ __device__ __noinline__ int tandem_repeat_length(const uint8_t *bases, int len, 
 // 20 on random sequence) enter the run-length loop.  Guard bytes are never trusted: the validity masks cut the lengths
 // that would reach outside the read.  Byte-identical to tandem_repeat_length (tests/test_gpu_engine.py).
 constexpr int kEnginePad = 24;
+// floor(run / s) for 0 <= run < 2^15, 1 <= s <= 20 without the ~25-instruction integer division: (run + 0.5) / s lies
+// at least 0.5/20 away from every integer, far more than the error of the approximate float division
+__device__ __forceinline__ int div_small(int run, int s) { return __float2int_rd(__fdividef((float)run + 0.5f, (float)s)); }
 __device__ __forceinline__ uint32_t zero_byte_flags(uint32_t x) {  // bit 8b+7 set iff byte b of x is 0
     return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
 }
@@ -107,7 +110,7 @@ __device__ __forceinline__ uint32_t window_eq_mask(const uint8_t *b, int first, 
     return mask;
 }
 __device__ __forceinline__ int tandem_repeat_length_staged(const uint8_t *b, int len, int offset) {
-    int max_bw = 1, bw_len = 1;
+    int bw_len = 1, bw_run = 0;  // found unit length and its run of equalities (0: none, one copy)
     uint32_t m = window_eq_mask<true>(b, offset - 20, b[offset]) & (offset >= 20 ? 0xfffffu : (1u << offset) - 1u);
     // a unit of length >= 2 needs the neighbouring byte pair to match as well: second screen, same window one byte down
     if (m & ~1u) m &= window_eq_mask<true>(b, offset - 21, b[offset - 1]) & (offset >= 21 ? 0xfffffu : (1u << (offset - 1)) - 1u) | 1u;
@@ -115,11 +118,12 @@ __device__ __forceinline__ int tandem_repeat_length_staged(const uint8_t *b, int
         const int s = __ffs(m);
         m &= m - 1;
         const int run = 1 + run_back(b, offset - 1, s);
-        if (run >= s) { max_bw = 1 + run / s; bw_len = s; break; }
+        if (run >= s) { bw_run = run; bw_len = s; break; }
     }
+    const int max_bw = 1 + div_small(bw_run, bw_len);  // outside the divergent loop, every lane at once
     int max_rl = max_bw;
     if (offset < len - 1) {
-        int fw_len = 1, max_fw = 1;
+        int fw_len = 1, fw_run = 0;
         const int room = len - 2 - offset;  // s <= room keeps b[offset + 1 + s] inside the read
         m = window_eq_mask<false>(b, offset + 2, b[offset + 1]) & (room >= 20 ? 0xfffffu : (1u << room) - 1u);
         if (m & ~1u) m &= window_eq_mask<false>(b, offset + 3, b[offset + 2]) & (room >= 21 ? 0xfffffu : (1u << (room - 1)) - 1u) | 1u;
@@ -129,15 +133,16 @@ __device__ __forceinline__ int tandem_repeat_length_staged(const uint8_t *b, int
             const int p0 = offset + 1 + s;
             int p = p0 + 1;
             while (p < len && b[p] == b[p - s]) p++;
-            if (p - p0 >= s) { max_fw = 1 + (p - p0) / s; fw_len = s; break; }
+            if (p - p0 >= s) { fw_run = p - p0; fw_len = s; break; }
         }
+        const int max_fw = 1 + div_small(fw_run, fw_len);
         if (fw_len == bw_len && same_bytes(b + offset + 1, b + offset + 1 - bw_len, fw_len)) {
             max_rl = max_bw + max_fw;
         } else {
             int before = 0;
             if (offset + 1 >= fw_len) {
                 const int run = run_back(b, offset + fw_len, fw_len);
-                before = run >= fw_len ? run / fw_len : 0;
+                before = run >= fw_len ? div_small(run, fw_len) : 0;
             }
             max_rl = max_fw + before;
         }
@@ -181,12 +186,14 @@ __global__ void __launch_bounds__(128) engine_modify_reads_kernel(EngineDevArgs 
             __syncwarp();
             for (int j = lane; j < len; j += 32) mine[kEnginePad + j] = bases[j];
             __syncwarp();
-            bases = mine + kEnginePad;
         }
+        // never assigned from a global pointer, so the search compiles to LDS with 32-bit addresses (a pointer that may be
+        // either costs a generic load and 64-bit address arithmetic per byte)
+        const uint8_t *staged_bases = mine + kEnginePad;
         for (int j = lane; j < len; j += 32) {
             uint8_t q = E.read_qual[o + j], qi = E.read_ins[o + j], qd = E.read_del[o + j];
             if (E.use_pcr && j < len - 1) {  // apply_pcr_error_model writes i-1 for i in 1..len: the last base is never touched
-                const uint8_t c = E.pcr_cache[staged ? tandem_repeat_length_staged(bases, len, j) : tandem_repeat_length(bases, len, j)];
+                const uint8_t c = E.pcr_cache[staged ? tandem_repeat_length_staged(staged_bases, len, j) : tandem_repeat_length(bases, len, j)];
                 qi = qi < c ? qi : c;
                 qd = qd < c ? qd : c;
             }
