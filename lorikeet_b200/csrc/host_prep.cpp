@@ -45,7 +45,8 @@ int choose_k(int R, int force_k) {
 }
 
 
-void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, bool fast_enabled, HostPrep &P) {
+void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, bool fast_enabled, HostPrep &P,
+                int64_t split_target_tasks) {
     // Everything produced here is LOCAL to the region range [g0, g1): read / haplotype / region indices and
     // result offsets start at 0, so a chunk can be staged and run on its own.
     const int64_t rbase = b->region_read_start[g0], hbase = b->region_hap_start[g0];
@@ -101,6 +102,7 @@ void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, 
         if (!k_present[K]) continue;
         FastLaunch L;
         L.K = K;
+        L.split = false;
         L.first_task = (int32_t)P.tasks.size();
         for (int64_t g = g0; g < g1; g++) {
             const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
@@ -112,12 +114,13 @@ void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, 
             auto len = [&](int64_t r) { return (int)(b->read_off[r + 1] - b->read_off[r]); };
             std::stable_sort(bucket.begin(), bucket.end(), [&](int64_t x, int64_t y) { return len(x) > len(y); });
             int lane = 0;
+            const TaskHaps whole{ 0, (int32_t)(b->region_hap_start[g + 1] - b->region_hap_start[g]) };
             WarpTask t{ (int32_t)P.groups.size(), 0 };
             for (size_t i = 0; i < bucket.size(); i++) {
                 const int64_t rx = bucket[i];
                 const int G = (len(rx) + K - 1) / K;
                 if (lane + G > 32) {
-                    P.tasks.push_back(t);
+                    P.tasks.push_back(t); P.task_haps.push_back(whole);
                     t = WarpTask{ (int32_t)P.groups.size(), 0 };
                     lane = 0;
                 }
@@ -125,9 +128,34 @@ void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, 
                 t.n_groups++;
                 lane += G;
             }
-            if (t.n_groups > 0) P.tasks.push_back(t);
+            if (t.n_groups > 0) { P.tasks.push_back(t); P.task_haps.push_back(whole); }
         }
         L.n_tasks = (int32_t)P.tasks.size() - L.first_task;
+        // A small launch (a few regions from the cross-thread batcher, say) leaves most warp slots empty while each task
+        // walks all haplotypes of its region: cut the tasks along the haplotype axis.  The per-row constants and the prior
+        // table are rebuilt per slice (a few % of a 4-haplotype sweep), so large launches stay whole.
+        if (split_target_tasks > 0 && L.n_tasks > 0 && L.n_tasks < split_target_tasks) {
+            const int64_t parts_wanted = (split_target_tasks + L.n_tasks - 1) / L.n_tasks;
+            std::vector<WarpTask> cut_t;
+            std::vector<TaskHaps> cut_h;
+            for (int32_t i = L.first_task; i < L.first_task + L.n_tasks; i++) {
+                const WarpTask t = P.tasks[(size_t)i];
+                const int32_t A = P.task_haps[(size_t)i].count;
+                const int64_t parts = std::max<int64_t>(1, std::min<int64_t>(parts_wanted, A / 4));
+                for (int64_t q = 0; q < parts; q++) {
+                    const int32_t lo = (int32_t)(A * q / parts), hi = (int32_t)(A * (q + 1) / parts);
+                    cut_t.push_back(t);
+                    cut_h.push_back(TaskHaps{ lo, hi - lo });
+                }
+            }
+            if ((int32_t)cut_t.size() > L.n_tasks) {
+                P.tasks.resize((size_t)L.first_task); P.task_haps.resize((size_t)L.first_task);
+                P.tasks.insert(P.tasks.end(), cut_t.begin(), cut_t.end());
+                P.task_haps.insert(P.task_haps.end(), cut_h.begin(), cut_h.end());
+                L.n_tasks = (int32_t)cut_t.size();
+                L.split = true;
+            }
+        }
         if (L.n_tasks > 0) P.launches.push_back(L);
     }
 }

@@ -103,6 +103,9 @@ extern "C" lk_status lk_create(int device, lk_ctx **out_ctx) {
     }
     const char *fk = getenv("LK_FORCE_K");
     ctx->force_k = fk ? atoi(fk) : 0;
+    // launches with fewer warp tasks than two rounds of the resident warps (3 blocks x 4 warps per SM) are cut finer
+    const char *sp = getenv("LK_SPLIT_TARGET");
+    ctx->split_target_tasks = sp ? atoll(sp) : (int64_t)ctx->n_sm * 12 * 2;
     *out_ctx = ctx;
     return LK_OK;
 }
@@ -233,7 +236,8 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
         return lk_cuda_fail(ctx, e, "event create");
     }
     HostPrep &P = R->prep;
-    build_prep(b, g0, g1, ctx->force_k, !ctx->force_f64, P);
+    // the haplotype-axis split of small launches exists for the engine's default gcp only (launch_fast_k)
+    build_prep(b, g0, g1, ctx->force_k, !ctx->force_f64, P, (!gcp.vargcp && gcp.constant == 10) ? ctx->split_target_tasks : 0);
     const int64_t rbase = b->region_read_start[g0], hbase = b->region_hap_start[g0];
     const int64_t n_reads = b->region_read_start[g1] - rbase, n_haps = b->region_hap_start[g1] - hbase;
     const int64_t n_regions = g1 - g0;
@@ -275,6 +279,7 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
         { &R->hap_off, b->hap_off + hbase, (size_t)(n_haps + 1) * 8 },
         { &R->henc_off, P.henc_off.data(), (size_t)n_haps * 8 },
         { &R->tasks, P.tasks.data(), P.tasks.size() * sizeof(WarpTask) },
+        { &R->task_haps, P.task_haps.data(), P.task_haps.size() * sizeof(TaskHaps) },
         { &R->groups, P.groups.data(), P.groups.size() * sizeof(TaskGroup) },
         { &R->rescue_pairs, P.direct.data(), (size_t)R->n_direct * sizeof(RescuePair) },
         { &R->band_pairs, P.direct.data(), (size_t)R->n_band * sizeof(RescuePair) },
@@ -410,6 +415,7 @@ static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, b
             PairHmmArgs AL = A;
             AL.tasks = (const WarpTask *)R->tasks.p + L.first_task;
             AL.n_tasks = L.n_tasks;
+            AL.task_haps = L.split ? (const TaskHaps *)R->task_haps.p + L.first_task : nullptr;
             if ((e = launch_fast(L.K, AL, R->vargcp, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_fast");
             R->launch_count++;
         }
@@ -505,7 +511,7 @@ static void release_buffers(lk_resident *R) {
     DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
                        &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
                        &R->region_read_start, &R->read_mapq, &R->ref_allele_index, &R->qual_orig, &R->values, &R->keep,
-                       &R->hap_bases, &R->hidx, &R->henc_off, &R->hap_flags, &R->tasks, &R->groups, &R->out,
+                       &R->hap_bases, &R->hidx, &R->henc_off, &R->hap_flags, &R->tasks, &R->task_haps, &R->groups, &R->out,
                        &R->flags, &R->counters, &R->rescue_pairs, &R->scratch, &R->band_pairs, &R->band_scratch,
                        &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,
                        &R->sw_ops, &R->sw_nops, &R->sw_offsets, &R->sw_order };

@@ -36,6 +36,7 @@ struct lk_ctx {
     bool tristate = true;
     bool force_f64 = false;
     int force_k = 0;
+    int64_t split_target_tasks = 0;  // launches with fewer warp tasks are cut along the haplotype axis (build_prep)
     int32_t last_launch_count = 0;
     DevBuf d_qerr_f, d_qerr_d, d_m2m;
     // reusable workspaces of lk_pairhmm_batch_host's chunk pipeline, one per stream.  Three, not two: chunk i+2's H2D then
@@ -70,7 +71,7 @@ struct lk_resident {
     int64_t read_byte0 = 0, hap_byte0 = 0;  // first arena byte staged: device pointers are biased by these
     DevBuf read_bases, read_qual, read_ins, read_del, read_gcp, read_off, read_region, read_out_base, read_flags;
     DevBuf region_hap_start, hap_off, hap_bases, hidx, henc_off, hap_flags;
-    DevBuf tasks, groups, out, flags, counters, rescue_pairs, scratch, band_pairs, band_scratch;
+    DevBuf tasks, task_haps, groups, out, flags, counters, rescue_pairs, scratch, band_pairs, band_scratch;
     // engine pre/post-ops on the device (N3)
     DevBuf region_read_start, read_mapq, ref_allele_index, qual_orig, values, keep;
     // ---- Smith-Waterman ----

@@ -95,6 +95,10 @@ struct WarpTask {        // all groups of a task belong to one region
     int32_t first_group;
     int32_t n_groups;
 };
+struct TaskHaps {        // haplotype slice of a split task, relative to its region's first haplotype
+    int32_t begin;
+    int32_t count;
+};
 struct RescuePair {
     int32_t read;
     int32_t hap;         // batch-global haplotype index
@@ -143,6 +147,10 @@ struct PairHmmArgs {
     float cf_uniform;              // 10^(-gcp_constant/10) = tII = tDD when gcp is uniform.  Lives in the kernel-parameter
                                    // constant bank so FFMAs can take it as a c[][] operand: a 3-register-source FFMA issues at
                                    // only ~2/3 rate on B200 (tools/microbench/ffma3.cu), a 2-register one at full rate.
+    // small launches only (SPLIT instantiations): per task, the slice of its region's haplotypes it sweeps.  Kept out
+    // of WarpTask and at the end of the struct: the whole-region kernels must compile exactly as without it (two more
+    // task fields cost the cfg#2 kernel 5 % through register allocation).
+    const TaskHaps *task_haps;
 };
 
 LK_DEV int lk_popc(unsigned v) {
@@ -188,7 +196,7 @@ LK_DEV double m2m_lookup(const double *m2m, int ins, int del) {
 // pair_hmm_likelihood_calculation_engine.rs:649-651): the factor 0.1f is then an FFMA immediate, which saves
 // one register-file read per cell in a kernel that is register-read bound.
 enum { GM_UNIFORM = 0, GM_VAR = 1, GM_Q10 = 2 };
-template <class W, int K, int GM>
+template <class W, int K, int GM, bool SPLIT = false>
 LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id, float *tab) {
     constexpr bool VARGCP = (GM == GM_VAR);
     const int lane = w.lane();
@@ -292,7 +300,13 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id, float *ta
     const int64_t h0 = A.region_hap_start[region], h1 = A.region_hap_start[region + 1];
     const int64_t out_base = A.read_out_base[read];
 
-    for (int64_t h = h0; h < h1; ++h) {
+    int64_t h_first = h0, h_end = h1;
+    if constexpr (SPLIT) {
+        const TaskHaps th = A.task_haps[task_id];
+        h_first = h0 + th.begin;
+        h_end = h_first + th.count;
+    }
+    for (int64_t h = h_first; h < h_end; ++h) {
         const int H = (int)(A.hap_off[h + 1] - A.hap_off[h]);
         const uint8_t *hp = A.hidx + A.henc_off[h] - 1 - lig;  // hp[s] = table slice of column (s - lig)
         const float kinit = kcoef * (FAST_INIT / (float)H);

@@ -99,14 +99,14 @@ __global__ void list_all_pairs_kernel(PairHmmArgs A, int64_t n_reads) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int K, int GM, int MINB>
+template <int K, int GM, int MINB, bool SPLIT = false>
 __global__ void __launch_bounds__(LK_FAST_THREADS, MINB) pairhmm_fast_kernel(const PairHmmArgs A) {
     extern __shared__ float4 lk_fast_smem[];  // per-warp prior tables
     const int task = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (task >= A.n_tasks) return;
     DevWarp w;
     float *tab = reinterpret_cast<float *>(lk_fast_smem) + (threadIdx.x >> 5) * fast_table_floats(K);
-    pairhmm_fast_task<DevWarp, K, GM>(w, A, task, tab);
+    pairhmm_fast_task<DevWarp, K, GM, SPLIT>(w, A, task, tab);
 }
 
 template <int K, bool Q10>
@@ -173,7 +173,7 @@ cudaError_t launch_list_all_pairs(const PairHmmArgs &A, int64_t n_reads, cudaStr
     return cudaGetLastError();
 }
 
-template <int K, int GM, int MINB>
+template <int K, int GM, int MINB, bool SPLIT = false>
 static cudaError_t launch_fast_kg(const PairHmmArgs &A, cudaStream_t st) {
     const int warps_per_block = LK_FAST_THREADS / 32;
     const unsigned blocks = (unsigned)((A.n_tasks + warps_per_block - 1) / warps_per_block);
@@ -184,18 +184,24 @@ static cudaError_t launch_fast_kg(const PairHmmArgs &A, cudaStream_t st) {
     cudaGetDevice(&dev);
     bool &configured = configured_on[dev & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pairhmm_fast_kernel<K, GM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pairhmm_fast_kernel<K, GM, MINB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    pairhmm_fast_kernel<K, GM, MINB><<<blocks, LK_FAST_THREADS, smem, st>>>(A);
+    pairhmm_fast_kernel<K, GM, MINB, SPLIT><<<blocks, LK_FAST_THREADS, smem, st>>>(A);
     return cudaGetLastError();
 }
 
 template <int K, int MINB>
 static cudaError_t launch_fast_k(const PairHmmArgs &A, bool vargcp, cudaStream_t st) {
     if (vargcp) return launch_fast_kg<K, GM_VAR, MINB>(A, st);
-    if (A.gcp_constant == 10 && A.cf_uniform == 0.1f) return launch_fast_kg<K, GM_Q10, MINB>(A, st);
+    if (A.gcp_constant == 10 && A.cf_uniform == 0.1f) {
+        // tasks cut along the haplotype axis (small launches, host_prep.cpp) exist for the engine's default gcp only; with
+        // any other gcp the whole-region kernel runs the same task list, each task then sweeping (and rewriting) all
+        // haplotypes of its region: redundant, never wrong
+        if (A.task_haps) return launch_fast_kg<K, GM_Q10, MINB, true>(A, st);
+        return launch_fast_kg<K, GM_Q10, MINB>(A, st);
+    }
     return launch_fast_kg<K, GM_UNIFORM, MINB>(A, st);
 }
 

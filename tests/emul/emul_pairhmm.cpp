@@ -4,6 +4,7 @@
 // GPU kernels run (lorikeet_b200/csrc/pairhmm_core.cuh) with shuffles implemented through a shared
 // slot array and barriers.  It exists because the build container has no GPU: it lets the CPU test
 // suite exercise the lane/strip/skew index logic of the kernels before a gpurun call.
+#include <cstdlib>
 #include <atomic>
 #include <barrier>
 #include <cstring>
@@ -62,10 +63,11 @@ struct EmulWarp {
 };
 
 template <int K>
-static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *tasks, int n_tasks) {
+static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *tasks, int n_tasks, const TaskHaps *task_haps) {
     PairHmmArgs AL = A;
     AL.tasks = tasks;
     AL.n_tasks = n_tasks;
+    AL.task_haps = task_haps;
     WarpShared sh;
     std::vector<float> tab((size_t)fast_table_floats(K));  // stands in for the warp's shared-memory prior table
     std::vector<std::thread> th;
@@ -74,7 +76,10 @@ static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *ta
             EmulWarp w{ l, &sh };
             for (int t = 0; t < n_tasks; t++) {
                 if (vargcp) pairhmm_fast_task<EmulWarp, K, GM_VAR>(w, AL, t, tab.data());
-                else if (AL.gcp_constant == 10 && AL.cf_uniform == 0.1f) pairhmm_fast_task<EmulWarp, K, GM_Q10>(w, AL, t, tab.data());
+                else if (AL.gcp_constant == 10 && AL.cf_uniform == 0.1f) {
+                    if (AL.task_haps) pairhmm_fast_task<EmulWarp, K, GM_Q10, true>(w, AL, t, tab.data());
+                    else pairhmm_fast_task<EmulWarp, K, GM_Q10>(w, AL, t, tab.data());
+                }
                 else pairhmm_fast_task<EmulWarp, K, GM_UNIFORM>(w, AL, t, tab.data());
             }
         });
@@ -108,13 +113,21 @@ static void run_plain(const PairHmmArgs &A, int n) {
     for (auto &t : th) t.join();
 }
 
+// number of warp tasks build_prep makes for a batch (split_target_tasks as in build_prep); lets the tests see the split
+extern "C" int64_t emul_count_fast_tasks(const lk_pairhmm_batch *b, int64_t split_target_tasks) {
+    HostPrep P;
+    build_prep(b, 0, b->n_regions, 0, true, P, split_target_tasks);
+    return (int64_t)P.tasks.size();
+}
+
 // Same contract as lk_pairhmm_batch_host, executed by the emulator.  force_k > 0 pins K; force_f64 sends
 // every pair through the plain-form pass.  n_rescued (may be null) receives the f64-pass pair count.
 extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, int force_k, int force_f64,
                                   double *out, uint8_t *flags, int32_t *n_rescued) {
     const int64_t n_reads = b->region_read_start[b->n_regions], n_haps = b->region_hap_start[b->n_regions];
     HostPrep P;
-    build_prep(b, 0, b->n_regions, force_k, !force_f64, P);
+    const char *split = getenv("LK_EMUL_SPLIT_TASKS");  // exercise the haplotype-axis task split of small launches
+    build_prep(b, 0, b->n_regions, force_k, !force_f64, P, split ? atoll(split) : 0);
     if (force_k == -4) { HostPrep Q; build_prep(b, 0, b->n_regions, -1, !force_f64, Q); P = Q; }
     ModelTables T;
     build_model_tables(T);
@@ -184,7 +197,7 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
         for (const auto &L : P.launches) {
             const WarpTask *t = P.tasks.data() + L.first_task;
             switch (L.K) {
-#define LK_CASE(KV, MINB) case KV: run_fast_tasks<KV>(A, vargcp, t, L.n_tasks); break;
+#define LK_CASE(KV, MINB) case KV: run_fast_tasks<KV>(A, vargcp, t, L.n_tasks, L.split ? P.task_haps.data() + L.first_task : nullptr); break;
                 LK_FAST_K_TABLE(LK_CASE)
 #undef LK_CASE
                 default: return -1;

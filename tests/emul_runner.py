@@ -38,6 +38,17 @@ def pairhmm_batch(batch, use_tristate=True, force_k=0, force_f64=False):
     return out, flags, n_resc.value
 
 
+def count_fast_tasks(batch, split_target_tasks=0):
+    """Warp tasks host_prep builds for the batch (to see the haplotype-axis split of small launches)."""
+    if isinstance(batch, dict):
+        batch = PairHmmBatch.from_dict(batch)
+    L = lib()
+    L.emul_count_fast_tasks.restype = C.c_int64
+    L.emul_count_fast_tasks.argtypes = [C.POINTER(_lib.PairHmmBatchStruct), C.c_int64]
+    s = batch.as_struct()
+    return int(L.emul_count_fast_tasks(C.byref(s), int(split_target_tasks)))
+
+
 def sw_batch(ref_off, refs, alt_off, alts, params, strategy, max_ops=64, force_k=0):
     from oracle.lk_oracle import SW_STRATEGY
     L = lib()

@@ -68,6 +68,46 @@ def test_region_layout_and_packing():
         assert np.max(np.abs(got - exp) / np.abs(exp)) < 1e-4
 
 
+@pytest.mark.parametrize("gcp", [10, 12])
+def test_small_launches_split_along_the_haplotype_axis(monkeypatch, gcp):
+    # host_prep cuts the warp tasks of a small launch into haplotype slices (>= 4 haplotypes each) so a few regions still
+    # fill the GPU; every pair must come out bit-for-bit as from the whole-region tasks, in the same out[r*A + h] slots.
+    # gcp = 10 runs the SPLIT instantiation; any other gcp runs the split task list through the whole-region routine
+    # (each task then sweeps all haplotypes: redundant, never wrong).
+    rng = np.random.default_rng(11)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    rrs, rhs, roff, hoff = [0], [0], [0], [0]
+    rb, rq, ri, rd, hb = [], [], [], [], []
+    for g, n_haps in enumerate((13, 3, 9, 16)):
+        base = rng.choice(acgt, 90 + 10 * g)
+        for _ in range(n_haps):
+            h = base.copy()
+            h[rng.integers(0, len(h), 2)] = rng.choice(acgt, 2)
+            hb.append(h); hoff.append(hoff[-1] + len(h))
+        rhs.append(rhs[-1] + n_haps)
+        for _ in range(5):
+            n = int(rng.integers(20, 80))
+            s0 = int(rng.integers(0, len(base) - n))
+            rb.append(base[s0:s0 + n].copy()); rq.append(rng.integers(6, 41, n).astype(np.uint8))
+            ri.append(np.full(n, 45, np.uint8)); rd.append(np.full(n, 45, np.uint8))
+            roff.append(roff[-1] + n)
+        rrs.append(rrs[-1] + 5)
+    batch = dict(region_read_start=np.array(rrs), region_hap_start=np.array(rhs), read_off=np.array(roff),
+                 hap_off=np.array(hoff), read_bases=np.concatenate(rb), read_qual=np.concatenate(rq),
+                 read_ins=np.concatenate(ri), read_del=np.concatenate(rd),
+                 read_gcp=np.full(roff[-1], gcp, np.uint8), hap_bases=np.concatenate(hb))
+    # the split really happens: more tasks than the whole-region packing (one launch per K class, each cut on its own)
+    assert E.count_fast_tasks(batch) < E.count_fast_tasks(batch, 7) <= E.count_fast_tasks(batch, 1000)
+    monkeypatch.delenv("LK_EMUL_SPLIT_TASKS", raising=False)
+    whole, _, _ = E.pairhmm_batch(batch)
+    exp = O.pairhmm_batch(batch)
+    assert np.max(np.abs(whole - exp) / np.abs(exp)) < 1e-4
+    for target in ("7", "1000"):
+        monkeypatch.setenv("LK_EMUL_SPLIT_TASKS", target)
+        got, flags, n_resc = E.pairhmm_batch(batch)
+        assert n_resc == 0 and np.array_equal(got, whole)
+
+
 def test_analytic_families_subset():
     cases = PC.basic_likelihood_cases(extensive=True)[::97] + PC.mismatch_sweep_cases()[::5] + PC.all_matching_cases()
     batch = PC.pack_cases(cases)
