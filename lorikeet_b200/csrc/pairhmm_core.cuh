@@ -554,16 +554,22 @@ LK_UNROLL_N(LK_BAND_UNROLL)
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
                 }
             }
-            if (s <= s_last) {
-                acc = fmaf(M[K - 1], wM, acc);
-                acc = fmaf(I[K - 1], wI, acc);
-                if (writes && s > lane) {
+            // columns past the haplotype read the guard band of the encoded haplotype (an ordinary table slice), so what a lane
+            // holds there is finite: the sum is gated by zeroed weights and the boundary store by a predicate instead of a
+            // divergent block
+            {
+                const bool in_cols = s <= s_last;
+                acc = fmaf(M[K - 1], in_cols ? wM : 0.f, acc);
+                acc = fmaf(I[K - 1], in_cols ? wI : 0.f, acc);
+                if (writes && in_cols && s > lane) {
                     Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi;
                     bout[s - lane] = v;
                 }
             }
-            // ---- block-floating-point upkeep: at the lane's first column and every 16 columns re-centre the strip ----
-            if ((s & 15) == 0 || s == lane + 1) {
+            // ---- block-floating-point upkeep: re-centre the strip every 16 columns, and at every step while lanes are still
+            // starting (a lane's first column is computed in the sender's scale and must be re-centred at once; testing
+            // `s <= 32` instead of `s == lane + 1` keeps the branch warp-uniform) ----
+            if ((s & 15) == 0 || s <= 32) {
                 float m = fmaxf(acc, fmaxf(Mu, fmaxf(Iu, Du)));  // the running sum and what is arriving must stay in range too
 #pragma unroll
                 for (int k = 0; k < K; k++) m = fmaxf(m, fmaxf(M[k], I[k]));
