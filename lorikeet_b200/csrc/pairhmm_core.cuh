@@ -523,11 +523,9 @@ LK_UNROLL_N(LK_BAND_UNROLL)
                 const Bnd4 v = cur_b;
                 cur_b = bin[s + 1 <= H ? s + 1 : H];
                 w.prefetch(bin + (s + 32 <= H ? s + 32 : H));
-                if (feeds) {
-                    const bool in = s <= H;
-                    Mu = in ? v.m : 0.f; Iu = in ? v.i : 0.f; Du = in ? v.d : 0.f;
-                    xi_up = in ? v.xi : xi_up;
-                }
+                // past the last column (s > H) the clamped index repeats element H: finite values that only ever reach
+                // columns beyond the haplotype, which nothing reads
+                if (feeds) { Mu = v.m; Iu = v.i; Du = v.d; xi_up = v.xi; }
             }
             // ---- bring what the row above sent into my exponent ----
             // A lane that has not started adopts the sender's exponent.  Afterwards the lane's scale is chosen at its
