@@ -42,3 +42,32 @@ def test_calculate_cigar_matches_host_path_on_haplotype_like_pairs(ctx):
         got = ctx.calculate_cigar_batch(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, strategy, max_ops=1024)
         exp = [calculate_cigar_host(r, a, strategy=strategy) for r, a in pairs]
         assert got == exp
+
+
+def test_large_batch_multithreaded_host_path_matches_small_batches(ctx):
+    # above 2048 pairs the per-pair host work of lk_calculate_cigar_batch (shortcuts, N padding, trim / left-align) is
+    # spread over the host cores and the Smith-Waterman call runs as a multi-chunk pipeline: every CIGAR must equal what the
+    # same pairs give in small single-threaded batches, including pairs the equal-length shortcut answers without SW
+    from lorikeet_b200 import synth
+    n = 9000
+    ro, refs, ao, alts = synth.sw_pairs(n, first_pair=40000, pad=0)
+    refs = refs.copy()
+    # every 50th pair: alternate := reference with one mismatch, so the <= 2-mismatch shortcut path is in the mix
+    alts = alts.copy()
+    pieces_r, pieces_a = [], []
+    for i in range(n):
+        r = refs[ro[i]:ro[i + 1]]
+        a = alts[ao[i]:ao[i + 1]]
+        if i % 50 == 0:
+            a = r.copy()
+            a[len(a) // 2] = ord("A") if a[len(a) // 2] != ord("A") else ord("C")
+        pieces_r.append(r); pieces_a.append(a)
+    ro2, refs2, ao2, alts2 = SC.pack(list(zip(pieces_r, pieces_a)))
+    big = ctx.calculate_cigar_batch(ro2, refs2, ao2, alts2, SC.NEW_SW_PARAMETERS, "InDel")
+    assert len(big) == n and sum(c is None for c in big) < n // 10
+    for lo in range(0, n, 1500):
+        hi = min(lo + 1500, n)
+        r_off = ro2[lo:hi + 1] - ro2[lo]
+        a_off = ao2[lo:hi + 1] - ao2[lo]
+        small = ctx.calculate_cigar_batch(r_off, refs2[ro2[lo]:ro2[hi]], a_off, alts2[ao2[lo]:ao2[hi]], SC.NEW_SW_PARAMETERS, "InDel")
+        assert small == big[lo:hi]

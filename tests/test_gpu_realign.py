@@ -71,3 +71,45 @@ def test_random_regions_match_host_pieces_with_oracle_sw():
         best, info, cigars, pos = ctx.realign_reads_batch(b)
     for i, (epos, ecig) in enumerate(expect):
         assert (int(pos[i]), cigars[i]) == (epos, ecig), i
+
+
+def test_large_batch_multithreaded_host_path_matches_small_batch():
+    # above 2048 reads the gather and the CIGAR composition of lk_realign_reads_batch run on several host threads: tiling
+    # one small set of regions many times must give, tile by tile, exactly what the small (single-threaded) batch gives
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    rrs, rhs, vals, haps, hcig, hstart, reads, rcig, rstart = [0], [0], [], [], [], [], [], [], []
+    for g in range(12):
+        ref = rng.choice(acgt, 200)
+        k, d = int(rng.integers(40, 150)), int(rng.integers(1, 6))
+        region_haps = [ref, np.concatenate([ref[:k], ref[k + d:]]), np.concatenate([ref[:k], rng.choice(acgt, d), ref[k:]])]
+        region_cigs = ["200M", "%dM%dD%dM" % (k, d, 200 - k - d), "%dM%dI%dM" % (k, d, 200 - k)]
+        R = 9
+        V = -rng.random((3, R)) * 5
+        for r in range(R):
+            a = int(np.argmax(V[:, r]))
+            V[a, r] += 1.0
+            h = region_haps[a]
+            s = int(rng.integers(0, len(h) - 70))
+            rd = h[s:s + 70].copy()
+            rd[int(rng.integers(0, 70))] = rng.choice(acgt)
+            reads.append(rd); rcig.append("70M")
+        haps += region_haps; hcig += region_cigs; hstart += [0, 0, 0]
+        vals.append(V.ravel()); rstart.append(1000 * (g + 1))
+        rrs.append(len(reads)); rhs.append(len(haps))
+    small = lk.RealignBatch(rrs, rhs, np.concatenate(vals), haps, hcig, hstart, reads, rcig, rstart)
+    tiles = 24  # 24 x 108 reads = 2592 > 2048
+    t_rrs, t_rhs = [0], [0]
+    for t in range(tiles):
+        t_rrs += [t * len(reads) + x for x in rrs[1:]]
+        t_rhs += [t * len(haps) + x for x in rhs[1:]]
+    big = lk.RealignBatch(t_rrs, t_rhs, np.concatenate(vals * tiles), haps * tiles, hcig * tiles, hstart * tiles, reads * tiles,
+                          rcig * tiles, rstart * tiles)
+    with lk.Context(0) as ctx:
+        sb, si, sc, sp = ctx.realign_reads_batch(small)
+        bb, bi, bc, bp = ctx.realign_reads_batch(big)
+    n = len(reads)
+    assert len(bc) == n * tiles and any(c is not None for c in sc)
+    for t in range(tiles):
+        assert np.array_equal(bb[t * n:(t + 1) * n], sb) and np.array_equal(bi[t * n:(t + 1) * n], si)
+        assert np.array_equal(bp[t * n:(t + 1) * n], sp) and bc[t * n:(t + 1) * n] == sc
