@@ -319,6 +319,18 @@ void lk_batcher_destroy(lk_batcher *b);
 lk_status lk_batcher_submit(lk_batcher *b, const lk_pairhmm_batch *region, const uint8_t *read_mapq,
                             int32_t ref_allele_index, double *values, uint8_t *keep_or_flags /* may be NULL */);
 void lk_batcher_stats(lk_batcher *b, int64_t *n_batches, int64_t *n_regions);
+/*
+ * Non-blocking form: queue a region and return at once with a ticket; lk_batcher_wait blocks until that region's
+ * results are in `values` / `keep_or_flags`, returns its status and releases the ticket.  Lets one worker keep several
+ * regions in flight (submit the likelihoods of region i+1.. while genotyping region i), which is what fills the GPU when
+ * there are fewer worker threads than ~100.  The region's arrays and the output buffers must stay valid until the wait
+ * returns; every ticket must be waited on exactly once, before lk_batcher_destroy.
+ */
+typedef struct lk_ticket lk_ticket;
+lk_status lk_batcher_submit_async(lk_batcher *b, const lk_pairhmm_batch *region, const uint8_t *read_mapq,
+                                  int32_t ref_allele_index, double *values, uint8_t *keep_or_flags /* may be NULL */,
+                                  lk_ticket **out_ticket);
+lk_status lk_batcher_wait(lk_batcher *b, lk_ticket *ticket);
 
 #ifdef __cplusplus
 }

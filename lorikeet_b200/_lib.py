@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = [
     "lk_engine_modify_read_qualities", "lk_engine_modify_read_qualities_device", "lk_engine_compute_read_likelihoods",
     "lk_realign_reads_batch", "lk_best_alleles_breaking_ties", "lk_realign_finish", "lk_cigar_apply_to_cigar",
     "lk_cigar_append_clipped_elements", "lk_read_start_on_reference_haplotype",
-    "lk_batcher_create", "lk_batcher_destroy", "lk_batcher_submit", "lk_batcher_stats",
+    "lk_batcher_create", "lk_batcher_destroy", "lk_batcher_submit", "lk_batcher_stats", "lk_batcher_submit_async",
+    "lk_batcher_wait",
 ]
 
 
@@ -181,6 +182,10 @@ def load():
     L.lk_batcher_destroy.argtypes = [vp]
     L.lk_batcher_submit.restype = C.c_int
     L.lk_batcher_submit.argtypes = [vp, bp, u8p, C.c_int32, f64p, u8p]
+    L.lk_batcher_submit_async.restype = C.c_int
+    L.lk_batcher_submit_async.argtypes = [vp, bp, u8p, C.c_int32, f64p, u8p, C.POINTER(vp)]
+    L.lk_batcher_wait.restype = C.c_int
+    L.lk_batcher_wait.argtypes = [vp, vp]
     L.lk_batcher_stats.restype = None
     L.lk_batcher_stats.argtypes = [vp, i64p, i64p]
     # introspection helpers (not part of the public header)

@@ -191,6 +191,26 @@ class RegionBatcher:
         self.ctx._check(st)
         return values, aux
 
+    def submit_async(self, region, read_mapq=None, ref_allele_index=0):
+        """Non-blocking (lk_batcher_submit_async): returns a ticket for wait(); several may be in flight per thread."""
+        assert region.n_regions == 1
+        values = np.empty(region.n_pairs, dtype=np.float64)
+        aux = np.zeros(region.n_reads if self.engine is not None else region.n_pairs, dtype=np.uint8)
+        mapq = None if read_mapq is None else np.ascontiguousarray(read_mapq, dtype=np.uint8)
+        s = region.as_struct()
+        t = C.c_void_p()
+        st = self._L.lk_batcher_submit_async(self._h, C.byref(s), mapq.ctypes.data_as(_lib.u8p) if mapq is not None else None,
+                                             int(ref_allele_index), values.ctypes.data_as(_lib.f64p), aux.ctypes.data_as(_lib.u8p),
+                                             C.byref(t))
+        self.ctx._check(st)
+        return (t, values, aux, region, s, mapq)  # keeps every buffer the library reads or writes alive until wait()
+
+    def wait(self, ticket):
+        """Blocks until the ticket's region is done; returns (values, keep) / (log10 likelihoods, flags) as submit()."""
+        t, values, aux = ticket[0], ticket[1], ticket[2]
+        self.ctx._check(self._L.lk_batcher_wait(self._h, t))
+        return values, aux
+
     def stats(self):
         a, b = C.c_int64(0), C.c_int64(0)
         self._L.lk_batcher_stats(self._h, C.byref(a), C.byref(b))

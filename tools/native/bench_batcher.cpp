@@ -2,7 +2,8 @@
 // lk_batcher (what Lorikeet's Rayon workers would do through the Rust binding, assembly_region_walker.rs:140-277),
 // next to the same regions handed to lk_engine_compute_read_likelihoods in one call.
 //   g++ -O2 -std=c++17 -I include tools/native/bench_batcher.cpp -L lorikeet_b200 -llorikeet_b200 -lpthread -o bench_batcher
-//   LD_LIBRARY_PATH=lorikeet_b200 ./bench_batcher [regions=4000] [threads=32] [max_regions=512] [max_wait_us=200]
+//   LD_LIBRARY_PATH=lorikeet_b200 ./bench_batcher [regions=4000] [threads=32] [max_regions=512] [max_wait_us=200] [in_flight=1]
+// in_flight > 1: every thread keeps that many regions queued through lk_batcher_submit_async / lk_batcher_wait
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -23,6 +24,7 @@ int main(int argc, char **argv) {
     const int T = argc > 2 ? atoi(argv[2]) : 32;
     const int max_regions = argc > 3 ? atoi(argv[3]) : 512;
     const int max_wait_us = argc > 4 ? atoi(argv[4]) : 200;
+    const int depth = argc > 5 ? std::max(1, atoi(argv[5])) : 1;
     lk_synth_params p;
     memset(&p, 0, sizeof p);
     p.seed_base = 0x4C4B0000; p.n_reads = 64; p.read_len = 150; p.n_haps = 16; p.hap_len = 300; p.min_edits = 1; p.max_edits = 4;
@@ -69,21 +71,31 @@ int main(int argc, char **argv) {
         std::vector<std::thread> pool;
         for (int t = 0; t < T; t++)
             pool.emplace_back([&]() {
+                // `depth` one-region views of the big arrays (offsets rebased to the region, arenas advanced to its first
+                // byte), kept alive until their tickets are waited on
+                struct Slot { int64_t rs1[2], hs1[2]; std::vector<int64_t> ro, ho; lk_pairhmm_batch one; lk_ticket *t; };
+                std::vector<Slot> slots((size_t)depth);
                 for (;;) {
-                    const int64_t g = next.fetch_add(1);
-                    if (g >= G) break;
-                    // a one-region view of the big arrays: offsets rebased to the region, arenas advanced to its first byte
-                    const int64_t r0 = rrs[g], nr = rrs[g + 1] - r0, h0 = rhs[g], nh = rhs[g + 1] - h0;
-                    int64_t rs1[2] = { 0, nr }, hs1[2] = { 0, nh };
-                    std::vector<int64_t> ro(nr + 1), ho(nh + 1);
-                    for (int64_t i = 0; i <= nr; i++) ro[i] = roff[r0 + i] - roff[r0];
-                    for (int64_t i = 0; i <= nh; i++) ho[i] = hoff[h0 + i] - hoff[h0];
-                    lk_pairhmm_batch one;
-                    memset(&one, 0, sizeof one);
-                    one.n_regions = 1; one.region_read_start = rs1; one.region_hap_start = hs1; one.read_off = ro.data();
-                    one.read_bases = rb.data() + roff[r0]; one.read_qual = rq.data() + roff[r0]; one.read_ins = ri.data() + roff[r0];
-                    one.read_del = rd.data() + roff[r0]; one.gcp_constant = 10; one.hap_off = ho.data(); one.hap_bases = hb.data() + hoff[h0];
-                    if (lk_batcher_submit(bt, &one, mapq.data() + r0, 0, viab.data() + pair_base[g], keep_b.data() + r0) != LK_OK) bad++;
+                    int used = 0;
+                    for (; used < depth; used++) {
+                        const int64_t g = next.fetch_add(1);
+                        if (g >= G) break;
+                        Slot &S = slots[(size_t)used];
+                        const int64_t r0 = rrs[g], nr = rrs[g + 1] - r0, h0 = rhs[g], nh = rhs[g + 1] - h0;
+                        S.rs1[0] = 0; S.rs1[1] = nr; S.hs1[0] = 0; S.hs1[1] = nh;
+                        S.ro.resize(nr + 1); S.ho.resize(nh + 1);
+                        for (int64_t i = 0; i <= nr; i++) S.ro[i] = roff[r0 + i] - roff[r0];
+                        for (int64_t i = 0; i <= nh; i++) S.ho[i] = hoff[h0 + i] - hoff[h0];
+                        memset(&S.one, 0, sizeof S.one);
+                        S.one.n_regions = 1; S.one.region_read_start = S.rs1; S.one.region_hap_start = S.hs1; S.one.read_off = S.ro.data();
+                        S.one.read_bases = rb.data() + roff[r0]; S.one.read_qual = rq.data() + roff[r0]; S.one.read_ins = ri.data() + roff[r0];
+                        S.one.read_del = rd.data() + roff[r0]; S.one.gcp_constant = 10; S.one.hap_off = S.ho.data(); S.one.hap_bases = hb.data() + hoff[h0];
+                        S.t = nullptr;
+                        if (lk_batcher_submit_async(bt, &S.one, mapq.data() + r0, 0, viab.data() + pair_base[g], keep_b.data() + r0, &S.t) != LK_OK) bad++;
+                    }
+                    for (int i = 0; i < used; i++)
+                        if (slots[(size_t)i].t && lk_batcher_wait(bt, slots[(size_t)i].t) != LK_OK) bad++;
+                    if (used < depth) break;
                 }
             });
         for (auto &th : pool) th.join();
@@ -92,7 +104,7 @@ int main(int argc, char **argv) {
     }
     int64_t nb = 0, nr = 0;
     lk_batcher_stats(bt, &nb, &nr);
-    printf("batcher %2d threads  regions=%lld  %.1f ms  %.0f GCUPS  (%.1f regions per launch)\n", T, (long long)G, best, n_cells / best / 1e6, (double)nr / (double)nb);
+    printf("batcher %2d threads x %d in flight  regions=%lld  %.1f ms  %.0f GCUPS  (%.1f regions per launch)\n", T, depth, (long long)G, best, n_cells / best / 1e6, (double)nr / (double)nb);
     const bool same = memcmp(direct.data(), viab.data(), n_pairs * 8) == 0 && memcmp(keep_d.data(), keep_b.data(), R) == 0;
     printf("batcher results %s the one-call results\n", same ? "are bit-identical to" : "DIFFER from");
     lk_batcher_destroy(bt);
