@@ -1,7 +1,8 @@
 /*
  * lorikeet_b200_synth.h — deterministic synthetic workload generators for the configurations
- * BASELINE.json names.  Host-only helpers living in the same shared library; used by
- * bench.py (both arms), the tests and __graft_entry__.smoke().  Not part of the drop-in boundary.
+ * BASELINE.json names.  Host-only helpers built into their OWN shared library
+ * (liblorikeet_b200_synth.so, no CUDA dependency); used by bench.py (both arms), the tests and
+ * __graft_entry__.smoke().  Not part of the drop-in boundary.
  *
  * Every region / pair draws from its own xoshiro256** stream seeded by splitmix64(seed_base + id), so any
  * sub-range of ids can be generated independently (multi-GPU sharding generates only its own shard).

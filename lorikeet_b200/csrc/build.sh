@@ -15,7 +15,7 @@ for f in pairhmm_kernels.cu sw_kernels.cu engine_kernels.cu lk_api.cu lk_sw_api.
     $NVCC $FLAGS -c "$f" -o "$o" & pids+=($!)
   fi
 done
-for f in host_model.cpp host_prep.cpp host_engine.cpp host_synth.cpp host_cigar.cpp host_batcher.cpp; do
+for f in host_model.cpp host_prep.cpp host_preops.cpp host_engine.cpp host_cigar.cpp host_batcher.cpp; do
   [ -f "$f" ] || continue
   o=$BUILD/${f%.cpp}.o
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find . -maxdepth 1 -name '*.h' -newer "$o" -print -quit)" ] || [ ../../include/lorikeet_b200.h -nt "$o" ]; then
@@ -23,5 +23,13 @@ for f in host_model.cpp host_prep.cpp host_engine.cpp host_synth.cpp host_cigar.
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
+rm -f $BUILD/host_synth.o  # generators moved to their own library
 $NVCC -shared -o $OUT $BUILD/*.o -Xcompiler -fPIC -lcudart_static -lpthread -ldl -lrt
 echo "built $OUT"
+# synthetic-workload generators (bench / tests only): a separate library with no CUDA dependency, so the reference arm
+# of bench.py can generate inputs without mapping the product library
+SYNTH_OUT=${LK_SYNTH_OUT:-../liblorikeet_b200_synth.so}
+if [ ! -f "$SYNTH_OUT" ] || [ host_synth.cpp -nt "$SYNTH_OUT" ] || [ host_preops.cpp -nt "$SYNTH_OUT" ] || [ ../../include/lorikeet_b200_synth.h -nt "$SYNTH_OUT" ]; then
+  g++ -O3 -std=c++17 -fPIC -shared -Wall -Wno-unknown-pragmas -o "$SYNTH_OUT" host_synth.cpp host_preops.cpp -lpthread
+  echo "built $SYNTH_OUT"
+fi

@@ -9,6 +9,7 @@
 
 #include "../../include/lorikeet_b200.h"
 #include "host_prep.h"
+#include "host_preops.h"
 
 struct DevBuf {
     void *p = nullptr;
@@ -96,8 +97,6 @@ struct lk_engine_hook {
     uint8_t *keep;                     // out, per read, may be null
     uint8_t pcr_cache[101];
 };
-// initialize_pcr_error_model (...engine.rs:169-193): cache[n] for repeat lengths 0..100 (host_engine.cpp)
-void lk_engine_fill_pcr_cache(const lk_engine_args *args, uint8_t cache[101]);
 lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags, const lk_engine_hook *hook);
 
 lk_status lk_fail(lk_ctx *ctx, lk_status st, const std::string &msg);

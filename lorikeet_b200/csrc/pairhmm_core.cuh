@@ -23,6 +23,7 @@
 // index logic where no GPU is present.  (b) is test tooling only and is never linked into the product.
 #pragma once
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -406,8 +407,31 @@ LK_DEV float pow2i(int e) {  // 2^e for e in [-126, 127]
 #endif
 }
 
+// Floats of per-warp shared memory pairhmm_band_pair<K> needs: the prior table plus a 32-element ring of boundary
+// elements (the previous band's last row, staged 32 columns at a time).
+constexpr int BAND_RING = 32;
+struct LeanTag { static constexpr bool value = true; };
+struct GenericTag { static constexpr bool value = false; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int band_smem_floats(int K) { return fast_table_floats(K) + BAND_RING * 4; }
+
+// Structure of one band (R rows of the read against all H columns):
+//   * steps 1..32 ("start-up": lanes come alive one by one; upkeep at every step) and the last steps, from the first
+//     column block in which lane 0 runs past the haplotype, go through the GENERIC step (column-range gates);
+//   * everything in between goes in BLOCKS of 16 steps through the LEAN step, in which every lane's column is inside
+//     [1, H] by construction, so nothing is gated, and all block-floating-point upkeep happens once per block:
+//     the checkpoint (re-centre the strip), ONE exchange of exponents (the factor `al` that brings the row above
+//     into my scale stays in a register for the 16 receipts of the block), and every second block the staging of the
+//     next 32 boundary elements of the previous band into the warp's shared-memory ring (one coalesced 16-byte load per
+//     lane; lane 0 then receives them like values from a lane above it, see `stage`).
+//   A lean step is: 1 LDG.U8 (next column's table slice) + KQ LDS.128 + K x (FMUL + 4 FFMA) + 2 FFMA (running sum)
+//   + 3 SHFL + 3 FMUL (re-alignment) + predicated LDS.128 (lane 0's feed) / STG.128 (last lane's boundary row).
+// Invariant: at the start of a step everything a lane holds (M, I, D, Mu.., Md.., acc, kinit) is in its own scale xi,
+// and `al` = 2^(xi - xi_up) with xi_up the current exponent of the lane above (lane 0: of the staged ring).
 template <class W, int K, bool Q10 = false>
-LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, Bnd4 *scratch, float *tab) {
+LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, Bnd4 *scratch, float *tab, Bnd4 *ring) {
     constexpr int KQ = (K + 3) / 4;
     const int lane = w.lane();
     const int64_t ro = A.read_off[read];
@@ -435,6 +459,7 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
     const float initH = ldexpf(1.0f, BAND_INIT_EXP) / (float)H;
     float acc_final = 0.f;
     int xi_final = 0;
+    const bool feeds = (lane == 0);
 
     for (int band = 0; band < n_bands; band++) {
         const int row0 = band * BAND;
@@ -487,55 +512,76 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         for (int k = K; k < KQ * 4; k++)
 #pragma unroll
             for (int sl = 0; sl < N_PRIOR_SLICES; sl++) tab[(((sl * KQ) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = 0.f;
+        if (band == 0) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = 0.f; z.xi = 0; ring[lane] = z; }  // band 0: row 0 feeds zeros
         w.sync();
         if (last_band && lane == lanes - 1) {
             const int kstar = (rows - 1) - lane * K;
             if (kstar == K - 1) { wM = 1.f; wI = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1)); }
             else { wM = 0.f; wI = 1.f; }
         }
-        const float kinit0 = (band == 0) ? kcoef * initH : 0.f;  // only row 1 (band 0, lane 0) has kcoef != 0
 
         float M[K], I[K], D[K];
 #pragma unroll
         for (int k = 0; k < K; k++) { M[k] = 0.f; I[k] = 0.f; D[k] = 0.f; }
-        float Mu = 0.f, Iu = 0.f, Du = 0.f, Md = 0.f, Id = 0.f, Dd = 0.f, acc = 0.f, kinit = kinit0;
-        int xi = 0, xi_up = 0;  // my exponent; exponent of the values in Mu/Iu/Du
+        float Mu = 0.f, Iu = 0.f, Du = 0.f, Md = 0.f, Id = 0.f, Dd = 0.f, acc = 0.f;
+        float kinit = (band == 0) ? kcoef * initH : 0.f;  // only row 1 (band 0, lane 0) has kcoef != 0
+        float al = 1.f;
+        int xi = 0, xi_up = 0;  // my exponent; exponent of the lane above (lane 0: of the ring, xc)
         const int n_steps = H + lanes - 1;
         const int s_last = H + lane;
-        const bool feeds = (lane == 0) && (band > 0);
         const bool writes = !last_band && (lane == lanes - 1);
-        if (writes) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = 0.f; z.xi = 0; bout[0] = z; }
-        Bnd4 cur_b;  // boundary element of the column lane 0 works on next
-        cur_b.m = 0.f; cur_b.i = 0.f; cur_b.d = 0.f; cur_b.xi = 0;
-        if (band > 0) cur_b = bin[1 <= H ? 1 : H];
+        Bnd4 *bw = bout - lane;  // bw[s] = boundary element of my column at step s
+        if (band > 0 && lane == 0) {  // column 1 of the row above: adopted as it is (al = 1)
+            const Bnd4 v = bin[1];
+            Mu = v.m; Iu = v.i; Du = v.d; xi = v.xi;
+        }
 
+        // ring <- boundary elements of columns c0 + 2 .. c0 + 33 (what lane 0 receives at the end of steps c0 + 1 .. c0 + 32):
+        // a plain coalesced copy.  No re-scaling is needed: the lane that wrote them (lane 31 of the previous band, at step
+        // column + 31) changes its exponent only at ITS upkeep steps (s = 1 mod 16 once past the start-up), i.e. between
+        // columns 16j + 1 and 16j + 2 -- exactly where lane 0 of this band, which receives column s + 1 at the end of step
+        // s, has its own upkeep.  The 16 elements one block receives therefore share one exponent, like 16 receipts
+        // from a lane above.
+        auto stage = [&](int c0) {
+            const int c = c0 + 2 + lane;
+            Bnd4 e = bin[c <= H ? c : H];
+            if (c > H) { e.m = 0.f; e.i = 0.f; e.d = 0.f; }
+            w.prefetch(bin + (c + 32 <= H ? c + 32 : H));
+            w.sync();  // every lane is past its last read of the previous chunk
+            ring[lane] = e;
+            w.sync();
+        };
+        // checkpoint + exchange at the START of a step (every step while lanes are starting, s <= 32; then when s = 1 mod 16):
+        // re-centre what I hold into [2^-20, 2^60] (looking at the running sum and at what has just arrived too), then learn
+        // the exponent of the lane above and set `al`.
+        auto upkeep = [&](int s) {
+            if (band > 0 && ((s - 1) & 31) == 0) stage(s - 1);
+            float m = fmaxf(acc, fmaxf(Mu, fmaxf(Iu, Du)));
+#pragma unroll
+            for (int k = 0; k < K; k++) m = fmaxf(m, fmaxf(M[k], I[k]));
+            if (m > 0.f && (m < 9.5367431640625e-07f || m > 1.152921504606847e18f)) {  // outside [2^-20, 2^60]
+                int sh = 20 - ilogbf(m);
+                sh = sh > 120 ? 120 : (sh < -120 ? -120 : sh);
+                const float f = pow2i(sh);
+#pragma unroll
+                for (int k = 0; k < K; k++) { M[k] *= f; I[k] *= f; D[k] *= f; }
+                Mu *= f; Iu *= f; Du *= f; Md *= f; Id *= f; Dd *= f; acc *= f; kinit *= f;
+                xi += sh;
+            }
+            xi_up = w.shfl_up1(xi);
+            if (lane == 0) xi_up = (band > 0) ? ring[(s - 1) & 31].xi : xi;  // exponent of what this block receives
+            if (s <= lane) xi = xi_up;  // not started yet (holds zeros only): adopt the sender's scale
+            al = pow2i(xi - xi_up);
+        };
         int slice_ahead = (int)w.ldg(hp + 1);
-LK_UNROLL_N(LK_BAND_UNROLL)
-        for (int s = 1; s <= n_steps; ++s) {
+        // LEAN = true: every lane's column is inside [1, H] (no gates); false: generic step
+        auto step = [&](int s, const Bnd4 *rp, auto lean_tag) {
+            constexpr bool LEAN = decltype(lean_tag)::value;
             const float *trow = tab + (slice_ahead * KQ * 32 + lane) * 4;
             slice_ahead = (int)w.ldg(hp + s + 1);  // next step's column, fetched ahead of the LDS address it forms
             float sel[KQ * 4];
 #pragma unroll
             for (int q = 0; q < KQ; q++) w.lds4(sel + 4 * q, trow + q * 128);
-            // row above lane 0 = last row of the previous band.  Every lane reads the same element (one broadcast
-            // transaction, no divergence) one step AHEAD of its use, so the L1/L2 latency hides behind a whole step.
-            if (band > 0) {
-                const Bnd4 v = cur_b;
-                cur_b = bin[s + 1 <= H ? s + 1 : H];
-                w.prefetch(bin + (s + 32 <= H ? s + 32 : H));
-                // past the last column (s > H) the clamped index repeats element H: finite values that only ever reach
-                // columns beyond the haplotype, which nothing reads
-                if (feeds) { Mu = v.m; Iu = v.i; Du = v.d; xi_up = v.xi; }
-            }
-            // ---- bring what the row above sent into my exponent ----
-            // A lane that has not started adopts the sender's exponent.  Afterwards the lane's scale is chosen at its
-            // checkpoints (below) from its own strip AND what is arriving, so incoming values sit in range: the top row of
-            // a strip is never more than ~1/tMI below the row that feeds it, and 16 columns cannot move either side by
-            // the 2^107 of headroom above the 2^20 centre.  (Should a value overflow all the same, the sum comes out
-            // inf / NaN and the pair is redone in f64.)
-            if (s <= lane + 1) xi = xi_up;
-            const float al = pow2i(xi - xi_up);
-            Mu *= al; Iu *= al; Du *= al;
             // ---- one column of the strip, rows top to bottom.  Row k reads row k-1 of the previous column (pm, pi, pd)
             // and, for I', row k-1 of this column (im, ii).  Written in this order the serial I' chain (one FFMA per row)
             // is spread evenly between the independent M'/D' work of the rows instead of being bunched at the end. ----
@@ -552,47 +598,49 @@ LK_UNROLL_N(LK_BAND_UNROLL)
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
                 }
             }
-            // columns past the haplotype read the guard band of the encoded haplotype (an ordinary table slice), so what a lane
-            // holds there is finite: the sum is gated by zeroed weights and the boundary store by a predicate instead of a
-            // divergent block
-            {
+            if (LEAN) {
+                acc = fmaf(M[K - 1], wM, acc);
+                acc = fmaf(I[K - 1], wI, acc);
+                if (writes) { Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi; bw[s] = v; }
+            } else {
+                // columns past the haplotype read the guard band of the encoded haplotype (an ordinary table slice), so what
+                // a lane holds there is finite: the sum is gated by zeroed weights and the boundary store by a predicate
                 const bool in_cols = s <= s_last;
                 acc = fmaf(M[K - 1], in_cols ? wM : 0.f, acc);
                 acc = fmaf(I[K - 1], in_cols ? wI : 0.f, acc);
-                if (writes && in_cols && s > lane) {
-                    Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi;
-                    bout[s - lane] = v;
-                }
-            }
-            // ---- block-floating-point upkeep: re-centre the strip every 16 columns, and at every step while lanes are still
-            // starting (a lane's first column is computed in the sender's scale and must be re-centred at once; testing
-            // `s <= 32` instead of `s == lane + 1` keeps the branch warp-uniform) ----
-            if ((s & 15) == 0 || s <= 32) {
-                float m = fmaxf(acc, fmaxf(Mu, fmaxf(Iu, Du)));  // the running sum and what is arriving must stay in range too
-#pragma unroll
-                for (int k = 0; k < K; k++) m = fmaxf(m, fmaxf(M[k], I[k]));
-                if (m > 0.f && (m < 9.5367431640625e-07f || m > 1.152921504606847e18f)) {  // outside [2^-20, 2^60]
-                    int sh = 20 - ilogbf(m);
-                    sh = sh > 120 ? 120 : (sh < -120 ? -120 : sh);
-                    const float f = pow2i(sh);
-#pragma unroll
-                    for (int k = 0; k < K; k++) { M[k] *= f; I[k] *= f; D[k] *= f; }
-                    Mu *= f; Iu *= f; Du *= f; acc *= f; kinit *= f;
-                    xi += sh;
-                }
+                if (writes && in_cols && s > lane) { Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi; bw[s] = v; }
             }
             Md = Mu; Id = Iu; Dd = Du;
-            Mu = w.shfl_up1(M[K - 1]);
-            Iu = w.shfl_up1(I[K - 1]);
-            Du = w.shfl_up1(D[K - 1]);
-            xi_up = w.shfl_up1(xi);
-            if (lane == 0) { Mu = 0.f; xi_up = xi; }  // band 0: virtual row 0; later bands: overwritten from scratch next step
+            float rm = w.shfl_up1(M[K - 1]), ri = w.shfl_up1(I[K - 1]), rd = w.shfl_up1(D[K - 1]);
+            if (feeds) { const Bnd4 v = *rp; rm = v.m; ri = v.i; rd = v.d; }  // row above lane 0: previous band's last row
+            Mu = rm * al; Iu = ri * al; Du = rd * al;
+        };
+
+        const int s_lean_end = (H >> 4) << 4;  // last step of the last block in which lane 0's column is still <= H
+        int s = 1, gen_end = n_steps < 32 ? n_steps : 32;
+        for (;;) {  // generic start-up, lean blocks, generic tail (one copy of the generic loop in the code)
+            for (; s <= gen_end; ++s) {
+                if (s <= 32 || (s & 15) == 1) upkeep(s);
+                step(s, ring + ((s - 1) & 31), GenericTag());
+            }
+            if (gen_end == n_steps) break;
+            while (s + 15 <= s_lean_end) {  // s = 1 (mod 16)
+                upkeep(s);
+                const Bnd4 *rp = ring + ((s - 1) & 31);
+LK_UNROLL_N(LK_BAND_UNROLL)
+                for (int u = 0; u < 16; ++u) step(s + u, rp + u, LeanTag());
+                s += 16;
+            }
+            gen_end = n_steps;
         }
         w.sync();  // the band's boundary row is visible to lane 0 of the next band
         if (last_band) { acc_final = w.shfl(acc, lanes - 1); xi_final = w.shfl(xi, lanes - 1); }
     }
 #if !defined(__CUDACC__) && defined(LK_EMUL_DEBUG)
     if (lane == 0) fprintf(stderr, "band result acc %g xi %d\n", (double)acc_final, xi_final);
+#endif
+#if defined(__CUDA_ARCH__) && defined(LK_BAND_DEBUG)
+    if (lane == 0 && (!(acc_final > 0.f) || !(acc_final < 3.0e38f))) printf("band rescue read %d hap %d R %d H %d acc %g xi %d\n", read, (int)h, R, H, (double)acc_final, xi_final);
 #endif
     if (!(acc_final > 0.f) || !(acc_final < 3.0e38f)) { to_rescue(); return; }  // flushed to zero / overflowed: f64 pass
     if (lane == 0) {

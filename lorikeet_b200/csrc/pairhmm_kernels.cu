@@ -20,6 +20,7 @@ struct DevWarp {
     template <class T> __device__ __forceinline__ T shfl_xor(T v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
     __device__ __forceinline__ unsigned reduce_or(unsigned v) const { return __reduce_or_sync(0xffffffffu, v); }
     __device__ __forceinline__ unsigned reduce_max(unsigned v) const { return __reduce_max_sync(0xffffffffu, v); }
+    __device__ __forceinline__ int reduce_min_i(int v) const { return __reduce_min_sync(0xffffffffu, v); }
     template <class T> __device__ __forceinline__ T ldg(const T *p) const { return __ldg(p); }
     __device__ __forceinline__ int atomic_add(int32_t *p, int v) const { return atomicAdd(p, v); }
     __device__ __forceinline__ void sync() const { __syncwarp(); __threadfence_block(); }
@@ -111,8 +112,9 @@ __global__ void __launch_bounds__(LK_FAST_THREADS, MINB) pairhmm_fast_kernel(con
 
 template <int K, bool Q10>
 __global__ void __launch_bounds__(LK_BAND_THREADS, LK_BAND_MINB) pairhmm_band_kernel(const PairHmmArgs A) {
-    extern __shared__ float4 lk_band_smem[];  // per-warp prior tables
-    float *tab = reinterpret_cast<float *>(lk_band_smem) + (threadIdx.x >> 5) * FastTable<K>::floats;
+    extern __shared__ float4 lk_band_smem[];  // per warp: prior table, then the ring of staged boundary elements
+    float *tab = reinterpret_cast<float *>(lk_band_smem) + (threadIdx.x >> 5) * band_smem_floats(K);
+    Bnd4 *ring = reinterpret_cast<Bnd4 *>(tab + fast_table_floats(K));
     DevWarp w;
     const int warp_in_grid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     Bnd4 *scratch = (Bnd4 *)A.band_scratch + (int64_t)warp_in_grid * A.band_scratch_stride;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(LK_BAND_THREADS, LK_BAND_MINB) pairhmm_band_ke
         idx = w.shfl(idx, 0);
         if (idx >= A.n_band) break;
         const RescuePair p = A.band_pairs[idx];
-        pairhmm_band_pair<DevWarp, K, Q10>(w, A, p.read, (int64_t)p.hap, scratch, tab);
+        pairhmm_band_pair<DevWarp, K, Q10>(w, A, p.read, (int64_t)p.hap, scratch, tab, ring);
         __syncwarp();
     }
 }
@@ -217,7 +219,7 @@ cudaError_t launch_fast(int K, const PairHmmArgs &A, bool vargcp, cudaStream_t s
 
 cudaError_t launch_band(const PairHmmArgs &A, int n_blocks, cudaStream_t st) {
     if (A.n_band == 0) return cudaSuccess;
-    const int smem = (LK_BAND_THREADS / 32) * FastTable<LK_BAND_K>::floats * (int)sizeof(float);
+    const int smem = (LK_BAND_THREADS / 32) * band_smem_floats(LK_BAND_K) * (int)sizeof(float);
     static bool configured_on[64] = { false };  // per device ordinal: the attribute is per function and device
     int dev = 0;
     cudaGetDevice(&dev);

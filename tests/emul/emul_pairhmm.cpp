@@ -55,6 +55,14 @@ struct EmulWarp {
         sh->bar.arrive_and_wait();
         return r;
     }
+    int reduce_min_i(int v) {
+        sh->slot[lane_] = (uint64_t)(int64_t)v;
+        sh->bar.arrive_and_wait();
+        int r = v;
+        for (int i = 0; i < 32; i++) r = std::min(r, (int)(int64_t)sh->slot[i]);
+        sh->bar.arrive_and_wait();
+        return r;
+    }
     template <class T> T ldg(const T *p) const { return *p; }
     void lds4(float *dst, const float *src) const { memcpy(dst, src, 16); }
     int atomic_add(int32_t *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -88,14 +96,15 @@ static void run_fast_tasks(const PairHmmArgs &A, bool vargcp, const WarpTask *ta
 
 static void run_band(const PairHmmArgs &A, int k_band) {
     WarpShared sh;
-    std::vector<float> tab((size_t)fast_table_floats(LK_BAND_K > 4 ? LK_BAND_K : 4));
+    std::vector<float> tab((size_t)band_smem_floats(LK_BAND_K > 4 ? LK_BAND_K : 4));
+    Bnd4 ring[BAND_RING];
     std::vector<std::thread> th;
     for (int l = 0; l < 32; l++)
         th.emplace_back([&, l]() {
             EmulWarp w{ l, &sh };
             for (int i = 0; i < A.n_band; i++) {
-                if (k_band == 4) pairhmm_band_pair<EmulWarp, 4>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch, tab.data());
-                else pairhmm_band_pair<EmulWarp, LK_BAND_K>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch, tab.data());
+                if (k_band == 4) pairhmm_band_pair<EmulWarp, 4>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch, tab.data(), ring);
+                else pairhmm_band_pair<EmulWarp, LK_BAND_K>(w, A, A.band_pairs[i].read, (int64_t)A.band_pairs[i].hap, (Bnd4 *)A.band_scratch, tab.data(), ring);
             }
         });
     for (auto &t : th) t.join();
