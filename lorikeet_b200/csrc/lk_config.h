@@ -11,7 +11,7 @@
 #define LK_PLAIN_K 4
 // band path (fp32, reads longer than 32 * max fast K): rows per lane, threads per block, min blocks per SM
 #ifndef LK_BAND_K
-#define LK_BAND_K 15
+#define LK_BAND_K 16
 #define LK_BAND_MINB 3
 #endif
 #define LK_BAND_THREADS 128

@@ -169,6 +169,9 @@ LK_DEV int lk_popc(unsigned v) {
 #ifndef LK_BAND_UNROLL
 #define LK_BAND_UNROLL 4
 #endif
+#ifndef LK_BAND_ORDER
+#define LK_BAND_ORDER 0  // statement order of the band kernel's cell (ptxas schedules them differently)
+#endif
 #define LK_PRAGMA_(x) _Pragma(#x)
 #define LK_PRAGMA(x) LK_PRAGMA_(x)
 #define LK_UNROLL_N(n) LK_PRAGMA(unroll n)
@@ -375,7 +378,7 @@ LK_UNROLL_N(LK_FAST_UNROLL)
 // fp32 cannot hold the decay of hundreds of noisy rows (a 10 kbp ONT-like read loses ~7000 binary orders),
 // so every lane carries a private binary exponent xi ("stored = true * 2^xi", block floating point per
 // lane): every 16 columns a lane looks at the magnitude of its strip and, if it drifted out of
-// [2^-20, 2^60], multiplies its whole state by 2^(+-40) and adjusts xi.  The exponent travels with the
+// its range (BAND_RANGE_LO/HI below), multiplies its whole state by a power of two and adjusts xi.  The exponent travels with the
 // data (a 4th shuffle / the 4th word of the boundary element) and the receiver re-aligns what it gets
 // with one FMUL per value.  Fully adaptive: no a-priori decay estimate, no retries.
 // =============================================================================================
@@ -387,6 +390,22 @@ struct alignas(16) Bnd4 { float m, i, d; int32_t xi; };
 #endif
 
 constexpr int BAND_INIT_EXP = 40;  // initial condition 2^40 / H
+// A lane re-centres its strip to 2^LK_BAND_CENTRE when its largest value leaves [2^-LK_BAND_SPAN, 2^+LK_BAND_SPAN] around
+// the centre.  Head-room budget above the centre: what a lane receives can grow between two checkpoints (16 columns) by
+// the whole spread of the sender's strip -- the alignment path enters the sender's strip at its top row and leaves at the
+// bottom row K columns later, and the bottom row sits 2^-(15 + 3.3 (K - 2)) below the path (one insertion opening, K - 2
+// extensions at gcp 10) -- on top of the sender's own allowed drift: centre + span + 15 + 3.3 (K - 2) must stay under
+// 127.  With centre 20 / span 40 (the first version) that holds for K <= 16 and K >= 19 overflowed on every pair; centre 0
+// / span 30 leaves room up to K = 24.
+#ifndef LK_BAND_CENTRE
+#define LK_BAND_CENTRE 0
+#endif
+#ifndef LK_BAND_SPAN
+#define LK_BAND_SPAN 30
+#endif
+constexpr float band_pow2(int e) { float r = 1.f; for (int i = 0; i < (e < 0 ? -e : e); i++) r = e < 0 ? r * 0.5f : r * 2.f; return r; }
+constexpr float BAND_RANGE_LO = band_pow2(LK_BAND_CENTRE - LK_BAND_SPAN);
+constexpr float BAND_RANGE_HI = band_pow2(LK_BAND_CENTRE + LK_BAND_SPAN);
 
 LK_DEV int __float_as_int_hd(float f) {
 #if defined(__CUDA_ARCH__)
@@ -428,7 +447,7 @@ constexpr int band_smem_floats(int K) { return fast_table_floats(K) + BAND_RING 
 //     lane; lane 0 then receives them like values from a lane above it, see `stage`).
 //   A lean step is: 1 LDG.U8 (next column's table slice) + KQ LDS.128 + K x (FMUL + 4 FFMA) + 2 FFMA (running sum)
 //   + 3 SHFL + 3 FMUL (re-alignment) + predicated LDS.128 (lane 0's feed) / STG.128 (last lane's boundary row).
-// Invariant: at the start of a step everything a lane holds (M, I, D, Mu.., Md.., acc, kinit) is in its own scale xi,
+// Invariant: at the start of a step everything a lane holds (M, I, D, Mu.., Md.., acc) is in its own scale xi,
 // and `al` = 2^(xi - xi_up) with xi_up the current exponent of the lane above (lane 0: of the staged ring).
 template <class W, int K, bool Q10 = false>
 LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, Bnd4 *scratch, float *tab, Bnd4 *ring) {
@@ -501,6 +520,9 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
             } else if (i == R) {
                 e = (float)(A.qerr_d[A.read_ins[ro + R - 1]] / a_tilde(R - 1));
             }
+            // read row 1 sees only D[0][j-1] = init / H of the virtual row 0 (pair_hmm.rs:515-529): that constant is what
+            // the ring feeds lane 0 in band 0 (d = init / H), and c'(row 1) = pm * tGM picks it up
+            if (i == 0) c = kcoef;
             cb[k] = b; cc[k] = c; ce[k] = e;
 #pragma unroll
             for (int sl = 0; sl < N_PRIOR_SLICES; sl++) {
@@ -512,7 +534,7 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         for (int k = K; k < KQ * 4; k++)
 #pragma unroll
             for (int sl = 0; sl < N_PRIOR_SLICES; sl++) tab[(((sl * KQ) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = 0.f;
-        if (band == 0) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = 0.f; z.xi = 0; ring[lane] = z; }  // band 0: row 0 feeds zeros
+        if (band == 0) { Bnd4 z; z.m = 0.f; z.i = 0.f; z.d = initH; z.xi = 0; ring[lane] = z; }  // band 0: the virtual row 0
         w.sync();
         if (last_band && lane == lanes - 1) {
             const int kstar = (rows - 1) - lane * K;
@@ -524,7 +546,7 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
 #pragma unroll
         for (int k = 0; k < K; k++) { M[k] = 0.f; I[k] = 0.f; D[k] = 0.f; }
         float Mu = 0.f, Iu = 0.f, Du = 0.f, Md = 0.f, Id = 0.f, Dd = 0.f, acc = 0.f;
-        float kinit = (band == 0) ? kcoef * initH : 0.f;  // only row 1 (band 0, lane 0) has kcoef != 0
+        if (band == 0 && lane == 0) { Dd = initH; Du = initH; }  // D[0][0], D[0][1]
         float al = 1.f;
         int xi = 0, xi_up = 0;  // my exponent; exponent of the lane above (lane 0: of the ring, xc)
         const int n_steps = H + lanes - 1;
@@ -552,33 +574,37 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
             w.sync();
         };
         // checkpoint + exchange at the START of a step (every step while lanes are starting, s <= 32; then when s = 1 mod 16):
-        // re-centre what I hold into [2^-20, 2^60] (looking at the running sum and at what has just arrived too), then learn
+        // re-centre what I hold into [BAND_RANGE_LO, BAND_RANGE_HI] (looking at the running sum and at what has just arrived too), then learn
         // the exponent of the lane above and set `al`.
         auto upkeep = [&](int s) {
             if (band > 0 && ((s - 1) & 31) == 0) stage(s - 1);
             float m = fmaxf(acc, fmaxf(Mu, fmaxf(Iu, Du)));
 #pragma unroll
             for (int k = 0; k < K; k++) m = fmaxf(m, fmaxf(M[k], I[k]));
-            if (m > 0.f && (m < 9.5367431640625e-07f || m > 1.152921504606847e18f)) {  // outside [2^-20, 2^60]
-                int sh = 20 - ilogbf(m);
+            if (m > 0.f && (m < BAND_RANGE_LO || m > BAND_RANGE_HI)) {
+                int sh = LK_BAND_CENTRE - ilogbf(m);
                 sh = sh > 120 ? 120 : (sh < -120 ? -120 : sh);
                 const float f = pow2i(sh);
 #pragma unroll
                 for (int k = 0; k < K; k++) { M[k] *= f; I[k] *= f; D[k] *= f; }
-                Mu *= f; Iu *= f; Du *= f; Md *= f; Id *= f; Dd *= f; acc *= f; kinit *= f;
+                Mu *= f; Iu *= f; Du *= f; Md *= f; Id *= f; Dd *= f; acc *= f;
                 xi += sh;
             }
             xi_up = w.shfl_up1(xi);
-            if (lane == 0) xi_up = (band > 0) ? ring[(s - 1) & 31].xi : xi;  // exponent of what this block receives
+            if (lane == 0) xi_up = ring[(s - 1) & 31].xi;  // exponent of what this block receives (band 0: 0)
             if (s <= lane) xi = xi_up;  // not started yet (holds zeros only): adopt the sender's scale
             al = pow2i(xi - xi_up);
         };
-        int slice_ahead = (int)w.ldg(hp + 1);
-        // LEAN = true: every lane's column is inside [1, H] (no gates); false: generic step
-        auto step = [&](int s, const Bnd4 *rp, auto lean_tag) {
+        // table slice of my column, fetched two steps ahead of the LDS address it forms
+        unsigned sl_a = w.ldg(hp + 1), sl_b = w.ldg(hp + 2);
+        const float *tab_lane = tab + lane * 4;
+        // One step.  hq = hp + s, bq = bw + s, rp = ring + ((s - 1) & 31) (passed in so that the unrolled lean block addresses
+        // them with immediate offsets).  LEAN = true: every lane's column is inside [1, H] (no gates); false: generic step.
+        auto step = [&](int s, const uint8_t *hq, Bnd4 *bq, const Bnd4 *rp, auto lean_tag) {
             constexpr bool LEAN = decltype(lean_tag)::value;
-            const float *trow = tab + (slice_ahead * KQ * 32 + lane) * 4;
-            slice_ahead = (int)w.ldg(hp + s + 1);  // next step's column, fetched ahead of the LDS address it forms
+            const float *trow = tab_lane + sl_a * (unsigned)(KQ * 128);
+            sl_a = sl_b;
+            sl_b = w.ldg(hq + 2);
             float sel[KQ * 4];
 #pragma unroll
             for (int q = 0; q < KQ; q++) w.lds4(sel + 4 * q, trow + q * 128);
@@ -586,29 +612,37 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
             // and, for I', row k-1 of this column (im, ii).  Written in this order the serial I' chain (one FFMA per row)
             // is spread evenly between the independent M'/D' work of the rows instead of being bunched at the end. ----
             {
-                float pm = Md + kinit, pi = Id, pd = Dd, im = Mu, ii = Iu;  // start lanes: Md = 0, b'0 = c'0 = 0 -> mm = kinit
+                float pm = Md, pi = Id, pd = Dd, im = Mu, ii = Iu;  // start lanes: b'0 = 0 and Md = 0 -> mm = c'0 * D[0][j-1]
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const float om = M[k], oi = I[k], od = D[k];
+#if LK_BAND_ORDER == 1
+                    D[k] = fmaf(od, Q10 ? 0.1f : A.cf_uniform, om);
+                    float mm = fmaf(pd, cc[k], pm);
+                    mm = fmaf(pi, cb[k], mm);
+                    M[k] = mm * sel[k];
+                    I[k] = fmaf(ii, ce[k], im);
+#else
                     float mm = fmaf(pi, cb[k], pm);
                     mm = fmaf(pd, cc[k], mm);
                     D[k] = fmaf(od, Q10 ? 0.1f : A.cf_uniform, om);
                     M[k] = mm * sel[k];
                     I[k] = fmaf(ii, ce[k], im);
+#endif
                     pm = om; pi = oi; pd = od; im = M[k]; ii = I[k];
                 }
             }
             if (LEAN) {
                 acc = fmaf(M[K - 1], wM, acc);
                 acc = fmaf(I[K - 1], wI, acc);
-                if (writes) { Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi; bw[s] = v; }
+                if (writes) { Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi; *bq = v; }
             } else {
                 // columns past the haplotype read the guard band of the encoded haplotype (an ordinary table slice), so what
                 // a lane holds there is finite: the sum is gated by zeroed weights and the boundary store by a predicate
                 const bool in_cols = s <= s_last;
                 acc = fmaf(M[K - 1], in_cols ? wM : 0.f, acc);
                 acc = fmaf(I[K - 1], in_cols ? wI : 0.f, acc);
-                if (writes && in_cols && s > lane) { Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi; bw[s] = v; }
+                if (writes && in_cols && s > lane) { Bnd4 v; v.m = M[K - 1]; v.i = I[K - 1]; v.d = D[K - 1]; v.xi = xi; *bq = v; }
             }
             Md = Mu; Id = Iu; Dd = Du;
             float rm = w.shfl_up1(M[K - 1]), ri = w.shfl_up1(I[K - 1]), rd = w.shfl_up1(D[K - 1]);
@@ -621,15 +655,20 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
         for (;;) {  // generic start-up, lean blocks, generic tail (one copy of the generic loop in the code)
             for (; s <= gen_end; ++s) {
                 if (s <= 32 || (s & 15) == 1) upkeep(s);
-                step(s, ring + ((s - 1) & 31), GenericTag());
+                step(s, hp + s, bw + s, ring + ((s - 1) & 31), GenericTag());
             }
             if (gen_end == n_steps) break;
             while (s + 15 <= s_lean_end) {  // s = 1 (mod 16)
                 upkeep(s);
                 const Bnd4 *rp = ring + ((s - 1) & 31);
-LK_UNROLL_N(LK_BAND_UNROLL)
-                for (int u = 0; u < 16; ++u) step(s + u, rp + u, LeanTag());
-                s += 16;
+                const uint8_t *hq = hp + s;
+                Bnd4 *bq = bw + s;
+#pragma unroll 1
+                for (int u4 = 0; u4 < 16 / LK_BAND_UNROLL; ++u4) {
+#pragma unroll
+                    for (int u = 0; u < LK_BAND_UNROLL; ++u) step(s + u, hq + u, bq + u, rp + u, LeanTag());
+                    hq += LK_BAND_UNROLL; bq += LK_BAND_UNROLL; rp += LK_BAND_UNROLL; s += LK_BAND_UNROLL;
+                }
             }
             gen_end = n_steps;
         }
