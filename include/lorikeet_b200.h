@@ -109,9 +109,12 @@ lk_status lk_pairhmm_batch_dims(const lk_pairhmm_batch *batch, int64_t *n_pairs,
  * Batch form of PairHMM::compute_likelihoods (pair_hmm.rs:345-375): for every region, for every
  * read r, for every haplotype h: out[base_g + r*A_g + h] = log10 P(read | hap), the layout of
  * m_log_likelihood_array (pair_hmm.rs:262-263,349-369); base_g is the running sum of
- * reads*haps over earlier regions.  All pointers are HOST pointers; the call stages, runs and
+ * reads*haps over earlier regions.  The batch pointers are HOST pointers; the call stages, runs and
  * copies back (chunked, overlapped) and returns when out is complete.
  * flags may be NULL; otherwise one LK_FLAG_* byte per pair.
+ * out / flags (and values / keep of lk_engine_compute_read_likelihoods) may also point into memory of
+ * the context's own device (unified addressing; the copies use cudaMemcpyDefault): a multi-GPU caller
+ * that hands the results to a collective keeps them in HBM instead of bouncing them through the host.
  */
 lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags);
 
@@ -125,6 +128,17 @@ lk_status lk_pairhmm_upload(lk_ctx *ctx, const lk_pairhmm_batch *batch, lk_resid
 lk_status lk_pairhmm_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms /* may be NULL */);
 lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *out, uint8_t *flags);
 void lk_resident_free(lk_ctx *ctx, lk_resident *res);
+/* Introspection of a resident batch and of the last host call; what bench.py and a multi-GPU dispatcher need. */
+int64_t lk_resident_pairs(const lk_resident *res);            /* (read, haplotype) pairs / SW pairs staged            */
+int64_t lk_resident_cells(const lk_resident *res);            /* sum of R*H (PairHMM) or n*m (SW) over them           */
+int32_t lk_resident_launch_count(const lk_resident *res);     /* kernels launched by the last run of this batch       */
+float lk_resident_last_fast_ms(const lk_resident *res);       /* device time of the dominant kernel(s) in the last
+                                                                 TIMED run (kernel_ms != NULL): fp32 wavefront + band */
+void *lk_resident_out_device_ptr(const lk_resident *res);     /* device address of the f64 result block [n_pairs], so
+                                                                 the results can be handed to a collective in place   */
+int32_t lk_debug_last_launch_count(const lk_ctx *ctx);        /* kernels launched by the last host-buffer call on ctx */
+/* FFMA-only microbenchmark on the context's device for `duration_ms`: the measured fp32 roofline denominator. */
+lk_status lk_measure_fp32_fma_tflops(lk_ctx *ctx, double duration_ms, double *tflops);
 
 /*
  * Single-pair convenience wrapper with exactly the argument list of the function pointer

@@ -586,10 +586,12 @@ lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double
         lk_resident *R = ctx->ws[i % LK_PIPE_DEPTH];
         cudaStream_t s = ctx->stream[i % LK_PIPE_DEPTH];
         if (R->n_pairs == 0) return LK_OK;
-        cudaError_t ce = cudaMemcpyAsync(out + pair_base[(size_t)i], hook ? R->values.p : R->out.p, (size_t)R->n_pairs * 8, cudaMemcpyDeviceToHost, s);
+        // cudaMemcpyDefault: the result pointers may be host memory or memory of this device (a caller that hands the
+        // results to a collective keeps them in HBM, see include/lorikeet_b200.h)
+        cudaError_t ce = cudaMemcpyAsync(out + pair_base[(size_t)i], hook ? R->values.p : R->out.p, (size_t)R->n_pairs * 8, cudaMemcpyDefault, s);
         if (ce == cudaSuccess && hook && hook->keep && R->n_reads > 0)
-            ce = cudaMemcpyAsync(hook->keep + batch->region_read_start[cut[(size_t)i]], R->keep.p, (size_t)R->n_reads, cudaMemcpyDeviceToHost, s);
-        if (ce == cudaSuccess && flags) ce = cudaMemcpyAsync(flags + pair_base[(size_t)i], R->flags.p, (size_t)R->n_pairs, cudaMemcpyDeviceToHost, s);
+            ce = cudaMemcpyAsync(hook->keep + batch->region_read_start[cut[(size_t)i]], R->keep.p, (size_t)R->n_reads, cudaMemcpyDefault, s);
+        if (ce == cudaSuccess && flags) ce = cudaMemcpyAsync(flags + pair_base[(size_t)i], R->flags.p, (size_t)R->n_pairs, cudaMemcpyDefault, s);
         if (ce != cudaSuccess) return lk_cuda_fail(ctx, ce, "D2H");
         return LK_OK;
     };

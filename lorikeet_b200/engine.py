@@ -39,17 +39,24 @@ class PairHMMLikelihoodCalculationEngine:
                                     1 if symmetrically_normalize_alleles_to_reference else 0,
                                     1 if disable_cap_read_qualities_to_mapq else 0, 1 if modify_soft_clipped_bases else 0)
 
-    def compute_read_likelihoods(self, batch, read_mapq, ref_allele_index=None, values=None, keep=None):
+    def compute_read_likelihoods(self, batch, read_mapq, ref_allele_index=None, values=None, keep=None, values_device_ptr=None):
         """compute_read_likelihoods (:195-242) for a batch of single-sample regions.
         Returns (values, keep): values holds per region an [A x R] row-major block ([allele][read], the reference's
-        AlleleLikelihoods layout) at the pair offsets of the batch, normalised and filtered; keep[r] = read survived."""
+        AlleleLikelihoods layout) at the pair offsets of the batch, normalised and filtered; keep[r] = read survived.
+        values_device_ptr: address of n_pairs f64 in the context's device memory; the matrices are then left in HBM
+        (for a collective) and `values` is returned as None."""
         L = _lib.load()
         n = batch.n_pairs
-        if values is None:
-            values = np.empty(n, dtype=np.float64)
+        if values_device_ptr is not None:
+            values_arg = C.cast(C.c_void_p(int(values_device_ptr)), _lib.f64p)
+        else:
+            if values is None:
+                values = np.empty(n, dtype=np.float64)
+            assert values.dtype == np.float64 and values.size == n
+            values_arg = values.ctypes.data_as(_lib.f64p)
         if keep is None:
             keep = np.ones(batch.n_reads, dtype=np.uint8)
-        assert values.dtype == np.float64 and values.size == n and keep.dtype == np.uint8 and keep.size == batch.n_reads
+        assert keep.dtype == np.uint8 and keep.size == batch.n_reads
         mapq = np.ascontiguousarray(read_mapq, dtype=np.uint8)
         assert mapq.size == batch.n_reads
         ref = None
@@ -58,9 +65,23 @@ class PairHMMLikelihoodCalculationEngine:
         s = batch.as_struct()
         st = L.lk_engine_compute_read_likelihoods(self.ctx._h, C.byref(self.args), C.byref(s), mapq.ctypes.data_as(_lib.u8p),
                                                   ref.ctypes.data_as(_lib.i32p) if ref is not None else C.cast(None, _lib.i32p),
-                                                  values.ctypes.data_as(_lib.f64p), keep.ctypes.data_as(_lib.u8p))
+                                                  values_arg, keep.ctypes.data_as(_lib.u8p))
         self.ctx._check(st)
         return values, keep
+
+    def modify_read_qualities_device(self, batch):
+        """modify_read_qualities (:352-426) as ONE device launch, in place on the batch's quality arenas
+        (lk_engine_modify_read_qualities_device); MAPQ capping must be disabled or irrelevant (MAPQ 60 assumed)."""
+        L = _lib.load()
+        mapq = np.full(batch.n_reads, 60, dtype=np.uint8)
+        p = lambda a, t: a.ctypes.data_as(t)
+        for a in (batch.read_qual, batch.read_ins, batch.read_del):
+            assert a.flags.writeable and a.flags.c_contiguous
+        st = L.lk_engine_modify_read_qualities_device(self.ctx._h, C.byref(self.args), batch.n_reads, p(batch.read_off, _lib.i64p),
+                                                      p(batch.read_bases, _lib.u8p), p(batch.read_qual, _lib.u8p),
+                                                      p(batch.read_ins, _lib.u8p), p(batch.read_del, _lib.u8p), p(mapq, _lib.u8p))
+        self.ctx._check(st)
+        return batch
 
 
 class PairHMM:

@@ -11,22 +11,39 @@ from conftest import ROOT
 from lorikeet_b200 import _lib
 
 
-def _declared_symbols():
-    names = set()
-    for hdr in ("lorikeet_b200.h", "lorikeet_b200_synth.h"):
-        src = open(os.path.join(ROOT, "include", hdr)).read()
-        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        names |= set(re.findall(r"\b(lk_[a-z0-9_]+)\s*\(", src))
-    return sorted(names)
+def _declared_symbols(hdr):
+    src = open(os.path.join(ROOT, "include", hdr)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lk_[a-z0-9_]+)\s*\(", src)))
+
+
+def _exported_symbols(so_path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", so_path], check=True, capture_output=True, text=True).stdout
+    return sorted(t[2] for t in (ln.split() for ln in out.splitlines()) if len(t) == 3 and t[1] == "T" and t[2].startswith("lk_"))
 
 
 def test_library_exports_every_declared_symbol():
     L = _lib.load()
-    declared = _declared_symbols()
-    assert len(declared) >= 20
+    declared = _declared_symbols("lorikeet_b200.h")
+    assert len(declared) >= 40
     for name in declared:
         assert hasattr(L, name), "missing export: " + name
     assert set(_lib.EXPORTED_SYMBOLS) <= set(declared)
+    # and nothing is exported behind the header's back
+    assert set(_exported_symbols(_lib.SO_PATH)) <= set(declared)
+
+
+def test_generator_library_is_separate_and_complete():
+    from lorikeet_b200 import synth
+    S = C.CDLL(synth.SYNTH_SO_PATH)
+    for name in _declared_symbols("lorikeet_b200_synth.h"):
+        assert hasattr(S, name), "missing export: " + name
+    # the generators are not part of the product library, and the generator library has no CUDA dependency
+    assert not [n for n in _exported_symbols(_lib.SO_PATH) if n.startswith("lk_synth")]
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", synth.SYNTH_SO_PATH], capture_output=True, text=True).stdout
+    assert "cuda" not in needed.lower()
 
 
 def test_version_and_dims_without_gpu():

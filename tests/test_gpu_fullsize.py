@@ -63,6 +63,38 @@ def test_cfg3_long_reads_two_waves(ctx):
     assert np.max(rel_err(out[7 * 32:8 * 32], exp)) < REL_TOL
 
 
+def test_cfg3_full_size_2000_regions(ctx):
+    """BASELINE cfg#3 at its full size (2 000 regions x 8 reads x 10 kbp vs 4 haps x 12 kbp = 7.68e12 cells) through the
+    host-buffer call; 8 random regions (256 pairs) against the rescaled f64 oracle, whole-output properties on the rest."""
+    from lorikeet_b200 import synth, PairHmmBatch
+    n = 2000
+    b = synth.pairhmm_regions(n, **synth.CFG3)
+    assert b.n_pairs == n * 32 and b.n_cells > 7.6e12
+    out, flags = ctx.pairhmm_batch(b, want_flags=True)
+    assert np.all(np.isfinite(out)) and out.max() <= 1e-9
+    assert int((flags & 1).sum()) == 0  # nothing fell back to the f64 pass
+    # the 111-region slice computed on its own is bit-identical to the same slice of the big batch
+    alone = ctx.pairhmm_batch(b.region_slice(1000, 1020))
+    assert np.array_equal(alone, out[1000 * 32:1020 * 32])
+    # every read scores best against one of its region's haplotypes by a clear margin over an unrelated pairing's ~-1700
+    assert out.reshape(n, 8, 4).max(axis=2).min() > -1200.0
+    # oracle on 8 random regions; one oracle task per READ (a region re-packed as 8 single-read regions) so the host cores
+    # share the 8 x 32 pairs of 1.2e8 cells each
+    rng = np.random.default_rng(33)
+    picks = sorted(int(g) for g in rng.choice(n, 8, replace=False))
+    parts = []
+    for g in picks:
+        reg = b.region_slice(g, g + 1)
+        for r in range(reg.n_reads):
+            o0, o1 = int(reg.read_off[r]), int(reg.read_off[r + 1])
+            parts.append(PairHmmBatch([0, 1], [0, reg.n_haps], [0, o1 - o0], reg.read_bases[o0:o1], reg.read_qual[o0:o1],
+                                      reg.read_ins[o0:o1], reg.read_del[o0:o1], reg.hap_off, reg.hap_bases, gcp_constant=10))
+    from lorikeet_b200.dispatch import concat_batches
+    exp = O.pairhmm_batch(concat_batches(parts), rescaled=True).reshape(len(picks), 32)
+    got = np.stack([out[g * 32:(g + 1) * 32] for g in picks])
+    assert np.max(rel_err(got.ravel(), exp.ravel())) < REL_TOL
+
+
 def test_cfg4_full_size_cigars(ctx):
     from lorikeet_b200 import synth
     n = 100000
