@@ -159,6 +159,20 @@ def run_extras(ctx, args, peak_fp32):
     except Exception as e:  # side measurements must never break the bench line
         out["cfg4_error"] = str(e)
     try:
+        # the rate Lorikeet's call pattern sees: Rayon-like host threads submitting ONE region each to lk_batcher (native
+        # harness tools/native/bench_batcher.cpp, one process, this GPU only; multi-device pool runs are in profiles/)
+        dev = str(torch.cuda.current_device())
+        tool = os.path.join(ROOT, "tools", "native", "bench_batcher")
+        runs = []
+        for threads, in_flight in ((64, 1), (256, 1), (16, 16)):
+            p = subprocess.run([tool, "4000", str(threads), "512", "200", str(in_flight), "1", dev], capture_output=True, text=True, timeout=300)
+            last = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+            runs.append(json.loads(last[-1]) if last else {"error": (p.stderr or p.stdout)[-300:], "threads": threads})
+        out["batcher"] = {"api": "lk_pool_batcher_create + lk_batcher_submit[_async] (one cfg2 region per submit, pageable buffers)",
+                          "runs": runs}
+    except Exception as e:
+        out["batcher_error"] = str(e)
+    try:
         # cfg3 at BASELINE's full size: 2 000 regions x (8 reads x 10 kbp, 4 haps x 12 kbp) = 7.68e12 cells
         n3 = args.cfg3_regions
         b = synth.pairhmm_regions(n3, **synth.CFG3)

@@ -346,6 +346,33 @@ lk_status lk_batcher_submit_async(lk_batcher *b, const lk_pairhmm_batch *region,
                                   lk_ticket **out_ticket);
 lk_status lk_batcher_wait(lk_batcher *b, lk_ticket *ticket);
 
+/* ---------------------------------------------------------------- several devices in one process */
+
+/*
+ * Lorikeet is ONE process whose Rayon workers call the engine (src/assembly/assembly_region_walker.rs:140-277,
+ * nested under src/haplotype/haplotype_caller_engine.rs:949-951).  A pool puts several GPUs behind one handle: one
+ * lk_ctx (three streams, chunk pipeline) and its dispatcher threads per device; regions are independent, so they are
+ * dealt to the devices with no data-path exchange and no collective.  devices == NULL (or n_devices <= 0): every
+ * visible device.  The batch entry points cut the batch into contiguous chunks of about equal CELL counts and deal them
+ * dynamically (one host thread per device pulls the next chunk when its device is free); results land in the caller's
+ * arrays exactly as from the single-device calls (bit-identical: a region's result does not depend on its batch).
+ */
+typedef struct lk_pool lk_pool;
+lk_status lk_pool_create(const int *devices, int32_t n_devices, lk_pool **out_pool);
+void lk_pool_destroy(lk_pool *pool);
+int32_t lk_pool_device_count(const lk_pool *pool);
+lk_ctx *lk_pool_ctx(lk_pool *pool, int32_t i);               /* the i-th device's context (owned by the pool) */
+const char *lk_pool_last_error(const lk_pool *pool);
+lk_status lk_pool_set_tristate_correction(lk_pool *pool, int use_tristate);
+lk_status lk_pool_pairhmm_batch_host(lk_pool *pool, const lk_pairhmm_batch *batch, double *out, uint8_t *flags);
+lk_status lk_pool_compute_read_likelihoods(lk_pool *pool, const lk_engine_args *args, const lk_pairhmm_batch *batch,
+                                           const uint8_t *read_mapq, const int32_t *ref_allele_index, double *values,
+                                           uint8_t *keep);
+/* The cross-thread batcher over every device of the pool: lk_batcher_submit / _submit_async / _wait / _stats / _destroy
+ * as above; the dispatcher threads of all devices pull from one queue, so a free device takes the next share. */
+lk_status lk_pool_batcher_create(lk_pool *pool, const lk_engine_args *args /* may be NULL */, int32_t max_regions,
+                                 int32_t max_wait_us, lk_batcher **out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,10 @@ EXPORTED_SYMBOLS = [
     "lk_cigar_append_clipped_elements", "lk_read_start_on_reference_haplotype",
     "lk_batcher_create", "lk_batcher_destroy", "lk_batcher_submit", "lk_batcher_stats", "lk_batcher_submit_async",
     "lk_batcher_wait",
+    "lk_pool_create", "lk_pool_destroy", "lk_pool_device_count", "lk_pool_ctx", "lk_pool_last_error",
+    "lk_pool_set_tristate_correction", "lk_pool_pairhmm_batch_host", "lk_pool_compute_read_likelihoods", "lk_pool_batcher_create",
+    "lk_resident_pairs", "lk_resident_cells", "lk_resident_launch_count", "lk_resident_last_fast_ms",
+    "lk_resident_out_device_ptr", "lk_debug_last_launch_count", "lk_measure_fp32_fma_tflops",
 ]
 
 
@@ -188,7 +192,26 @@ def load():
     L.lk_batcher_wait.argtypes = [vp, vp]
     L.lk_batcher_stats.restype = None
     L.lk_batcher_stats.argtypes = [vp, i64p, i64p]
-    # introspection helpers (not part of the public header)
+    # several devices behind one handle
+    L.lk_pool_create.restype = C.c_int
+    L.lk_pool_create.argtypes = [C.POINTER(C.c_int), C.c_int32, C.POINTER(vp)]
+    L.lk_pool_destroy.restype = None
+    L.lk_pool_destroy.argtypes = [vp]
+    L.lk_pool_device_count.restype = C.c_int32
+    L.lk_pool_device_count.argtypes = [vp]
+    L.lk_pool_ctx.restype = vp
+    L.lk_pool_ctx.argtypes = [vp, C.c_int32]
+    L.lk_pool_last_error.restype = C.c_char_p
+    L.lk_pool_last_error.argtypes = [vp]
+    L.lk_pool_set_tristate_correction.restype = C.c_int
+    L.lk_pool_set_tristate_correction.argtypes = [vp, C.c_int]
+    L.lk_pool_pairhmm_batch_host.restype = C.c_int
+    L.lk_pool_pairhmm_batch_host.argtypes = [vp, bp, f64p, u8p]
+    L.lk_pool_compute_read_likelihoods.restype = C.c_int
+    L.lk_pool_compute_read_likelihoods.argtypes = [vp, ep, bp, u8p, i32p, f64p, u8p]
+    L.lk_pool_batcher_create.restype = C.c_int
+    L.lk_pool_batcher_create.argtypes = [vp, ep, C.c_int32, C.c_int32, C.POINTER(vp)]
+    # introspection helpers
     L.lk_resident_launch_count.restype = C.c_int32
     L.lk_resident_launch_count.argtypes = [vp]
     L.lk_resident_cells.restype = C.c_int64

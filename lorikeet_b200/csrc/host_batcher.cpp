@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <deque>
 #include <mutex>
 #include <new>
@@ -36,7 +37,7 @@ struct Request {
 }  // namespace
 
 struct lk_batcher {
-    lk_ctx *ctx = nullptr;
+    std::vector<lk_ctx *> ctxs;  // one per device (lk_batcher_create: one; lk_pool_batcher_create: the pool's)
     bool engine = false;
     lk_engine_args args;
     int32_t max_regions = 256;
@@ -47,7 +48,7 @@ struct lk_batcher {
     bool stop = false;
     // statistics
     int64_t n_batches = 0, n_regions = 0;
-    size_t last_batch = 1;  // callers released by the previous batch: once that many are back there is nobody left to wait for
+    int idle_primaries = 0;  // primary dispatchers (one per device) waiting for work: a waking one leaves them their share
     // gather buffers, one set per dispatcher thread, kept across batches (fresh vectors cost more in page faults than the
     // copies)
     struct Scratch {
@@ -56,20 +57,25 @@ struct lk_batcher {
         std::vector<int32_t> ref_idx;
         std::vector<double> out;
     };
-    // two dispatcher threads: the device calls serialise on the context, but one thread gathers / scatters its batch while
-    // the other's is on the GPU
+    // two dispatcher threads PER DEVICE: the device calls serialise on the context, but one thread gathers / scatters its
+    // batch while the other's is on the GPU.  All dispatchers of all devices pull from the one queue, so the deal over
+    // devices is by time: whichever device is free takes the next share.
     static constexpr int kWorkers = 2;
     static constexpr int kBacklogForSecond = 48;
-    Scratch scratch[kWorkers];
-    std::thread workers[kWorkers];
+    struct Worker {
+        Scratch scratch;
+        std::thread thread;
+        size_t last_batch = 1;  // callers released by this dispatcher's previous batch: once that many are back there is nobody left to wait for
+    };
+    std::vector<Worker> workers;  // [device * kWorkers + w]
 
-    void run(int w);
-    void process(std::vector<Request *> &reqs, Scratch &S);
+    void run(int dev, int w);
+    void process(lk_ctx *ctx, std::vector<Request *> &reqs, Scratch &S);
 };
 
 static double bt_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-void lk_batcher::process(std::vector<Request *> &reqs, Scratch &S) {
+void lk_batcher::process(lk_ctx *ctx, std::vector<Request *> &reqs, Scratch &S) {
     auto &rrs = S.rrs; auto &rhs = S.rhs; auto &read_off = S.read_off; auto &hap_off = S.hap_off;
     auto &bases = S.bases; auto &qual = S.qual; auto &ins = S.ins; auto &del = S.del; auto &gcp = S.gcp; auto &haps = S.haps;
     auto &mapq = S.mapq; auto &aux = S.aux; auto &ref_idx = S.ref_idx; auto &out = S.out;
@@ -81,7 +87,9 @@ void lk_batcher::process(std::vector<Request *> &reqs, Scratch &S) {
     bases.clear(); qual.clear(); ins.clear(); del.clear(); gcp.clear(); haps.clear(); mapq.clear();
     ref_idx.assign(G, 0);
     bool any_gcp = false, need_mapq = engine && !args.disable_cap_read_qualities_to_mapq;
-    for (Request *q : reqs) any_gcp |= (q->region->read_gcp != nullptr);
+    // callers are independent: a region with a per-base gcp array, or two regions with different constants, turn the merged
+    // batch into the per-base form (each region keeps exactly the penalties its caller gave)
+    for (Request *q : reqs) any_gcp |= (q->region->read_gcp != nullptr) || (q->region->gcp_constant != reqs[0]->region->gcp_constant);
     lk_status bad = LK_OK;
     for (size_t g = 0; g < G; g++) {
         const lk_pairhmm_batch *b = reqs[g]->region;
@@ -101,8 +109,8 @@ void lk_batcher::process(std::vector<Request *> &reqs, Scratch &S) {
             else gcp.insert(gcp.end(), (size_t)(rb1 - rb0), b->gcp_constant);
         }
         haps.insert(haps.end(), b->hap_bases + hb0, b->hap_bases + hb1);
-        if (need_mapq) {
-            if (!reqs[g]->read_mapq && nr > 0) { bad = LK_ERR_INVALID; break; }
+        if (need_mapq && nr > 0) {
+            if (!reqs[g]->read_mapq) { bad = LK_ERR_INVALID; break; }  // (rejected at submit; kept as a guard)
             mapq.insert(mapq.end(), reqs[g]->read_mapq, reqs[g]->read_mapq + nr);
         }
         ref_idx[g] = reqs[g]->ref_allele_index;
@@ -144,49 +152,89 @@ void lk_batcher::process(std::vector<Request *> &reqs, Scratch &S) {
     if (trace) fprintf(stderr, "[lk] batcher: %zu regions, gather %.2f ms, device call %.2f ms, scatter %.2f ms\n", G, t1 - t0, t2 - t1, bt_now_ms() - t2);
 }
 
-void lk_batcher::run(int w) {
+void lk_batcher::run(int dev, int w) {
+    lk_ctx *ctx = ctxs[(size_t)dev];
+    Worker &me = workers[(size_t)(dev * kWorkers + w)];
+    const size_t n_dev = ctxs.size();
     std::unique_lock<std::mutex> lock(mu);
     for (;;) {
-        // The second dispatcher only steps in for a backlog (callers that keep many regions in flight): with blocked
-        // callers it would split them into two half-sized groups that alternate, each launch paying the fixed latency
-        // for half the regions (16 threads: 925 instead of 1 170 GCUPS).
-        const size_t need = (w == 0) ? 1 : (size_t)kBacklogForSecond;
+        // The second dispatcher of a device only steps in for a backlog (callers that keep many regions in flight): with
+        // blocked callers it would split them into two half-sized groups that alternate, each launch paying the fixed
+        // latency for half the regions (16 threads: 925 instead of 1 170 GCUPS).
+        const size_t need = (w == 0) ? 1 : (size_t)kBacklogForSecond * n_dev;
+        if (w == 0) idle_primaries++;
         cv_work.wait(lock, [&] { return stop || queue.size() >= need; });
+        const int idle_now = idle_primaries;  // primaries (me included) that could share what is queued
+        if (w == 0) idle_primaries--;
         if (stop && queue.empty()) return;
-        if (queue.size() < need) { cv_work.wait_for(lock, std::chrono::microseconds(50)); continue; }  // stopping: leave the rest to worker 0
+        if (queue.size() < need) { cv_work.wait_for(lock, std::chrono::microseconds(50)); continue; }  // stopping: leave the rest to a primary
         // give stragglers a moment: a fuller batch uses the GPU better than a prompt one
         if ((int32_t)queue.size() < max_regions && max_wait_us > 0 && !stop)
             cv_work.wait_for(lock, std::chrono::microseconds(max_wait_us),
-                             [&] { return stop || (int32_t)queue.size() >= max_regions || queue.size() >= last_batch; });
+                             [&] { return stop || (int32_t)queue.size() >= max_regions || queue.size() >= me.last_batch * (size_t)(n_dev > 1 ? idle_now : 1); });
+        // several devices: leave the other idle devices their share of what is queued (a share below ~8 regions is not
+        // worth a launch of its own)
+        size_t take = (size_t)max_regions;
+        if (n_dev > 1 && w == 0 && idle_now > 1) {
+            const size_t share = (queue.size() + (size_t)idle_now - 1) / (size_t)idle_now;
+            take = std::min(take, std::max<size_t>(share, 8));
+        }
         std::vector<Request *> reqs;
-        while (!queue.empty() && (int32_t)reqs.size() < max_regions) { reqs.push_back(queue.front()); queue.pop_front(); }
-        if (reqs.empty()) continue;  // the other dispatcher took everything while this one waited for stragglers
+        while (!queue.empty() && reqs.size() < take) { reqs.push_back(queue.front()); queue.pop_front(); }
+        if (reqs.empty()) continue;  // another dispatcher took everything while this one waited for stragglers
+        const bool more = !queue.empty();
         lock.unlock();
-        process(reqs, scratch[w]);
+        if (more) cv_work.notify_all();
+        try {
+            process(ctx, reqs, me.scratch);
+        } catch (...) {  // gather buffers could not grow: fail this batch's callers, keep the dispatcher alive
+            for (Request *q : reqs) q->status = LK_ERR_NOMEM;
+        }
         lock.lock();
         n_batches++;
         n_regions += (int64_t)reqs.size();
-        last_batch = reqs.size();
+        me.last_batch = reqs.size();
         for (Request *q : reqs) q->done = true;
         cv_done.notify_all();
     }
 }
 
+static lk_status batcher_create(lk_ctx *const *ctxs, int n_ctx, const lk_engine_args *args, int32_t max_regions, int32_t max_wait_us,
+                                lk_batcher **out) {
+    if (!ctxs || n_ctx < 1 || !out) return LK_ERR_INVALID;
+    *out = nullptr;
+    for (int i = 0; i < n_ctx; i++)
+        if (!ctxs[i]) return LK_ERR_INVALID;
+    if (max_regions < 1 || max_wait_us < 0) return lk_fail(ctxs[0], LK_ERR_INVALID, "bad batcher arguments");
+    if (args && (args->pcr_error_model < 0 || args->pcr_error_model > 3)) return lk_fail(ctxs[0], LK_ERR_INVALID, "bad PCR error model");
+    try {
+        lk_batcher *b = new lk_batcher();
+        b->ctxs.assign(ctxs, ctxs + n_ctx);
+        b->engine = args != nullptr;
+        if (args) b->args = *args;
+        b->max_regions = max_regions;
+        b->max_wait_us = max_wait_us;
+        b->workers = std::vector<lk_batcher::Worker>((size_t)(n_ctx * lk_batcher::kWorkers));
+        for (int d = 0; d < n_ctx; d++)
+            for (int w = 0; w < lk_batcher::kWorkers; w++)
+                b->workers[(size_t)(d * lk_batcher::kWorkers + w)].thread = std::thread([b, d, w] {
+                    try { b->run(d, w); } catch (...) { /* a dispatcher must never unwind into std::terminate */ }
+                });
+        *out = b;
+        return LK_OK;
+    } catch (...) {
+        return lk_fail(ctxs[0], LK_ERR_NOMEM, "out of host memory (batcher)");
+    }
+}
+
 extern "C" lk_status lk_batcher_create(lk_ctx *ctx, const lk_engine_args *args, int32_t max_regions, int32_t max_wait_us,
                                        lk_batcher **out) {
-    if (!ctx || !out) return LK_ERR_INVALID;
-    *out = nullptr;
-    if (max_regions < 1 || max_wait_us < 0) return lk_fail(ctx, LK_ERR_INVALID, "bad batcher arguments");
-    lk_batcher *b = new (std::nothrow) lk_batcher();
-    if (!b) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
-    b->ctx = ctx;
-    b->engine = args != nullptr;
-    if (args) b->args = *args;
-    b->max_regions = max_regions;
-    b->max_wait_us = max_wait_us;
-    for (int w = 0; w < lk_batcher::kWorkers; w++) b->workers[w] = std::thread([b, w] { b->run(w); });
-    *out = b;
-    return LK_OK;
+    return batcher_create(&ctx, 1, args, max_regions, max_wait_us, out);
+}
+
+lk_status lk_batcher_create_multi(lk_ctx *const *ctxs, int n_ctx, const lk_engine_args *args, int32_t max_regions,
+                                  int32_t max_wait_us, lk_batcher **out) {
+    return batcher_create(ctxs, n_ctx, args, max_regions, max_wait_us, out);
 }
 
 extern "C" void lk_batcher_destroy(lk_batcher *b) {
@@ -196,8 +244,8 @@ extern "C" void lk_batcher_destroy(lk_batcher *b) {
         b->stop = true;
     }
     b->cv_work.notify_all();
-    for (auto &t : b->workers)
-        if (t.joinable()) t.join();
+    for (auto &w : b->workers)
+        if (w.thread.joinable()) w.thread.join();
     delete b;
 }
 
@@ -214,6 +262,8 @@ extern "C" lk_status lk_batcher_submit_async(lk_batcher *b, const lk_pairhmm_bat
     int64_t np = 0;
     if (lk_pairhmm_batch_dims(region, &np, nullptr) != LK_OK) return LK_ERR_INVALID;
     if (np > 0 && !values) return LK_ERR_INVALID;
+    // a request that could only fail inside a merged batch is rejected here, so it cannot take co-batched callers down
+    if (b->engine && !b->args.disable_cap_read_qualities_to_mapq && !read_mapq && region->region_read_start[1] > 0) return LK_ERR_INVALID;
     lk_ticket *t = new (std::nothrow) lk_ticket();
     if (!t) return LK_ERR_NOMEM;
     Request &q = t->q;

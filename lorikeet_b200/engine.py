@@ -31,7 +31,7 @@ class PairHMMLikelihoodCalculationEngine:
                  base_quality_score_threshold=18, dynamic_read_disqualification=False, read_disqualification_scale=1.0,
                  expected_error_rate_per_base=0.02, symmetrically_normalize_alleles_to_reference=True,
                  disable_cap_read_qualities_to_mapq=False, modify_soft_clipped_bases=False, avx_mode=AVXMode.GPU):
-        assert isinstance(ctx, Context)
+        assert ctx is None or isinstance(ctx, (Context, DevicePool))
         self.ctx = ctx
         self.args = _lib.EngineArgs(int(constant_gcp), float(log10_global_read_mismapping_rate), int(pcr_error_model),
                                     int(base_quality_score_threshold), 1 if dynamic_read_disqualification else 0,
@@ -187,18 +187,76 @@ class SmithWatermanAligner:
         return cigar, off
 
 
+class DevicePool:
+    """Several GPUs behind one handle in ONE process (lk_pool_*): the batch calls deal contiguous chunks of about
+    equal cell counts to one host thread per device; RegionBatcher(pool, ...) batches per-region calls over all devices."""
+
+    def __init__(self, devices=None):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        if devices is None:
+            st = self._L.lk_pool_create(None, 0, C.byref(self._h))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            st = self._L.lk_pool_create(arr, len(devices), C.byref(self._h))
+        if st != _lib.LK_OK:
+            raise _lib.LorikeetError(st, "lk_pool_create failed (no CUDA device? there is no CPU fallback)")
+
+    def _check(self, st):
+        if st != _lib.LK_OK:
+            raise _lib.LorikeetError(st, (self._L.lk_pool_last_error(self._h) or b"").decode())
+
+    @property
+    def device_count(self):
+        return int(self._L.lk_pool_device_count(self._h))
+
+    def pairhmm_batch(self, batch, want_flags=False):
+        out = np.empty(batch.n_pairs, dtype=np.float64)
+        flags = np.zeros(batch.n_pairs, dtype=np.uint8)
+        s = batch.as_struct()
+        self._check(self._L.lk_pool_pairhmm_batch_host(self._h, C.byref(s), out.ctypes.data_as(_lib.f64p), flags.ctypes.data_as(_lib.u8p)))
+        return (out, flags) if want_flags else out
+
+    def compute_read_likelihoods(self, engine, batch, read_mapq, ref_allele_index=None, values=None, keep=None):
+        """lk_pool_compute_read_likelihoods with the arguments of `engine` (a PairHMMLikelihoodCalculationEngine)."""
+        if values is None:
+            values = np.empty(batch.n_pairs, dtype=np.float64)
+        if keep is None:
+            keep = np.ones(batch.n_reads, dtype=np.uint8)
+        mapq = np.ascontiguousarray(read_mapq, dtype=np.uint8)
+        ref = None if ref_allele_index is None else np.ascontiguousarray(ref_allele_index, dtype=np.int32)
+        s = batch.as_struct()
+        self._check(self._L.lk_pool_compute_read_likelihoods(self._h, C.byref(engine.args), C.byref(s), mapq.ctypes.data_as(_lib.u8p),
+                                                             ref.ctypes.data_as(_lib.i32p) if ref is not None else C.cast(None, _lib.i32p),
+                                                             values.ctypes.data_as(_lib.f64p), keep.ctypes.data_as(_lib.u8p)))
+        return values, keep
+
+    def close(self):
+        if self._h:
+            self._L.lk_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 class RegionBatcher:
     """Cross-thread batching front-end (lk_batcher, include/lorikeet_b200.h): worker threads submit ONE region each, as
     Lorikeet's Rayon tasks do (assembly_region_walker.rs:140-277); a dispatcher thread inside the library runs one launch
     for everything pending.  engine=None batches bare PairHMM calls."""
 
     def __init__(self, ctx, engine=None, max_regions=256, max_wait_us=200):
+        """ctx: a Context (one device) or a DevicePool (the dispatcher threads of all its devices share one queue)."""
         self.ctx = ctx
         self.engine = engine
         self._L = _lib.load()
         self._h = C.c_void_p()
         args = C.byref(engine.args) if engine is not None else None
-        ctx._check(self._L.lk_batcher_create(ctx._h, args, int(max_regions), int(max_wait_us), C.byref(self._h)))
+        create = self._L.lk_pool_batcher_create if isinstance(ctx, DevicePool) else self._L.lk_batcher_create
+        ctx._check(create(ctx._h, args, int(max_regions), int(max_wait_us), C.byref(self._h)))
 
     def submit(self, region, read_mapq=None, ref_allele_index=0):
         """Blocking; returns (values, keep) for an engine batcher, (log10 likelihoods [r*A + h], flags) otherwise."""

@@ -1,9 +1,10 @@
 // bench_batcher.cpp — developer check of the drop-in call pattern: T host threads each submit ONE region at a time to
 // lk_batcher (what Lorikeet's Rayon workers would do through the Rust binding, assembly_region_walker.rs:140-277),
 // next to the same regions handed to lk_engine_compute_read_likelihoods in one call.
-//   g++ -O2 -std=c++17 -I include tools/native/bench_batcher.cpp -L lorikeet_b200 -llorikeet_b200 -lpthread -o bench_batcher
-//   LD_LIBRARY_PATH=lorikeet_b200 ./bench_batcher [regions=4000] [threads=32] [max_regions=512] [max_wait_us=200] [in_flight=1]
+//   (built by lorikeet_b200/csrc/build.sh into tools/native/bench_batcher)
+//   tools/native/bench_batcher [regions=4000] [threads=32] [max_regions=512] [max_wait_us=200] [in_flight=1] [devices=1] [first_device=0]
 // in_flight > 1: every thread keeps that many regions queued through lk_batcher_submit_async / lk_batcher_wait
+// devices: GPUs in the lk_pool (0 = every visible one); ONE process drives them all.  The last line is JSON.
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -25,6 +26,8 @@ int main(int argc, char **argv) {
     const int max_regions = argc > 3 ? atoi(argv[3]) : 512;
     const int max_wait_us = argc > 4 ? atoi(argv[4]) : 200;
     const int depth = argc > 5 ? std::max(1, atoi(argv[5])) : 1;
+    const int n_dev_arg = argc > 6 ? atoi(argv[6]) : 1;
+    const int first_dev = argc > 7 ? atoi(argv[7]) : 0;
     lk_synth_params p;
     memset(&p, 0, sizeof p);
     p.seed_base = 0x4C4B0000; p.n_reads = 64; p.read_len = 150; p.n_haps = 16; p.hap_len = 300; p.min_edits = 1; p.max_edits = 4;
@@ -34,8 +37,13 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> rb(R * p.read_len), rq(rb.size()), ri(rb.size()), rd(rb.size()), hb(G * lk_synth_max_hap_bytes_per_region(&p));
     if (lk_synth_pairhmm_regions(&p, 0, G, rrs.data(), rhs.data(), roff.data(), rb.data(), rq.data(), ri.data(), rd.data(), hoff.data(), hb.data(), 0) != LK_OK) return 1;
     std::vector<uint8_t> mapq(R, 60);
-    lk_ctx *ctx = nullptr;
-    if (lk_create(0, &ctx) != LK_OK) { fprintf(stderr, "no CUDA device\n"); return 2; }
+    lk_pool *pool = nullptr;
+    {
+        std::vector<int> devs;
+        for (int d = 0; d < n_dev_arg; d++) devs.push_back(first_dev + d);
+        if (lk_pool_create(n_dev_arg > 0 ? devs.data() : nullptr, n_dev_arg, &pool) != LK_OK) { fprintf(stderr, "no CUDA device / bad device list\n"); return 2; }
+    }
+    const int n_dev = lk_pool_device_count(pool);
     lk_engine_args args;
     memset(&args, 0, sizeof args);
     args.constant_gcp = 10; args.log10_global_read_mismapping_rate = -4.5; args.pcr_error_model = LK_PCR_CONSERVATIVE;
@@ -54,13 +62,19 @@ int main(int argc, char **argv) {
     double best = 1e30;
     for (int it = 0; it < 3; it++) {
         const double t0 = now_ms();
-        if (lk_engine_compute_read_likelihoods(ctx, &args, &all, mapq.data(), nullptr, direct.data(), keep_d.data()) != LK_OK) { fprintf(stderr, "%s\n", lk_last_error(ctx)); return 3; }
+        if (lk_pool_compute_read_likelihoods(pool, &args, &all, mapq.data(), nullptr, direct.data(), keep_d.data()) != LK_OK) { fprintf(stderr, "%s\n", lk_pool_last_error(pool)); return 3; }
         best = std::min(best, now_ms() - t0);
     }
-    printf("one call            regions=%lld  %.1f ms  %.0f GCUPS\n", (long long)G, best, n_cells / best / 1e6);
+    const double one_call_gcups = n_cells / best / 1e6;
+    printf("one call (%d device%s)  regions=%lld  %.1f ms  %.0f GCUPS\n", n_dev, n_dev > 1 ? "s" : "", (long long)G, best, one_call_gcups);
+    // single-device reference for the bit-for-bit check of the pooled results
+    std::vector<double> single(n_pairs);
+    std::vector<uint8_t> keep_s(R);
+    if (lk_engine_compute_read_likelihoods(lk_pool_ctx(pool, 0), &args, &all, mapq.data(), nullptr, single.data(), keep_s.data()) != LK_OK) return 3;
+    const bool pool_same = memcmp(direct.data(), single.data(), n_pairs * 8) == 0 && memcmp(keep_d.data(), keep_s.data(), R) == 0;
     // ---- T threads, one region per submit ----
     lk_batcher *bt = nullptr;
-    if (lk_batcher_create(ctx, &args, max_regions, max_wait_us, &bt) != LK_OK) return 4;
+    if (lk_pool_batcher_create(pool, &args, max_regions, max_wait_us, &bt) != LK_OK) return 4;
     std::vector<int64_t> pair_base(G + 1, 0);
     for (int64_t g = 0; g < G; g++) pair_base[g + 1] = pair_base[g] + (rrs[g + 1] - rrs[g]) * (rhs[g + 1] - rhs[g]);
     best = 1e30;
@@ -105,9 +119,12 @@ int main(int argc, char **argv) {
     int64_t nb = 0, nr = 0;
     lk_batcher_stats(bt, &nb, &nr);
     printf("batcher %2d threads x %d in flight  regions=%lld  %.1f ms  %.0f GCUPS  (%.1f regions per launch)\n", T, depth, (long long)G, best, n_cells / best / 1e6, (double)nr / (double)nb);
-    const bool same = memcmp(direct.data(), viab.data(), n_pairs * 8) == 0 && memcmp(keep_d.data(), keep_b.data(), R) == 0;
-    printf("batcher results %s the one-call results\n", same ? "are bit-identical to" : "DIFFER from");
+    const bool same = pool_same && memcmp(single.data(), viab.data(), n_pairs * 8) == 0 && memcmp(keep_s.data(), keep_b.data(), R) == 0;
+    printf("pooled one-call and batcher results %s the single-device one-call results\n", same ? "are bit-identical to" : "DIFFER from");
+    printf("{\"devices\": %d, \"threads\": %d, \"in_flight\": %d, \"regions\": %lld, \"one_call_gcups\": %.1f, \"batcher_gcups\": %.1f, "
+           "\"regions_per_launch\": %.1f, \"bit_identical\": %s}\n", n_dev, T, depth, (long long)G, one_call_gcups, n_cells / best / 1e6,
+           (double)nr / (double)nb, same ? "true" : "false");
     lk_batcher_destroy(bt);
-    lk_destroy(ctx);
+    lk_pool_destroy(pool);
     return same ? 0 : 6;
 }
