@@ -201,8 +201,9 @@ def run_extras(ctx, args, peak_fp32):
 
 
 # figures read from the committed ncu capture of the SW kernel (never measured inside the bench)
-SW_NCU = {"instr_per_cell": 20.2, "dram_bytes_per_cell": 1.26,
-          "source": "profiles/r01_sw_kernel_k17_final_ncu_details.txt"}
+SW_NCU = {"instr_per_cell": 17.9, "dram_bytes_per_cell": 0.80,
+          "source": "profiles/r02_sw_kernel_k17_metrics.txt (20 000 cfg4 pairs: 9.67e10 thread instructions, 3.07 GB written + "
+                    "1.28 GB read over 5.408e9 cells)"}
 
 
 def run_reference(args, rank):

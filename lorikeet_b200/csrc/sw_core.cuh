@@ -18,9 +18,11 @@
 //     ho  a horizontal gap was (re)opened at this cell  (gap_size_h[i] reset to 1, :235-239)
 //     vo  a vertical gap was (re)opened at this cell    (gap_size_v[j] reset to 1, :212-218)
 // from which the stored gap length k of the reference's btrack (-ki / +kd) is recovered during the
-// traceback by walking back to the cell where the gap was opened.  Bit k of a plane word belongs to
-// the lane's k-th row; the four words of one (step, lane) are stored as one 16-byte element,
-// step-major ([step][lane]) so every warp store is one coalesced 512-byte run.
+// traceback by walking back to the cell where the gap was opened.  The planes of one (step, lane) are packed into
+// TWO words -- (pd, pr) interleaved in one, (vo, ho) in the other, two bits per row for the lane's first 16 rows --
+// stored step-major ([step][lane], 8 bytes each) so every warp store is one coalesced 256-byte run; a 17th row
+// (K = 17, the variant 520-row haplotype pairs use) adds one byte per (step, lane) in a second step-major array.
+// That is 0.53 B/cell of backtrack traffic at K = 17 (the first version stored four 32-bit planes: 0.94 B/cell).
 // Per cell: compare+select+add (diagonal), add + VIADDMNMX + compare (each gap direction),
 // max + 2 compares + VIMNMX3 (choice, the -1e8 clamp rides in the 3-input max), 4 predicated ORs.
 #pragma once
@@ -117,11 +119,16 @@ LK_DEV int32_t sw_pick(const int32_t (&H)[K], int k) {
     return v;
 }
 
-// number of backtrack words one pair needs (host + device agree on this)
+// number of backtrack words one pair needs (host + device agree on this): per band and (step, lane) two plane words,
+// plus one byte when K > 16
+LK_HD int64_t sw_band_words(int m, int K) {
+    const int64_t steps = (int64_t)m + 32;
+    return steps * 32 * 2 + (K > 16 ? steps * 8 : 0);
+}
 LK_HD int64_t sw_bt_words(int n, int m, int K) {
     const int band_rows = 32 * K;
     const int n_bands = (n + band_rows - 1) / band_rows;
-    return (int64_t)n_bands * (int64_t)(m + 32) * 4 * 32;  // one uint4 of bit-planes per (step, lane)
+    return (int64_t)n_bands * sw_band_words(m, K);
 }
 
 // CLAMP = false drops the max(-1e8, .) of smith_waterman_aligner.rs:31,248-260 from the cell: the host proves per launch
@@ -134,8 +141,14 @@ LK_HD bool sw_clamp_inactive(int64_t nm_max, int32_t wm, int32_t wx, int32_t wo,
     return (nm_max + 2) * mx < 100000000LL;
 }
 
-// words of per-warp scratch one pair needs: backtrack planes, two band-boundary rows, one class byte per alternate base
-LK_HD int64_t sw_scratch_words(int n, int m, int K) { return sw_bt_words(n, m, K) + 2 * ((int64_t)m + 1) + ((int64_t)m + 3) / 4 + 36; }
+// words of per-warp scratch one pair needs: backtrack planes, two band-boundary rows, the bottom row, one class byte per
+// alternate base (even, so that every warp's slice keeps the 8-byte alignment of the plane stores)
+LK_HD int64_t sw_scratch_words(int n, int m, int K) {
+    const int64_t w = sw_bt_words(n, m, K) + 3 * ((int64_t)m + 1) + ((int64_t)m + 3) / 4 + 36;
+    return (w + 1) & ~(int64_t)1;
+}
+struct SwLeanTag { static constexpr bool value = true; };
+struct SwGenericTag { static constexpr bool value = false; };
 
 template <class Wp, int K, bool CLAMP = true>
 LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, int32_t *wtab) {
@@ -179,15 +192,19 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
     // ---- fill -----------------------------------------------------------------------------------
     const int32_t wm = A.w_match, wx = A.w_mismatch, wo = A.w_open, we = A.w_extend;
     const bool edge_gaps = (strategy == SW_INDEL || strategy == SW_LEADING_INDEL);  // :146-179
+    const bool need_bottom = (strategy == SW_SOFTCLIP || strategy == SW_IGNORE);    // the bottom row is searched only then (:316)
     const int BAND = 32 * K;
     const int n_bands = (n + BAND - 1) / BAND;
-    static_assert(K <= 32, "one plane bit per row");
-    const int64_t band_words = (int64_t)(m + 32) * 4 * 32;
-    uint32_t *bt = scratch;                                         // [band][step][lane] x uint4 {pd, pr, ho, vo}
-    int32_t *bndH = (int32_t *)(scratch + sw_bt_words(n, m, K));    // two boundary rows: H then F
+    static_assert(K <= 17, "two plane bits per row in one word for 16 rows, one extra byte for a 17th");
+    constexpr int PR = K < 16 ? K : 16;  // rows of a lane whose bits live in the two plane words
+    constexpr bool HAS_NIB = K > 16;     // row 16 of a lane: one byte per (step, lane)
+    const int64_t band_words = sw_band_words(m, K);
+    uint32_t *bt = scratch;                                         // [band]: [step][lane] x 2 words, then [step][lane] bytes
+    int32_t *bndH = (int32_t *)(scratch + sw_bt_words(n, m, K));    // band-boundary row: H then F
     int32_t *bndF = bndH + (m + 1);
+    int32_t *botH = bndF + (m + 1);                                 // bottom row of the matrix, one value per column
     // class of every alternate base, once per pair; the weight table is used when all of them are A C G T N (warp-uniform)
-    uint8_t *acls = (uint8_t *)(bndF + (m + 1));
+    uint8_t *acls = (uint8_t *)(botH + (m + 1));
     bool use_table;
     {
         bool other = false;
@@ -199,11 +216,9 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
         use_table = w.ballot(other) == 0u;
         w.sync();
     }
-    // best cell of the last column (scan top->bottom with >=, :301-307) and bottom-row summary
+    // best cell of the last column (scan top->bottom with >=, :301-307)
     int32_t col_max = (int32_t)(-2147483647 - 1);
     int col_p1 = 0;
-    int32_t bot_max = (int32_t)(-2147483647 - 1);
-    int bot_j = 0;
 
     for (int band = 0; band < n_bands; band++) {
         const int row0 = band * BAND;  // rows row0+1 .. row0+rows (1-based)
@@ -229,40 +244,47 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
         w.sync();
         // column 0 of the row above this lane's strip
         const int i_above = row0 + lane * K;  // matrix row index of the row above (0 = top row)
-        int32_t Hd = (i_above == 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
+        const int32_t hd0 = (i_above == 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
+        int32_t Hd = hd0;
+        // (Hu, Fu) = the row above at this lane's column of the coming step.  Lane 0's comes from the matrix top row (band 0:
+        // sw[0][c] = 0, or open + (c-1) extend for the edge-gap strategies, :146-179) or from the previous band's last row.
         int32_t Hu = 0, Fu = SW_LOW_INIT;
+        const int32_t hu_inc = (band == 0 && edge_gaps) ? we : 0;
+        if (lane == 0) {
+            if (band == 0) Hu = edge_gaps ? wo : 0;
+            else { Hu = bndH[1]; Fu = bndF[1]; }
+        }
         uint32_t *btb = bt + (int64_t)band * band_words;
+        uint8_t *btn = (uint8_t *)(btb + ((int64_t)m + 32) * 64);  // row-16 nibbles of the band (K = 17)
         const bool has_bottom = (band == n_bands - 1);
         const int bottom_lane = (rows - 1) / K, bottom_k = (rows - 1) % K;
+        const bool keeps_bottom = need_bottom && has_bottom && lane == bottom_lane;
+        const bool writes_bnd = !has_bottom && lane == lanes - 1;
         const int n_steps = m + lanes - 1;
 
         int cls_ahead = (use_table && lane == 0) ? (int)acls[0] : 0;  // column of step 1 (only lane 0 is active then)
-        for (int s = 1; s <= n_steps; s++) {
+        // One step of the wavefront.  LEAN: every lane's column is inside [1, m-1] (steps 32 .. m-1), so nothing is gated; lanes
+        // past the reference's last row then run on rows that never match -- their cells are never read.
+        auto step = [&](int s, auto lean_tag, bool band0) {
+            constexpr bool LEAN = decltype(lean_tag)::value;
             const int c = s - lane;
-            // row above lane 0 comes from the matrix top row or from the previous band (selects, not a divergent branch)
-            if (band == 0) {
-                const int32_t top = edge_gaps ? (wo + (c - 1) * we) : 0;
-                Hu = lane == 0 ? top : Hu;
-                Fu = lane == 0 ? SW_LOW_INIT : Fu;
-            } else if (lane == 0 && c <= m) { Hu = bndH[c]; Fu = bndF[c]; }
-            const bool active = (c >= 1) && (c <= m) && (lane < lanes);
+            const bool active = LEAN || ((c >= 1) && (c <= m) && (lane < lanes));
             // class of the NEXT step's column, fetched one step ahead so its latency hides behind this step's cells
-            const int cls_next = cls_ahead;
-            if (use_table) cls_ahead = (c >= 0 && c < m) ? (int)acls[c] : 0;
+            const int cls_now = cls_ahead;
+            if (use_table) cls_ahead = (LEAN || (c >= 0 && c < m)) ? (int)acls[c] : 0;
             int32_t h_last = 0, f_last = SW_LOW_INIT;
             if (active) {
                 int32_t wt[KQ * 4];
                 if (use_table) {
-                    const int cls = cls_next;
 #pragma unroll
-                    for (int q = 0; q < KQ; q++) w.lds4i(wt + 4 * q, wtab + ((cls * KQ + q) * 32 + lane) * 4);
+                    for (int q = 0; q < KQ; q++) w.lds4i(wt + 4 * q, wtab + ((cls_now * KQ + q) * 32 + lane) * 4);
                 } else {  // some alternate byte is outside ACGTN: raw byte compare for this pair, as the reference does everywhere
                     const uint32_t ab = w.ldg(alt + c - 1);
 #pragma unroll
                     for (int k = 0; k < K; k++) wt[k] = (rb[k] == ab) ? wm : wx;
                 }
                 int32_t hdiag = Hd, hup = Hu, fup = Fu;
-                uint32_t pl_d = 0u, pl_r = 0u, pl_h = 0u, pl_v = 0u;
+                uint32_t pw_m = 0u, pw_g = 0u, nib = 0u;  // (pd, pr) pairs; (vo, ho) pairs; row 16's four bits
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const int32_t hold = H[k];
@@ -282,41 +304,80 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
                         best = sw_max3(step_diag, step_right, step_down);
                         not_diag = step_diag - best;
                     }
-                    // each plane shifts in the SIGN BIT of a difference (one funnel shift per bit; the subtractions can
-                    // issue on the FMA pipe): row k ends up at bit K-1-k
-                    pl_v = sw_push_sign(pl_v, ext_v - step_down);      // set: opened (hup + wo > fup + we)
-                    pl_h = sw_push_sign(pl_h, ext_h - step_right);     // set: opened
-                    pl_d = sw_push_sign(pl_d, not_diag);               // set: NOT diagonal (:248-252 wants diag >= both)
-                    pl_r = sw_push_sign(pl_r, step_right - step_down); // set: vertical (right < down), clear: horizontal
+                    // each plane bit is the SIGN BIT of a difference, shifted in by one funnel shift (the subtractions can issue
+                    // on the FMA pipe): row k ends up at bits 2 (PR-1-k) + {1, 0} of its word
+                    if (k < 16) {
+                        pw_g = sw_push_sign(pw_g, ext_v - step_down);      // vo set: opened (hup + wo > fup + we)
+                        pw_g = sw_push_sign(pw_g, ext_h - step_right);     // ho set: opened
+                        pw_m = sw_push_sign(pw_m, not_diag);               // pd set: NOT diagonal (:248-252 wants diag >= both)
+                        pw_m = sw_push_sign(pw_m, step_right - step_down); // pr set: vertical (right < down), clear: horizontal
+                    } else {
+                        nib = sw_push_sign(nib, ext_v - step_down);
+                        nib = sw_push_sign(nib, ext_h - step_right);
+                        nib = sw_push_sign(nib, not_diag);
+                        nib = sw_push_sign(nib, step_right - step_down);
+                    }
                     E[k] = step_right;
                     H[k] = best;
                     hdiag = hold; hup = best; fup = step_down;
                 }
                 h_last = H[K - 1]; f_last = fup;
-                w.store4(btb + ((int64_t)s * 32 + lane) * 4, pl_d, pl_r, pl_h, pl_v);
-                if (c == m) {  // this lane's rows of the last column, top -> bottom with >=  (:301-307)
+                w.store2(btb + ((int64_t)s * 32 + lane) * 2, pw_m, pw_g);
+                if (HAS_NIB) btn[(int64_t)s * 32 + lane] = (uint8_t)nib;
+                if (!LEAN && c == m) {  // this lane's rows of the last column, top -> bottom with >=  (:301-307)
 #pragma unroll
                     for (int k = 0; k < K; k++) {
                         const int i = row0 + lane * K + k + 1;
                         if (i <= n && H[k] >= col_max) { col_max = H[k]; col_p1 = i; }
                     }
                 }
-                if (has_bottom) {  // bottom row summary (:316-329), see below.  Every lane keeps one for its row at register
-                    // bottom_k (warp-uniform index, no divergence); only bottom_lane's is read afterwards.
-                    int32_t cur = sw_pick<K>(H, bottom_k);
-                    const int dj = (n > c) ? (n - c) : (c - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
-                    if (cur > bot_max || (cur == bot_max && dj < db)) { bot_max = cur; bot_j = c; }
-                }
-                if (!has_bottom && lane == lanes - 1) { bndH[c] = h_last; bndF[c] = f_last; }
+                // the matrix's bottom row goes to scratch, one value per column; its summary (:316-329) is taken after the fill
+                if (keeps_bottom) botH[c] = sw_pick<K>(H, bottom_k);
+                if (writes_bnd) { bndH[c] = h_last; bndF[c] = f_last; }
             }
             // hand the strip's last row to the next lane; keep this step's "up" as next step's diagonal
             Hd = Hu;
             const int32_t hs = w.shfl_up1(h_last), fs = w.shfl_up1(f_last);
-            if (lane != 0) { Hu = hs; Fu = fs; }
+            if (band0) {
+                Hu = (lane != 0) ? hs : Hu + hu_inc;  // lane 0: next column of the top row
+                Fu = (lane != 0) ? fs : Fu;
+            } else {
+                int32_t lh = hs, lf = fs;
+                if (lane == 0 && (LEAN || s + 1 <= m)) { lh = bndH[s + 1]; lf = bndF[s + 1]; }  // previous band's last row
+                Hu = lh; Fu = lf;
+            }
             // a lane that has not started yet must keep seeing column 0 of the row above as its diagonal
-            if (c < 1) Hd = (i_above == 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
+            if (!LEAN && c < 1) Hd = hd0;
+        };
+        const int s_lean_end = m - 1;  // last step at which lane 0's column is still < m
+        int s = 1, gen_end = n_steps < 31 ? n_steps : 31;
+        for (;;) {  // generic start-up, lean middle, generic tail (one copy of the generic loop in the code)
+            for (; s <= gen_end; ++s) step(s, SwGenericTag(), band == 0);
+            if (gen_end == n_steps) break;
+            if (band == 0) { for (; s <= s_lean_end; ++s) step(s, SwLeanTag(), true); }
+            else { for (; s <= s_lean_end; ++s) step(s, SwLeanTag(), false); }
+            gen_end = n_steps;
         }
         w.sync();
+    }
+
+    // ---- bottom row summary (:316-329): the reference scans it left->right taking a cell if it is strictly better, or equal
+    // and closer to the diagonal than the current best.  Its outcome depends only on the row maximum and on the maximal cell
+    // closest to the diagonal (leftmost on ties): every lane scans its columns in that order, then the lanes are combined. ----
+    int32_t bot_max = (int32_t)(-2147483647 - 1);
+    int bot_j = 0;
+    if (need_bottom) {
+        for (int c = lane + 1; c <= m; c += 32) {
+            const int32_t cur = botH[c];
+            const int dj = (n > c) ? (n - c) : (c - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
+            if (cur > bot_max || (cur == bot_max && dj < db)) { bot_max = cur; bot_j = c; }
+        }
+        for (int d = 16; d >= 1; d >>= 1) {
+            const int32_t ov = w.shfl_xor(bot_max, d);
+            const int oj = w.shfl_xor(bot_j, d);
+            const int dj = (n > oj) ? (n - oj) : (oj - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
+            if (ov > bot_max || (ov == bot_max && (dj < db || (dj == db && oj < bot_j)))) { bot_max = ov; bot_j = oj; }
+        }
     }
 
     // ---- start cell (:288-333) -------------------------------------------------------------------
@@ -325,11 +386,6 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
         const int32_t ov = w.shfl_xor(col_max, d);
         const int op = w.shfl_xor(col_p1, d);
         if (ov > col_max || (ov == col_max && op > col_p1)) { col_max = ov; col_p1 = op; }
-    }
-    {
-        const int bl = ((n - (n_bands - 1) * BAND) - 1) / K;
-        bot_max = w.shfl(bot_max, bl);
-        bot_j = w.shfl(bot_j, bl);
     }
     int p1, p2;
     int32_t segment_length = 0;
@@ -353,11 +409,21 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
     // nibble of matrix cell (i, j), 1-based: bits 0-1 move (0 diagonal, 1 horizontal, 2 vertical), bit 2 ho, bit 3 vo
     auto nibble = [&](int i, int j) -> uint32_t {
         const int band = (i - 1) / BAND, r = (i - 1) % BAND, ln = r / K, k = r % K;
+        const uint32_t *bb = bt + (int64_t)band * band_words;
+        const int64_t el = (int64_t)(j + ln) * 32 + ln;  // the cell was written at step j + ln by lane ln
         uint32_t pd, pr, ho, vo;
-        w.load4(bt + (int64_t)band * band_words + ((int64_t)(j + ln) * 32 + ln) * 4, pd, pr, ho, vo);
-        const int bit = K - 1 - k;  // planes were filled by shifting left once per row
-        const uint32_t mv = ((pd >> bit) & 1u) ? (((pr >> bit) & 1u) ? 2u : 1u) : 0u;
-        return mv | (((ho >> bit) & 1u) << 2) | (((vo >> bit) & 1u) << 3);
+        if (HAS_NIB && k == 16) {
+            const uint32_t nb = ((const uint8_t *)(bb + ((int64_t)m + 32) * 64))[el];
+            vo = (nb >> 3) & 1u; ho = (nb >> 2) & 1u; pd = (nb >> 1) & 1u; pr = nb & 1u;
+        } else {
+            uint32_t pw_m, pw_g;
+            w.load2(bb + el * 2, pw_m, pw_g);
+            const int sh = 2 * (PR - 1 - k);  // the words were filled by shifting left twice per row
+            pd = (pw_m >> (sh + 1)) & 1u; pr = (pw_m >> sh) & 1u;
+            vo = (pw_g >> (sh + 1)) & 1u; ho = (pw_g >> sh) & 1u;
+        }
+        const uint32_t mv = pd ? (pr ? 2u : 1u) : 0u;
+        return mv | (ho << 2) | (vo << 3);
     };
     int n_out = 0;
     bool overflow = false;

@@ -19,6 +19,11 @@ struct SwDevWarp {
     __device__ __forceinline__ void store4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
         *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
     }
+    __device__ __forceinline__ void store2(uint32_t *p, uint32_t a, uint32_t b) const { *reinterpret_cast<uint2 *>(p) = make_uint2(a, b); }
+    __device__ __forceinline__ void load2(const uint32_t *p, uint32_t &a, uint32_t &b) const {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        a = v.x; b = v.y;
+    }
     __device__ __forceinline__ void lds4i(int32_t *dst, const int32_t *src) const {
         const int4 v = *reinterpret_cast<const int4 *>(src);
         dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;

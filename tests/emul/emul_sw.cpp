@@ -45,6 +45,8 @@ struct SwEmulWarp {
     template <class T> T ldg(const T *p) const { return *p; }
     void sync() { sh->bar.arrive_and_wait(); }
     void store4(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
+    void store2(uint32_t *p, uint32_t a, uint32_t b) const { p[0] = a; p[1] = b; }
+    void load2(const uint32_t *p, uint32_t &a, uint32_t &b) const { a = p[0]; b = p[1]; }
     void lds4i(int32_t *dst, const int32_t *src) const { memcpy(dst, src, 16); }
     void load4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const { a = p[0]; b = p[1]; c = p[2]; d = p[3]; }
 };

@@ -62,3 +62,28 @@ def test_bytes_outside_acgtn_take_the_compare_path():
     pairs = SC.random_pairs(40, seed=17, alphabet=b"ACGTNacgtRY-")
     for strategy in ("SoftClip", "InDel"):
         _compare(pairs, SC.NEW_SW_PARAMETERS, strategy)
+
+
+@pytest.mark.parametrize("force_k", [16, 17])
+def test_lean_steps_and_packed_planes(force_k):
+    # references of 500..544 rows against alternates of 450..560 columns: the ungated middle steps (32 .. m-1) carry almost
+    # all cells, K = 16 uses the two plane words only, K = 17 also the row-16 byte; every strategy (bottom-row summary from
+    # scratch for SoftClip / Ignore, band-boundary feed when K = 16 needs a second band for > 512 rows)
+    rng = np.random.default_rng(force_k)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    pairs = []
+    for n in (500, 512, 513, 544):
+        ref = rng.choice(acgt, n)
+        alt = ref.copy()
+        for _ in range(3):  # a few indels and SNPs
+            p = int(rng.integers(20, len(alt) - 20))
+            if rng.random() < 0.5:
+                alt = np.delete(alt, slice(p, p + int(rng.integers(1, 12))))
+            else:
+                alt = np.insert(alt, p, rng.choice(acgt, int(rng.integers(1, 12))))
+        alt[rng.integers(0, len(alt), 5)] = rng.choice(acgt, 5)
+        pairs.append((bytes(ref), bytes(alt)))
+    pairs.append((bytes(rng.choice(acgt, 520)), bytes(rng.choice(acgt, 470))))  # unrelated
+    for strategy in SC.STRATEGIES:
+        _compare(pairs, SC.NEW_SW_PARAMETERS, strategy, max_ops=512, force_k=force_k)
+    _compare(pairs, SC.STANDARD_NGS, "LeadingInDel", max_ops=512, force_k=force_k)
