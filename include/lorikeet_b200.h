@@ -100,6 +100,14 @@ typedef struct lk_pairhmm_batch {
     uint8_t gcp_constant;
     const int64_t *hap_off;           /* n_haps + 1    */
     const uint8_t *hap_bases;
+    /* Optional: several SAMPLES per region.  The reference computes one [A x R_s] matrix per sample over the region's
+     * shared haplotypes and normalises / filters each on its own (pair_hmm_likelihood_calculation_engine.rs:201-239,
+     * 321-340).  Region g owns samples [region_sample_start[g], region_sample_start[g+1]); sample s owns reads
+     * [sample_read_start[s], sample_read_start[s+1]); the samples of a region tile its reads in order.  Both NULL: every
+     * region is one sample.  Only the region driver (and the batcher in engine mode) looks at them: haplotypes are staged
+     * and encoded once per region however many samples share them; lk_pairhmm_batch_host's [r*A + h] layout is unaffected. */
+    const int64_t *region_sample_start; /* n_regions + 1, or NULL */
+    const int64_t *sample_read_start;   /* n_samples + 1, or NULL */
 } lk_pairhmm_batch;
 
 /* Number of (read, haplotype) pairs = sum_g reads_g * haps_g, and sum of R*H over them. */
@@ -209,7 +217,10 @@ lk_status lk_calculate_cigar_finish(const uint8_t *ref, int64_t ref_len, const u
 
 /*
  * Batch form of AssemblyBasedCallerUtils::realign_reads_to_their_best_haplotype
- * (src/assembly/assembly_based_caller_utils.rs:208-246) for single-sample regions.
+ * (src/assembly/assembly_based_caller_utils.rs:208-246); regions may hold several samples (see the struct).
+ * `values` may be HOST memory or memory of the context's device (e.g. the buffer lk_engine_compute_read_likelihoods
+ * just filled): in the second case the best-allele search runs as a kernel on the matrices where they are and only one
+ * int32 + one flag per read come back to the host.
  * Per read: the best haplotype with the reference's tie-breaking (AlleleLikelihoods::search_best_allele with
  * priorities, src/model/allele_likelihoods.rs:457-554; priority = is_ref + 1 - cigar elements,
  * assembly_based_caller_utils.rs:187-195), then AlignmentUtils::create_read_aligned_to_ref
@@ -239,6 +250,12 @@ typedef struct lk_realign_batch {
     const uint32_t *read_cigars;       /* the reads' original CIGARs (their clips are re-attached) */
     const int64_t *read_orig_len;      /* original read lengths (with soft clips) */
     double informative_threshold;      /* 0 = LOG_10_INFORMATIVE_THRESHOLD (0.2) */
+    /* Optional: several samples per region, as in lk_pairhmm_batch: `values` then holds per region one [A_g x R_s] block
+     * per sample, consecutive (what lk_engine_compute_read_likelihoods returns for such a batch), and sample_n_evidence
+     * (may be NULL = all) counts the reads of each SAMPLE that are still evidence; region_n_evidence is then ignored. */
+    const int64_t *region_sample_start; /* [n_regions + 1], or NULL */
+    const int64_t *sample_read_start;   /* [n_samples + 1], or NULL */
+    const int64_t *sample_n_evidence;   /* [n_samples], or NULL */
 } lk_realign_batch;
 
 /*
@@ -302,7 +319,8 @@ lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const lk_engine_ar
                                                  uint8_t *read_ins, uint8_t *read_del, const uint8_t *read_mapq);
 
 /*
- * Region driver = compute_read_likelihoods (:195-242) for a batch of single-sample regions:
+ * Region driver = compute_read_likelihoods (:195-242) for a batch of regions (one sample each, or several: see
+ * lk_pairhmm_batch.region_sample_start; the [A_g x R_s] blocks of a region's samples then follow one another):
  * modify_read_qualities on copies -> PairHMM on the GPU -> transpose into the reference's
  * [allele][read] matrices -> normalize_likelihoods (allele_likelihoods.rs:378-444) ->
  * filter_poorly_modeled_evidence (:925-1018, thresholds :244-319 computed from the ORIGINAL
@@ -311,6 +329,11 @@ lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const lk_engine_ar
  * lk_pairhmm_batch_host; removed reads' columns are compacted away and the tail set to NaN as the
  * reference does.  keep[r] (per read, may be NULL) = 1 if the read survived the filter.
  * ref_allele_index[g] (may be NULL = 0 for all) is the index of the reference haplotype in region g.
+ * Reads of a region without haplotypes are all filtered (keep = 0; the maximum over no alleles is -inf).
+ * Known divergence (non-default path): with modify_soft_clipped_bases == 0 the reference computes the disqualification
+ * thresholds from the ORIGINAL evidence read, soft-clipped bases included (read.len(), read.qual(); the "HMMQuals" key
+ * quirk); this entry point sees the reads as passed in (hard-clipped by the caller), so for soft-clipped reads
+ * ceil(len * rate) and the dynamic mean / variance sums use the clipped length and qualities.
  */
 lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_engine_args *args, const lk_pairhmm_batch *batch,
                                              const uint8_t *read_mapq, const int32_t *ref_allele_index,

@@ -59,6 +59,8 @@ class PairHmmBatchStruct(C.Structure):
         ("gcp_constant", C.c_uint8),
         ("hap_off", i64p),
         ("hap_bases", u8p),
+        ("region_sample_start", i64p),
+        ("sample_read_start", i64p),
     ]
 
 
@@ -102,6 +104,9 @@ class RealignBatchStruct(C.Structure):
         ("read_cigars", u32p),
         ("read_orig_len", i64p),
         ("informative_threshold", C.c_double),
+        ("region_sample_start", i64p),
+        ("sample_read_start", i64p),
+        ("sample_n_evidence", i64p),
     ]
 
 

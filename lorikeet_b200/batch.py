@@ -39,6 +39,16 @@ class PairHmmBatch:
         self.gcp_constant = int(gcp_constant)
         self.hap_off = _i64(hap_off)
         self.hap_bases = _u8(hap_bases)
+        # optional: several samples per region (set_samples)
+        self.region_sample_start = None
+        self.sample_read_start = None
+
+    def set_samples(self, region_sample_start, sample_read_start):
+        """Several samples per region: region g owns samples [region_sample_start[g], region_sample_start[g+1]), sample s
+        owns reads [sample_read_start[s], sample_read_start[s+1]); the samples of a region tile its reads in order."""
+        self.region_sample_start = _i64(region_sample_start)
+        self.sample_read_start = _i64(sample_read_start)
+        return self
 
     @classmethod
     def from_dict(cls, d, gcp_constant=None):
@@ -104,6 +114,9 @@ class PairHmmBatch:
         s.gcp_constant = self.gcp_constant
         s.hap_off = p(self.hap_off, _lib.i64p)
         s.hap_bases = p(self.hap_bases, _lib.u8p)
+        if self.region_sample_start is not None:
+            s.region_sample_start = p(self.region_sample_start, _lib.i64p)
+            s.sample_read_start = p(self.sample_read_start, _lib.i64p)
         return s
 
     def region_slice(self, g0, g1):
@@ -117,4 +130,10 @@ class PairHmmBatch:
                             self.read_ins[rb0:rb1], self.read_del[rb0:rb1], self.hap_off[h0:h1 + 1] - hb0,
                             self.hap_bases[hb0:hb1],
                             read_gcp=None if self.read_gcp is None else self.read_gcp[rb0:rb1],
-                            gcp_constant=self.gcp_constant)
+                            gcp_constant=self.gcp_constant)._slice_samples(self, g0, g1, r0)
+
+    def _slice_samples(self, parent, g0, g1, r0):
+        if parent.region_sample_start is not None:
+            s0, s1 = int(parent.region_sample_start[g0]), int(parent.region_sample_start[g1])
+            self.set_samples(parent.region_sample_start[g0:g1 + 1] - s0, parent.sample_read_start[s0:s1 + 1] - r0)
+        return self

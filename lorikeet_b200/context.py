@@ -26,11 +26,16 @@ class RealignBatch:
 
     def __init__(self, region_read_start, region_hap_start, values, hap_seqs, hap_cigars, hap_start_wrt_ref, read_seqs,
                  read_cigars, reference_start, read_orig_len=None, ref_allele_index=None, region_n_evidence=None,
-                 informative_threshold=0.0):
+                 informative_threshold=0.0, region_sample_start=None, sample_read_start=None, sample_n_evidence=None,
+                 values_device_ptr=None):
         as_u8 = lambda x: np.frombuffer(x.encode(), np.uint8) if isinstance(x, str) else np.asarray(x, np.uint8)
         self.region_read_start = np.ascontiguousarray(region_read_start, np.int64)
         self.region_hap_start = np.ascontiguousarray(region_hap_start, np.int64)
-        self.values = np.ascontiguousarray(values, np.float64).ravel()
+        # values: host matrices, or (values_device_ptr) the address of the same blocks in the context's device memory
+        self.values = None if values is None else np.ascontiguousarray(values, np.float64).ravel()
+        self.values_device_ptr = values_device_ptr
+        i64 = lambda x: None if x is None else np.ascontiguousarray(x, np.int64)
+        self.region_sample_start, self.sample_read_start, self.sample_n_evidence = i64(region_sample_start), i64(sample_read_start), i64(sample_n_evidence)
         haps = [as_u8(h) for h in hap_seqs]
         reads = [as_u8(r) for r in read_seqs]
         hc = [cigar_from_string(c) if isinstance(c, str) else np.asarray(c, np.uint32) for c in hap_cigars]
@@ -55,12 +60,14 @@ class RealignBatch:
     def as_struct(self):
         p = lambda a, t: None if a is None else a.ctypes.data_as(t)
         S = _lib.RealignBatchStruct
+        vals = p(self.values, _lib.f64p) if self.values_device_ptr is None else C.cast(C.c_void_p(int(self.values_device_ptr)), _lib.f64p)
         return S(len(self.region_read_start) - 1, p(self.region_read_start, _lib.i64p), p(self.region_hap_start, _lib.i64p),
-                 p(self.values, _lib.f64p), p(self.region_n_evidence, _lib.i64p), p(self.ref_allele_index, _lib.i32p),
+                 vals, p(self.region_n_evidence, _lib.i64p), p(self.ref_allele_index, _lib.i32p),
                  p(self.reference_start, _lib.i64p), p(self.hap_off, _lib.i64p), p(self.hap_bases, _lib.u8p),
                  p(self.hap_cigar_off, _lib.i64p), p(self.hap_cigars, _lib.u32p), p(self.hap_start_wrt_ref, _lib.i64p),
                  p(self.read_off, _lib.i64p), p(self.read_bases, _lib.u8p), p(self.read_cigar_off, _lib.i64p),
-                 p(self.read_cigars, _lib.u32p), p(self.read_orig_len, _lib.i64p), self.informative_threshold)
+                 p(self.read_cigars, _lib.u32p), p(self.read_orig_len, _lib.i64p), self.informative_threshold,
+                 p(self.region_sample_start, _lib.i64p), p(self.sample_read_start, _lib.i64p), p(self.sample_n_evidence, _lib.i64p))
 
 
 class Context:

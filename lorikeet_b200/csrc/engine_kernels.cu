@@ -16,6 +16,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "best_allele.h"
 #include "lk_internal.h"
 
 namespace lk {
@@ -206,17 +207,23 @@ __global__ void __launch_bounds__(128) engine_modify_reads_kernel(EngineDevArgs 
     }
 }
 
-// one warp per region
-__global__ void engine_epilogue_kernel(EngineDevArgs E, int64_t n_regions) {
+// one warp per (region, sample) block: the reference normalises and filters each sample's [A x R_s] matrix on its own
+// (pair_hmm_likelihood_calculation_engine.rs:201-239, allele_likelihoods.rs:378-444,925-1018)
+__global__ void engine_epilogue_kernel(EngineDevArgs E, int64_t n_blocks) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double ninf = -INFINITY;
-    for (int64_t g = warp; g < n_regions; g += n_warps) {
-        const int64_t r0 = E.region_read_start[g];
-        const int R = (int)(E.region_read_start[g + 1] - r0);
+    for (int64_t b = warp; b < n_blocks; b += n_warps) {
+        const int64_t g = E.block_region ? (int64_t)E.block_region[b] : b;
+        const int64_t r0 = E.block_read_start[b];
+        const int R = (int)(E.block_read_start[b + 1] - r0);
         const int A = (int)(E.region_hap_start[g + 1] - E.region_hap_start[g]);
-        if (R == 0 || A == 0) continue;
+        if (R == 0) continue;
+        if (A == 0) {  // no alleles: the maximum over none is -inf, below any threshold -> every read is filtered
+            if (E.keep) for (int r = lane; r < R; r += 32) E.keep[r0 + r] = 0;
+            continue;
+        }
         const int64_t base = E.read_out_base[r0];  // pairs before this region (chunk-local)
         const double *src = E.lk + base;            // [r*A + a]
         double *v = E.values + base;                // [a*R + r]
@@ -228,15 +235,17 @@ __global__ void engine_epilogue_kernel(EngineDevArgs E, int64_t n_regions) {
             bool keep = false;
             double worst = ninf;
             if (r < R) {
-                // search_best_allele(.., can_be_reference = symmetric, None): only the best likelihood is needed
-                int first = (E.symmetric || ref_idx != 0) ? 0 : 1;
-                double best = src[(int64_t)r * A + first];
-                for (int a = first + 1; a < A; a++) {
-                    if (!E.symmetric && a == ref_idx) continue;
-                    const double c = src[(int64_t)r * A + a];
-                    if (c > best) best = c;
+                if (normalise) {  // (A >= 2, so an allele other than the reference exists)
+                    // search_best_allele(.., can_be_reference = symmetric, None): only the best likelihood is needed
+                    int first = (E.symmetric || ref_idx != 0) ? 0 : 1;
+                    double best = src[(int64_t)r * A + first];
+                    for (int a = first + 1; a < A; a++) {
+                        if (!E.symmetric && a == ref_idx) continue;
+                        const double c = src[(int64_t)r * A + a];
+                        if (c > best) best = c;
+                    }
+                    worst = __dadd_rn(best, E.cap_diff);
                 }
-                if (normalise) worst = __dadd_rn(best, E.cap_diff);
                 // maximum over ALL alleles after normalisation (filter_poorly_modeled_evidence)
                 double mx = ninf;
                 for (int a = 0; a < A; a++) {
@@ -295,12 +304,39 @@ cudaError_t launch_engine_modify(const EngineDevArgs &E, int64_t n_reads, cudaSt
     return cudaGetLastError();
 }
 
-cudaError_t launch_engine_epilogue(const EngineDevArgs &E, int64_t n_regions, cudaStream_t st) {
-    if (n_regions == 0) return cudaSuccess;
+cudaError_t launch_engine_epilogue(const EngineDevArgs &E, int64_t n_blocks, cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
     const int threads = 128;
-    int64_t blocks = (n_regions * 32 + threads - 1) / threads;
+    int64_t blocks = (n_blocks * 32 + threads - 1) / threads;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    engine_epilogue_kernel<<<(unsigned)blocks, threads, 0, st>>>(E, n_regions);
+    engine_epilogue_kernel<<<(unsigned)blocks, threads, 0, st>>>(E, n_blocks);
+    return cudaGetLastError();
+}
+
+// Best haplotype of every read with the reference's tie-breaking, on likelihood matrices that are already in HBM
+// (realign_reads_to_their_best_haplotype, assembly_based_caller_utils.rs:208-246): one thread per read.
+__global__ void best_alleles_kernel(const double *__restrict__ values, const BestAlleleBlock *__restrict__ blocks, int64_t n_blocks,
+                                    const int32_t *__restrict__ priorities, double informative_threshold,
+                                    int32_t *__restrict__ best_allele, uint8_t *__restrict__ informative) {
+    for (int64_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const BestAlleleBlock B = blocks[b];
+        for (int r = threadIdx.x; r < B.n_reads; r += blockDim.x) {
+            int32_t best = -1;
+            uint8_t info = 0;
+            if (r < B.n_evidence)
+                best_allele_of_read(values + B.values_off, B.n_alleles, B.n_reads, r, priorities + B.prio_off, informative_threshold,
+                                    &best, nullptr, &info);
+            best_allele[B.first_read + r] = best;
+            informative[B.first_read + r] = info;
+        }
+    }
+}
+
+cudaError_t launch_best_alleles(const double *values, const BestAlleleBlock *blocks, int64_t n_blocks, const int32_t *priorities,
+                                double informative_threshold, int32_t *best_allele, uint8_t *informative, cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
+    const int64_t grid = n_blocks < 148 * 16 ? n_blocks : 148 * 16;
+    best_alleles_kernel<<<(unsigned)grid, 64, 0, st>>>(values, blocks, n_blocks, priorities, informative_threshold, best_allele, informative);
     return cudaGetLastError();
 }
 

@@ -52,7 +52,7 @@ struct lk_batcher {
     // gather buffers, one set per dispatcher thread, kept across batches (fresh vectors cost more in page faults than the
     // copies)
     struct Scratch {
-        std::vector<int64_t> rrs, rhs, read_off, hap_off;
+        std::vector<int64_t> rrs, rhs, read_off, hap_off, rss, srs;
         std::vector<uint8_t> bases, qual, ins, del, gcp, haps, mapq, aux;
         std::vector<int32_t> ref_idx;
         std::vector<double> out;
@@ -91,9 +91,26 @@ void lk_batcher::process(lk_ctx *ctx, std::vector<Request *> &reqs, Scratch &S) 
     // batch into the per-base form (each region keeps exactly the penalties its caller gave)
     for (Request *q : reqs) any_gcp |= (q->region->read_gcp != nullptr) || (q->region->gcp_constant != reqs[0]->region->gcp_constant);
     lk_status bad = LK_OK;
+    // several samples per region (engine mode): as soon as one caller's region has them, the merged batch carries sample
+    // arrays for all (a region without them is one sample)
+    bool any_samples = false;
+    for (Request *q : reqs) any_samples |= engine && q->region->region_sample_start && q->region->sample_read_start;
+    auto &rss = S.rss; auto &srs = S.srs;
+    rss.assign(1, 0); srs.assign(1, 0);
     for (size_t g = 0; g < G; g++) {
         const lk_pairhmm_batch *b = reqs[g]->region;
         const int64_t nr = b->region_read_start[1], nh = b->region_hap_start[1];
+        if (any_samples) {
+            if (b->region_sample_start && b->sample_read_start) {
+                const int64_t ns = b->region_sample_start[1];
+                if (ns < 0 || b->region_sample_start[0] != 0 || (ns == 0 && nr > 0) || (ns > 0 && (b->sample_read_start[0] != 0 || b->sample_read_start[ns] != nr))) { bad = LK_ERR_INVALID; break; }
+                for (int64_t sm = 1; sm <= ns; sm++) srs.push_back(rrs[g] + b->sample_read_start[sm]);
+                rss.push_back(rss.back() + ns);
+            } else {
+                srs.push_back(rrs[g] + nr);
+                rss.push_back(rss.back() + 1);
+            }
+        }
         rrs[g + 1] = rrs[g] + nr;
         rhs[g + 1] = rhs[g] + nh;
         const int64_t rb0 = nr ? b->read_off[0] : 0, rb1 = nr ? b->read_off[nr] : 0;
@@ -124,6 +141,7 @@ void lk_batcher::process(lk_ctx *ctx, std::vector<Request *> &reqs, Scratch &S) 
     big.read_gcp = any_gcp ? gcp.data() : nullptr;
     big.gcp_constant = reqs[0]->region->gcp_constant;
     big.hap_off = hap_off.data(); big.hap_bases = haps.data();
+    if (any_samples && bad == LK_OK) { big.region_sample_start = rss.data(); big.sample_read_start = srs.data(); }
     int64_t n_pairs = 0;
     for (size_t g = 0; g < G; g++) n_pairs += (rrs[g + 1] - rrs[g]) * (rhs[g + 1] - rhs[g]);
     out.resize((size_t)n_pairs);

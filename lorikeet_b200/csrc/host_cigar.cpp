@@ -10,6 +10,8 @@
 // The O(n*m) part (one SW per haplotype, <= 128 per region: read_threading_assembler.rs:787,827) runs on the GPU as
 // ONE lk_sw batch; what remains here is O(n+m) CIGAR surgery per pair, kept on the host like the reference.
 // CIGAR elements are BAM-encoded u32 (len << 4 | op; M=0 I=1 D=2 N=3 S=4 H=5 P=6 '='=7 X=8).
+#include <cuda_runtime.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -19,6 +21,7 @@
 #include <vector>
 
 #include "../../include/lorikeet_b200.h"
+#include "best_allele.h"
 #include "host_parallel.h"
 #include "lk_api_internal.h"
 
@@ -498,39 +501,9 @@ extern "C" lk_status lk_best_alleles_breaking_ties(const double *values, int64_t
     if (n_alleles < 0 || n_reads < 0 || n_evidence < 0 || n_evidence > n_reads || (n_alleles > 0 && n_reads > 0 && !values))
         return LK_ERR_INVALID;
     if (!best_allele) return LK_ERR_INVALID;
-    for (int64_t r = 0; r < n_evidence; r++) {
-        if (n_alleles == 0) {  // BestAllele with allele None
-            best_allele[r] = -1;
-            if (confidence) confidence[r] = 0.0;
-            if (informative) informative[r] = 0;
-            continue;
-        }
-        auto v = [&](int64_t a) { return values[a * n_reads + r]; };
-        int64_t best = 0, second = 0;
-        double best_lk = v(0), second_lk = -INFINITY;
-        for (int64_t a = 1; a < n_alleles; a++) {
-            const double c = v(a);
-            if (c > best_lk) { second = best; best = a; second_lk = best_lk; best_lk = c; }
-            else if (c > second_lk) { second = a; second_lk = c; }
-        }
-        if (priorities && (best_lk - second_lk) < informative_threshold) {
-            int32_t best_pr = priorities[best], second_pr = priorities[second];
-            for (int64_t a = 0; a < n_alleles; a++) {
-                const double c = v(a);
-                if (a == best || (best_lk - c) > informative_threshold) continue;
-                const int32_t pr = priorities[a];
-                if (pr > best_pr) { second = best; best = a; second_pr = best_pr; best_pr = pr; }
-                else if (pr > second_pr) { second = a; second_pr = pr; }
-            }
-        }
-        best_lk = v(best);
-        second_lk = (second != best) ? v(second) : -INFINITY;
-        const double diff = best_lk - second_lk;
-        const double conf = (fabs(diff) < 2.220446049250313e-16) ? 0.0 : diff;  // f64::EPSILON
-        best_allele[r] = (int32_t)best;
-        if (confidence) confidence[r] = conf;
-        if (informative) informative[r] = conf > informative_threshold ? 1 : 0;
-    }
+    for (int64_t r = 0; r < n_evidence; r++)
+        lk::best_allele_of_read(values, n_alleles, n_reads, r, priorities, informative_threshold, best_allele + r,
+                                confidence ? confidence + r : nullptr, informative ? informative + r : nullptr);
     return LK_OK;
 }
 
@@ -575,7 +548,7 @@ extern "C" lk_status lk_realign_finish(const uint8_t *read, int64_t read_len, co
     return LK_OK;
 }
 
-// realign_reads_to_their_best_haplotype for a batch of single-sample regions (assembly_based_caller_utils.rs:208-246).
+// realign_reads_to_their_best_haplotype for a batch of regions (assembly_based_caller_utils.rs:208-246).
 extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch *b, int32_t max_ops, int32_t *best_allele,
                                             uint8_t *informative, uint32_t *cigar_ops, int32_t *n_ops, int64_t *pos) {
     if (!ctx) return LK_ERR_INVALID;
@@ -587,38 +560,74 @@ extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch 
         return lk_fail(ctx, LK_ERR_INVALID, "null realign arrays");
     const int64_t n_reads = b->region_read_start[b->n_regions];
     const double thr = b->informative_threshold > 0.0 ? b->informative_threshold : 0.2;  // LOG_10_INFORMATIVE_THRESHOLD
-    // ---- best haplotype per read (host) ----
+    // ---- best haplotype per read: one search per (region, sample) block; on the host, or as a kernel when the matrices are
+    // in device memory (the caller kept lk_engine_compute_read_likelihoods' output in HBM) ----
+    if ((b->region_sample_start != nullptr) != (b->sample_read_start != nullptr)) return lk_fail(ctx, LK_ERR_INVALID, "region_sample_start and sample_read_start go together");
     std::vector<uint8_t> info((size_t)n_reads, 0);
     std::vector<int64_t> pair_of((size_t)n_reads, -1);
-    int64_t vbase = 0;
     std::vector<int64_t> ro(1, 0), ao(1, 0);
     std::vector<int64_t> todo;
-    for (int64_t g = 0; g < b->n_regions; g++) {
-        const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
-        const int64_t h0 = b->region_hap_start[g], h1 = b->region_hap_start[g + 1];
-        const int64_t A = h1 - h0, R = r1 - r0;
-        if (A < 0 || R < 0) return lk_fail(ctx, LK_ERR_INVALID, "decreasing region offsets");
-        const int64_t n_ev = b->region_n_evidence ? b->region_n_evidence[g] : R;
-        if (n_ev < 0 || n_ev > R) return lk_fail(ctx, LK_ERR_INVALID, "bad evidence count");
-        // haplotype_alignment_tiebreaking_priority: (is_ref ? 1 : 0) + 1 - cigar elements
-        std::vector<int32_t> prio((size_t)A);
-        for (int64_t a = 0; a < A; a++) {
-            const int32_t n_el = (int32_t)(b->hap_cigar_off[h0 + a + 1] - b->hap_cigar_off[h0 + a]);
-            const bool is_ref = b->ref_allele_index ? (b->ref_allele_index[g] == a) : (a == 0);
-            prio[(size_t)a] = (is_ref ? 1 : 0) + 1 - n_el;
+    std::vector<lk::BestAlleleBlock> blocks;
+    std::vector<int32_t> prio_all;
+    {
+        int64_t vbase = 0;
+        for (int64_t g = 0; g < b->n_regions; g++) {
+            const int64_t r0 = b->region_read_start[g], r1 = b->region_read_start[g + 1];
+            const int64_t h0 = b->region_hap_start[g], h1 = b->region_hap_start[g + 1];
+            const int64_t A = h1 - h0, R = r1 - r0;
+            if (A < 0 || R < 0) return lk_fail(ctx, LK_ERR_INVALID, "decreasing region offsets");
+            // haplotype_alignment_tiebreaking_priority: (is_ref ? 1 : 0) + 1 - cigar elements
+            const int64_t prio_off = (int64_t)prio_all.size();
+            for (int64_t a = 0; a < A; a++) {
+                const int32_t n_el = (int32_t)(b->hap_cigar_off[h0 + a + 1] - b->hap_cigar_off[h0 + a]);
+                const bool is_ref = b->ref_allele_index ? (b->ref_allele_index[g] == a) : (a == 0);
+                prio_all.push_back((is_ref ? 1 : 0) + 1 - n_el);
+            }
+            const int64_t s0 = b->region_sample_start ? b->region_sample_start[g] : g, s1 = b->region_sample_start ? b->region_sample_start[g + 1] : g + 1;
+            int64_t covered = r0;
+            for (int64_t sm = s0; sm < s1; sm++) {
+                const int64_t q0 = b->region_sample_start ? b->sample_read_start[sm] : r0, q1 = b->region_sample_start ? b->sample_read_start[sm + 1] : r1;
+                if (q0 != covered || q1 < q0 || q1 > r1) return lk_fail(ctx, LK_ERR_INVALID, "samples must tile their region's reads");
+                covered = q1;
+                const int64_t Rs = q1 - q0;
+                const int64_t n_ev = b->region_sample_start ? (b->sample_n_evidence ? b->sample_n_evidence[sm] : Rs)
+                                                            : (b->region_n_evidence ? b->region_n_evidence[g] : Rs);
+                if (n_ev < 0 || n_ev > Rs) return lk_fail(ctx, LK_ERR_INVALID, "bad evidence count");
+                lk::BestAlleleBlock B;
+                B.values_off = vbase + A * (q0 - r0); B.first_read = q0; B.prio_off = prio_off;
+                B.n_alleles = (int32_t)A; B.n_reads = (int32_t)Rs; B.n_evidence = (int32_t)n_ev; B.pad = 0;
+                blocks.push_back(B);
+            }
+            if (covered != r1) return lk_fail(ctx, LK_ERR_INVALID, "samples must tile their region's reads");
+            vbase += A * R;
         }
-        lk_status st = lk_best_alleles_breaking_ties(b->values + vbase, A, R, n_ev, prio.data(), thr, best_allele + r0, nullptr,
-                                                     info.data() + r0);
-        if (st != LK_OK) return lk_fail(ctx, st, "best_alleles failed");
-        for (int64_t r = r0; r < r1; r++) {
-            if (r - r0 >= n_ev || best_allele[r] < 0) { best_allele[r] = -1; n_ops[r] = -1; pos[r] = 0; continue; }
+    }
+    cudaPointerAttributes pattr;
+    const bool values_on_device = cudaPointerGetAttributes(&pattr, b->values) == cudaSuccess && pattr.type == cudaMemoryTypeDevice;
+    (void)cudaGetLastError();
+    if (values_on_device) {
+        const lk_status bs = lk_best_alleles_device(ctx, b->values, blocks.data(), (int64_t)blocks.size(), prio_all.data(), (int64_t)prio_all.size(),
+                                                    thr, n_reads, best_allele, info.data());
+        if (bs != LK_OK) return bs;
+    } else {
+        for (const lk::BestAlleleBlock &B : blocks) {
+            lk_status st = lk_best_alleles_breaking_ties(b->values + B.values_off, B.n_alleles, B.n_reads, B.n_evidence,
+                                                         prio_all.data() + B.prio_off, thr, best_allele + B.first_read, nullptr,
+                                                         info.data() + B.first_read);
+            if (st != LK_OK) return lk_fail(ctx, st, "best_alleles failed");
+            for (int64_t r = B.n_evidence; r < B.n_reads; r++) best_allele[B.first_read + r] = -1;
+        }
+    }
+    for (int64_t g = 0; g < b->n_regions; g++) {
+        const int64_t h0 = b->region_hap_start[g];
+        for (int64_t r = b->region_read_start[g]; r < b->region_read_start[g + 1]; r++) {
+            if (best_allele[r] < 0) { best_allele[r] = -1; n_ops[r] = -1; pos[r] = 0; continue; }
             const int64_t h = h0 + best_allele[r];
             pair_of[(size_t)r] = (int64_t)todo.size();
             todo.push_back(r);
             ro.push_back(ro.back() + (b->hap_off[h + 1] - b->hap_off[h]));
             ao.push_back(ao.back() + (b->read_off[r + 1] - b->read_off[r]));
         }
-        vbase += A * R;
     }
     if (informative) memcpy(informative, info.data(), (size_t)n_reads);
     if (todo.empty()) return LK_OK;

@@ -28,6 +28,23 @@ extern "C" lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_en
     if (!args->disable_cap_read_qualities_to_mapq && !read_mapq && batch->region_read_start[batch->n_regions] > 0)
         return lk_fail(ctx, LK_ERR_INVALID, "read_mapq is required unless capping to MAPQ is disabled");
     if (args->pcr_error_model < 0 || args->pcr_error_model > 3) return lk_fail(ctx, LK_ERR_INVALID, "bad PCR error model");
+    if ((batch->region_sample_start != nullptr) != (batch->sample_read_start != nullptr))
+        return lk_fail(ctx, LK_ERR_INVALID, "region_sample_start and sample_read_start go together");
+    if (batch->region_sample_start) {  // the samples of a region tile its reads in order (:219-224 loops the samples)
+        const int64_t *rs = batch->region_sample_start, *sr = batch->sample_read_start;
+        if (rs[0] != 0) return lk_fail(ctx, LK_ERR_INVALID, "region_sample_start must start at 0");
+        for (int64_t g = 0; g < batch->n_regions; g++) {
+            if (rs[g + 1] < rs[g]) return lk_fail(ctx, LK_ERR_INVALID, "region_sample_start must be non-decreasing");
+            const int64_t r0 = batch->region_read_start[g], r1 = batch->region_read_start[g + 1];
+            if (rs[g + 1] == rs[g]) {
+                if (r1 != r0) return lk_fail(ctx, LK_ERR_INVALID, "a region with reads needs at least one sample");
+                continue;
+            }
+            if (sr[rs[g]] != r0 || sr[rs[g + 1]] != r1) return lk_fail(ctx, LK_ERR_INVALID, "samples must tile their region's reads");
+            for (int64_t sm = rs[g]; sm < rs[g + 1]; sm++)
+                if (sr[sm + 1] < sr[sm]) return lk_fail(ctx, LK_ERR_INVALID, "sample_read_start must be non-decreasing");
+        }
+    }
     lk_engine_hook hook;
     memset(&hook, 0, sizeof hook);
     hook.args = args;

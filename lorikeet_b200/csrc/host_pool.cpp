@@ -140,7 +140,7 @@ lk_status deal(lk_pool *pool, const lk_pairhmm_batch *b, F call) {
         std::atomic<int> error_dev{ -1 };
         auto worker = [&](size_t d) {
             try {
-                std::vector<int64_t> rrs, rhs;
+                std::vector<int64_t> rrs, rhs, rss, srs;
                 for (;;) {
                     const size_t i = next.fetch_add(1);
                     if (i >= chunks.size() || first_error.load() != (int)LK_OK) break;
@@ -156,6 +156,13 @@ lk_status deal(lk_pool *pool, const lk_pairhmm_batch *b, F call) {
                     v.region_read_start = rrs.data(); v.region_hap_start = rhs.data();
                     v.read_off = b->read_off ? b->read_off + r0 : nullptr;
                     v.hap_off = b->hap_off ? b->hap_off + h0 : nullptr;
+                    if (b->region_sample_start && b->sample_read_start) {  // the chunk's samples, re-based like its regions
+                        const int64_t s0 = b->region_sample_start[c.g0], s1 = b->region_sample_start[c.g1];
+                        rss.resize(rrs.size()); srs.resize((size_t)(s1 - s0) + 1);
+                        for (int64_t g = c.g0; g <= c.g1; g++) rss[(size_t)(g - c.g0)] = b->region_sample_start[g] - s0;
+                        for (int64_t sm = s0; sm <= s1; sm++) srs[(size_t)(sm - s0)] = b->sample_read_start[sm] - r0;
+                        v.region_sample_start = rss.data(); v.sample_read_start = srs.data();
+                    }
                     const lk_status cs = call(pool->ctxs[d], &v, c.g0, r0, pair_base[(size_t)c.g0]);
                     if (cs != LK_OK) {
                         int expected = (int)LK_OK;

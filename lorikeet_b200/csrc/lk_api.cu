@@ -262,13 +262,28 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
     struct Piece { DevBuf *dst; const void *src; size_t bytes; };
     std::vector<int64_t> local_rhs((size_t)n_regions + 1);
     for (int64_t g = 0; g <= n_regions; g++) local_rhs[(size_t)g] = b->region_hap_start[g0 + g] - hbase;
+    // (region, sample) blocks of the engine epilogue: one per region, or one per sample of every region
     std::vector<int64_t> local_rrs;
+    std::vector<int32_t> local_breg;
+    const bool sampled = hook && b->region_sample_start && b->sample_read_start;
     if (hook) {
-        local_rrs.resize((size_t)n_regions + 1);
-        for (int64_t g = 0; g <= n_regions; g++) local_rrs[(size_t)g] = b->region_read_start[g0 + g] - rbase;
+        if (sampled) {
+            for (int64_t g = g0; g < g1; g++)
+                for (int64_t sm = b->region_sample_start[g]; sm < b->region_sample_start[g + 1]; sm++) {
+                    local_rrs.push_back(b->sample_read_start[sm] - rbase);
+                    local_breg.push_back((int32_t)(g - g0));
+                }
+            local_rrs.push_back(n_reads);
+        } else {
+            local_rrs.resize((size_t)n_regions + 1);
+            for (int64_t g = 0; g <= n_regions; g++) local_rrs[(size_t)g] = b->region_read_start[g0 + g] - rbase;
+        }
+        R->n_blocks = (int64_t)local_rrs.size() - 1;
+        R->sampled = sampled;
     }
     const Piece pieces[] = {
-        { &R->region_read_start, hook ? local_rrs.data() : nullptr, hook ? (size_t)(n_regions + 1) * 8 : 0 },
+        { &R->region_read_start, hook ? local_rrs.data() : nullptr, hook ? local_rrs.size() * 8 : 0 },
+        { &R->block_region, sampled ? local_breg.data() : nullptr, sampled ? local_breg.size() * 4 : 0 },
         { &R->read_mapq, hook && hook->read_mapq ? hook->read_mapq + rbase : nullptr, hook && hook->read_mapq ? (size_t)n_reads : 0 },
         { &R->ref_allele_index, hook && hook->ref_allele_index ? hook->ref_allele_index + g0 : nullptr,
           hook && hook->ref_allele_index ? (size_t)n_regions * 4 : 0 },
@@ -362,7 +377,8 @@ static void fill_engine_args(const lk_engine_hook *hook, lk_resident *R, const P
     E.read_off = A.read_off;
     E.read_mapq = hook->read_mapq ? (const uint8_t *)R->read_mapq.p : nullptr;
     E.read_out_base = A.read_out_base;
-    E.region_read_start = (const int64_t *)R->region_read_start.p;
+    E.block_read_start = (const int64_t *)R->region_read_start.p;
+    E.block_region = R->sampled ? (const int32_t *)R->block_region.p : nullptr;
     E.region_hap_start = A.region_hap_start;
     E.ref_allele_index = hook->ref_allele_index ? (const int32_t *)R->ref_allele_index.p : nullptr;
     E.lk = A.out;
@@ -428,7 +444,7 @@ static lk_status enqueue_kernels(lk_ctx *ctx, lk_resident *R, cudaStream_t st, b
     if ((e = launch_plain(A, R->plain_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "pairhmm_plain");
     R->launch_count++;
     if (hook) {
-        if ((e = launch_engine_epilogue(E, R->n_regions, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "engine_epilogue");
+        if ((e = launch_engine_epilogue(E, R->n_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "engine_epilogue");
         R->launch_count += 2;  // modify_reads + epilogue
     }
     return LK_OK;
@@ -510,7 +526,7 @@ extern "C" lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *
 static void release_buffers(lk_resident *R) {
     DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
                        &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
-                       &R->region_read_start, &R->read_mapq, &R->ref_allele_index, &R->qual_orig, &R->values, &R->keep,
+                       &R->region_read_start, &R->block_region, &R->read_mapq, &R->ref_allele_index, &R->qual_orig, &R->values, &R->keep,
                        &R->hap_bases, &R->hidx, &R->henc_off, &R->hap_flags, &R->tasks, &R->task_haps, &R->groups, &R->out,
                        &R->flags, &R->counters, &R->rescue_pairs, &R->scratch, &R->band_pairs, &R->band_scratch,
                        &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,
@@ -546,6 +562,19 @@ lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double
     int64_t n_pairs = 0;
     for (int64_t r = 0; r < batch->n_regions; r++)
         n_pairs += (batch->region_read_start[r + 1] - batch->region_read_start[r]) * (batch->region_hap_start[r + 1] - batch->region_hap_start[r]);
+    // reads of a region without haplotypes are all filtered (the maximum over no alleles is -inf): written here, on the host,
+    // because a chunk that holds no pair at all launches nothing
+    if (hook && hook->keep) {
+        cudaPointerAttributes pa;
+        const bool keep_on_host = cudaPointerGetAttributes(&pa, hook->keep) != cudaSuccess || pa.type != cudaMemoryTypeDevice;
+        (void)cudaGetLastError();
+        for (int64_t r = 0; r < batch->n_regions; r++)
+            if (batch->region_hap_start[r + 1] == batch->region_hap_start[r] && batch->region_read_start[r + 1] > batch->region_read_start[r]) {
+                const size_t nr = (size_t)(batch->region_read_start[r + 1] - batch->region_read_start[r]);
+                if (keep_on_host) memset(hook->keep + batch->region_read_start[r], 0, nr);
+                else cudaMemset(hook->keep + batch->region_read_start[r], 0, nr);
+            }
+    }
     if (n_pairs == 0) { ctx->last_launch_count = 0; return LK_OK; }
     if (!out) return lk_fail(ctx, LK_ERR_INVALID, "null out");
     cudaError_t e = cudaSetDevice(ctx->device);

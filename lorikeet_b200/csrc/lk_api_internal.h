@@ -74,7 +74,9 @@ struct lk_resident {
     DevBuf region_hap_start, hap_off, hap_bases, hidx, henc_off, hap_flags;
     DevBuf tasks, task_haps, groups, out, flags, counters, rescue_pairs, scratch, band_pairs, band_scratch;
     // engine pre/post-ops on the device (N3)
-    DevBuf region_read_start, read_mapq, ref_allele_index, qual_orig, values, keep;
+    DevBuf region_read_start, block_region, read_mapq, ref_allele_index, qual_orig, values, keep;
+    int64_t n_blocks = 0;   // (region, sample) blocks of the staged chunk
+    bool sampled = false;   // several samples per region: block_region is in use
     // ---- Smith-Waterman ----
     struct SwLaunch { int K; int32_t first; int32_t count; bool clamp; };
     std::vector<SwLaunch> sw_launches;
@@ -101,3 +103,9 @@ lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double
 
 lk_status lk_fail(lk_ctx *ctx, lk_status st, const std::string &msg);
 lk_status lk_cuda_fail(lk_ctx *ctx, cudaError_t e, const char *what);
+
+// best-allele search on likelihood matrices in device memory (lk_sw_api.cu); best_allele / informative are host arrays
+namespace lk { struct BestAlleleBlock; }
+lk_status lk_best_alleles_device(lk_ctx *ctx, const double *d_values, const lk::BestAlleleBlock *blocks, int64_t n_blocks,
+                                 const int32_t *priorities, int64_t n_priorities, double informative_threshold, int64_t n_reads,
+                                 int32_t *best_allele, uint8_t *informative);

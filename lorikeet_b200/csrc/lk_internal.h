@@ -27,7 +27,8 @@ struct EngineDevArgs {
     const int64_t *read_off;
     const uint8_t *read_mapq;          // per read (chunk-local index)
     const int64_t *read_out_base;      // per read: first pair of (read, haplotype 0)
-    const int64_t *region_read_start;  // chunk-local
+    const int64_t *block_read_start;   // chunk-local: reads of (region, sample) block b = [block_read_start[b], block_read_start[b+1])
+    const int32_t *block_region;       // chunk-local region of block b; null = one block per region (b == region)
     const int64_t *region_hap_start;   // chunk-local
     const int32_t *ref_allele_index;   // per region, may be null
     const double *lk;                  // PairHMM result [r*A + h] per region
@@ -39,7 +40,10 @@ struct EngineDevArgs {
     uint8_t pcr_cache[101];
 };
 cudaError_t launch_engine_modify(const EngineDevArgs &E, int64_t n_reads, cudaStream_t st);
-cudaError_t launch_engine_epilogue(const EngineDevArgs &E, int64_t n_regions, cudaStream_t st);
+cudaError_t launch_engine_epilogue(const EngineDevArgs &E, int64_t n_blocks, cudaStream_t st);
+struct BestAlleleBlock;
+cudaError_t launch_best_alleles(const double *values, const BestAlleleBlock *blocks, int64_t n_blocks, const int32_t *priorities,
+                                double informative_threshold, int32_t *best_allele, uint8_t *informative, cudaStream_t st);
 cudaError_t launch_sw(int K, bool clamp, const SwArgs &A, int n_blocks, cudaStream_t st);
 
 }  // namespace lk

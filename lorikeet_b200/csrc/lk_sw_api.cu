@@ -311,3 +311,33 @@ extern "C" lk_status lk_sw_align(lk_ctx *ctx, const uint8_t *ref, int64_t ref_le
     memcpy(cigar_text, text.c_str(), text.size() + 1);
     return LK_OK;
 }
+
+// ---- best haplotype per read on matrices that stayed in HBM (N2 without the round trip of `values` through the host) ----
+#include "best_allele.h"
+lk_status lk_best_alleles_device(lk_ctx *ctx, const double *d_values, const lk::BestAlleleBlock *blocks, int64_t n_blocks,
+                                 const int32_t *priorities, int64_t n_priorities, double informative_threshold, int64_t n_reads,
+                                 int32_t *best_allele, uint8_t *informative) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (n_blocks == 0 || n_reads == 0) return LK_OK;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    cudaStream_t st = ctx->stream[0];
+    DevBuf d_blocks, d_prio, d_best, d_info;
+    auto done = [&](lk_status r) { d_blocks.release(); d_prio.release(); d_best.release(); d_info.release(); return r; };
+    if ((e = d_blocks.reserve((size_t)n_blocks * sizeof(lk::BestAlleleBlock))) != cudaSuccess || (e = d_prio.reserve((size_t)std::max<int64_t>(n_priorities, 1) * 4)) != cudaSuccess ||
+        (e = d_best.reserve((size_t)n_reads * 4)) != cudaSuccess || (e = d_info.reserve((size_t)n_reads)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "alloc best-allele buffers"));
+    if ((e = cudaMemcpyAsync(d_blocks.p, blocks, (size_t)n_blocks * sizeof(lk::BestAlleleBlock), cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (n_priorities > 0 && (e = cudaMemcpyAsync(d_prio.p, priorities, (size_t)n_priorities * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) ||
+        (e = cudaMemsetAsync(d_best.p, 0xff, (size_t)n_reads * 4, st)) != cudaSuccess || (e = cudaMemsetAsync(d_info.p, 0, (size_t)n_reads, st)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "H2D best-allele inputs"));
+    if ((e = lk::launch_best_alleles(d_values, (const lk::BestAlleleBlock *)d_blocks.p, n_blocks, (const int32_t *)d_prio.p, informative_threshold,
+                                     (int32_t *)d_best.p, (uint8_t *)d_info.p, st)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "best_alleles_kernel"));
+    if ((e = cudaMemcpyAsync(best_allele, d_best.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(informative, d_info.p, (size_t)n_reads, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "best-allele D2H"));
+    return done(LK_OK);
+}
