@@ -213,6 +213,20 @@ lk_status lk_calculate_cigar_finish(const uint8_t *ref, int64_t ref_len, const u
                                     const uint32_t *sw_ops, int32_t sw_n_ops, int32_t sw_offset, int32_t max_ops,
                                     uint32_t *out_ops, int32_t *out_n_ops);
 
+/* ---------------------------------------------------------------- dangling-end merges of the read-threading graph (N4) */
+
+/*
+ * The alignment step of ReadThreadingGraph's dangling-tail / dangling-head recovery
+ * (src/read_threading/read_threading_graph.rs:1370-1486; align calls at :1408-1414 and :1471-1477): each dangling path
+ * (alts) is aligned to its reference path (refs) with OverhangStrategy::LeadingInDel and the dangling-end parameters the
+ * caller passes (STANDARD_NGS by default), then AlignmentUtils::remove_trailing_deletions (alignment_utils.rs:702-707)
+ * drops a final deletion.  Only the CIGAR is used by the callers.  All the dangling ends of a region's graph (or of many
+ * regions) go in ONE Smith-Waterman launch.  Results as in lk_sw_batch_host (n_ops -1 empty sequence, -2 capacity).
+ */
+lk_status lk_dangling_end_sw_batch(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                                   const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params, int32_t max_ops,
+                                   uint32_t *cigar_ops, int32_t *n_ops);
+
 /* ---------------------------------------------------------------- read -> best-haplotype realignment (N2) */
 
 /*
@@ -312,6 +326,12 @@ lk_status lk_engine_modify_read_qualities(const lk_engine_args *args, int64_t n_
                                           const uint8_t *read_bases, uint8_t *read_qual, uint8_t *read_ins,
                                           uint8_t *read_del, const uint8_t *read_mapq, int n_threads);
 
+/* VariantContextUtils::find_number_of_repetitions (src/model/variant_context_utils.rs:240-337), the repeat counter under
+ * the PCR error model: how many times repeat_unit occurs back to back at the start (leading_repeats != 0) or at the end of
+ * test_string.  Host utility; -1 on bad arguments. */
+int64_t lk_find_number_of_repetitions(const uint8_t *repeat_unit, int64_t unit_len, const uint8_t *test_string,
+                                      int64_t test_len, int leading_repeats);
+
 /* The same pre-ops as one device launch (the kernel the region driver runs on its staged copies): upload, launch,
  * download, in place on the caller's arrays.  Byte-identical to lk_engine_modify_read_qualities. */
 lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const lk_engine_args *args, int64_t n_reads,
@@ -338,6 +358,17 @@ lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const lk_engine_ar
 lk_status lk_engine_compute_read_likelihoods(lk_ctx *ctx, const lk_engine_args *args, const lk_pairhmm_batch *batch,
                                              const uint8_t *read_mapq, const int32_t *ref_allele_index,
                                              double *values, uint8_t *keep);
+
+/*
+ * The post-ops of the region driver on their own: AlleleLikelihoods::normalize_likelihoods (allele_likelihoods.rs:378-444)
+ * and filter_poorly_modeled_evidence (:925-1018, thresholds ...engine.rs:244-319) as the device epilogue, applied to
+ * likelihoods the caller supplies in lk_pairhmm_batch_host's layout (per region [r*A + h]); values / keep as in
+ * lk_engine_compute_read_likelihoods.  Of the batch only the region / sample structure, read_off and read_qual (the
+ * ORIGINAL qualities the thresholds are computed from) are read.
+ */
+lk_status lk_engine_normalize_and_filter_device(lk_ctx *ctx, const lk_engine_args *args, const lk_pairhmm_batch *batch,
+                                                const int32_t *ref_allele_index, const double *likelihoods, double *values,
+                                                uint8_t *keep);
 
 /* ---------------------------------------------------------------- cross-thread batching front-end (N4) */
 

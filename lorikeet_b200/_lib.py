@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "lk_cigar_append_clipped_elements", "lk_read_start_on_reference_haplotype",
     "lk_batcher_create", "lk_batcher_destroy", "lk_batcher_submit", "lk_batcher_stats", "lk_batcher_submit_async",
     "lk_batcher_wait",
+    "lk_engine_normalize_and_filter_device", "lk_dangling_end_sw_batch", "lk_find_number_of_repetitions",
     "lk_pool_create", "lk_pool_destroy", "lk_pool_device_count", "lk_pool_ctx", "lk_pool_last_error",
     "lk_pool_set_tristate_correction", "lk_pool_pairhmm_batch_host", "lk_pool_compute_read_likelihoods", "lk_pool_batcher_create",
     "lk_resident_pairs", "lk_resident_cells", "lk_resident_launch_count", "lk_resident_last_fast_ms",
@@ -197,6 +198,12 @@ def load():
     L.lk_batcher_wait.argtypes = [vp, vp]
     L.lk_batcher_stats.restype = None
     L.lk_batcher_stats.argtypes = [vp, i64p, i64p]
+    L.lk_engine_normalize_and_filter_device.restype = C.c_int
+    L.lk_engine_normalize_and_filter_device.argtypes = [vp, ep, bp, i32p, f64p, f64p, u8p]
+    L.lk_dangling_end_sw_batch.restype = C.c_int
+    L.lk_dangling_end_sw_batch.argtypes = [vp, C.c_int64, i64p, u8p, i64p, u8p, C.POINTER(SwParams), C.c_int32, u32p, i32p]
+    L.lk_find_number_of_repetitions.restype = C.c_int64
+    L.lk_find_number_of_repetitions.argtypes = [u8p, C.c_int64, u8p, C.c_int64, C.c_int]
     # several devices behind one handle
     L.lk_pool_create.restype = C.c_int
     L.lk_pool_create.argtypes = [C.POINTER(C.c_int), C.c_int32, C.POINTER(vp)]

@@ -205,6 +205,20 @@ class Context:
                 out.append(cigar_to_string(ops[i, :n_ops[i]]))
         return out
 
+    def dangling_end_sw_batch(self, ref_off, refs, alt_off, alts, params, max_ops=64):
+        """The alignment step of the read-threading graph's dangling-end merges (read_threading_graph.rs:1408,1471):
+        LeadingInDel + remove_trailing_deletions; list of CIGAR strings."""
+        from .batch import _u8, _i64
+        ref_off, alt_off, refs, alts = _i64(ref_off), _i64(alt_off), _u8(refs), _u8(alts)
+        n = len(ref_off) - 1
+        prm = _lib.SwParams(*[int(x) for x in params])
+        ops = np.zeros((n, max_ops), dtype=np.uint32)
+        n_ops = np.zeros(n, dtype=np.int32)
+        self._check(self._L.lk_dangling_end_sw_batch(self._h, n, ref_off.ctypes.data_as(_lib.i64p), refs.ctypes.data_as(_lib.u8p),
+                                                     alt_off.ctypes.data_as(_lib.i64p), alts.ctypes.data_as(_lib.u8p), C.byref(prm),
+                                                     int(max_ops), ops.ctypes.data_as(_lib.u32p), n_ops.ctypes.data_as(_lib.i32p)))
+        return [cigar_to_string(ops[i, :n_ops[i]]) if n_ops[i] >= 0 else None for i in range(n)]
+
     def realign_reads_batch(self, batch, max_ops=64):
         """realign_reads_to_their_best_haplotype: (best_allele[int32], informative[uint8], cigars[list of str or None where
         the read is not realigned], pos[int64])."""

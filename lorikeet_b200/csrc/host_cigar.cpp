@@ -684,3 +684,38 @@ extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch 
     if (failed.load() != (int)LK_OK) return lk_fail(ctx, (lk_status)failed.load(), "realign_finish failed");
     return LK_OK;
 }
+
+// The alignment step of the read-threading graph's dangling-end merges (src/read_threading/read_threading_graph.rs:1370-1486:
+// generate_cigar_against_downwards_reference_path :1408-1414 and ..._upwards_... :1471-1477): every dangling tail / head of a
+// region's graph is aligned to its reference path with OverhangStrategy::LeadingInDel (the callers pass the
+// dangling-end parameters, STANDARD_NGS by default) and AlignmentUtils::remove_trailing_deletions (alignment_utils.rs:702-707)
+// is applied to the result; only the CIGAR is used.  One Smith-Waterman launch for all pairs.
+extern "C" lk_status lk_dangling_end_sw_batch(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
+                                              const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
+                                              int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (n_pairs < 0 || max_ops < 1 || !params) return lk_fail(ctx, LK_ERR_INVALID, "bad dangling-end arguments");
+    if (n_pairs == 0) return LK_OK;
+    if (!ref_off || !refs || !alt_off || !alts || !cigar_ops || !n_ops) return lk_fail(ctx, LK_ERR_INVALID, "null dangling-end arrays");
+    try {
+        // one element of slack: a CIGAR that fits max_ops only after its trailing deletion is dropped still comes back
+        const int32_t sw_max = max_ops + 1;
+        std::vector<uint32_t> ops((size_t)n_pairs * (size_t)sw_max);
+        std::vector<int32_t> offs((size_t)n_pairs);
+        const lk_status st = lk_sw_batch_host(ctx, n_pairs, ref_off, refs, alt_off, alts, params, LK_SW_LEADING_INDEL, sw_max, ops.data(),
+                                              n_ops, offs.data());
+        if (st != LK_OK) return st;
+        for (int64_t p = 0; p < n_pairs; p++) {
+            int32_t n = n_ops[p];
+            if (n < 0) continue;  // -1 empty sequence (the reference asserts), -2 capacity
+            const uint32_t *src = ops.data() + (size_t)p * (size_t)sw_max;
+            if (n > 0 && (src[n - 1] & 0xFu) == D) n--;  // remove_trailing_deletions
+            if (n > max_ops) { n_ops[p] = -2; continue; }
+            memcpy(cigar_ops + (size_t)p * (size_t)max_ops, src, (size_t)n * 4);
+            n_ops[p] = n;
+        }
+        return LK_OK;
+    } catch (...) {
+        return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    }
+}

@@ -152,6 +152,15 @@ extern "C" lk_status lk_engine_modify_read_qualities(const lk_engine_args *args,
     return LK_OK;
 }
 
+// VariantContextUtils::find_number_of_repetitions (variant_context_utils.rs:240-257) as a host utility: the repeat counter the
+// PCR error model is built on, exposed so that it can be pinned on the reference's own known answers
+// (tests/variant_context_utils_unit_tests.rs:22-140).  -1: bad arguments (the reference asserts a non-empty unit).
+extern "C" int64_t lk_find_number_of_repetitions(const uint8_t *repeat_unit, int64_t unit_len, const uint8_t *test_string,
+                                                 int64_t test_len, int leading_repeats) {
+    if (!repeat_unit || unit_len <= 0 || test_len < 0 || (test_len > 0 && !test_string) || unit_len > 0x7fffffff || test_len > 0x7fffffff) return -1;
+    return count_repeats(Span{ repeat_unit, (int)unit_len }, test_string, (int)test_len, leading_repeats != 0);
+}
+
 void lk_engine_fill_pcr_cache(const lk_engine_args *args, uint8_t cache[101]) {  // initialize_pcr_error_model :169-184
     memset(cache, 0, 101);
     if (args->pcr_error_model != LK_PCR_NONE)

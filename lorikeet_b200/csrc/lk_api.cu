@@ -724,3 +724,85 @@ extern "C" lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const l
     d_off.release(); d_b.release(); d_q.release(); d_i.release(); d_d.release(); d_m.release();
     return LK_OK;
 }
+
+// normalize_likelihoods + filter_poorly_modeled_evidence on the device, stand-alone: the epilogue kernel the region driver runs
+// after the PairHMM kernels, applied to likelihoods the CALLER supplies (layout of lk_pairhmm_batch_host: per region [r*A + h]).
+// Exists so that the post-ops can be checked on their own against the reference's AlleleLikelihoods tests.
+extern "C" lk_status lk_engine_normalize_and_filter_device(lk_ctx *ctx, const lk_engine_args *args, const lk_pairhmm_batch *batch,
+                                                           const int32_t *ref_allele_index, const double *likelihoods,
+                                                           double *values, uint8_t *keep) {
+    if (!ctx) return LK_ERR_INVALID;
+    if (!args || !batch) return lk_fail(ctx, LK_ERR_INVALID, "null arguments");
+    int64_t n_reads = 0, n_haps = 0;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        const lk_status vs = validate_batch(ctx, batch, &n_reads, &n_haps);
+        if (vs != LK_OK) return vs;
+    }
+    const int64_t G = batch->n_regions;
+    std::vector<int64_t> out_base((size_t)std::max<int64_t>(n_reads, 1)), brs;
+    std::vector<int32_t> breg;
+    int64_t n_pairs = 0;
+    const bool sampled = batch->region_sample_start && batch->sample_read_start;
+    for (int64_t g = 0; g < G; g++) {
+        const int64_t r0 = batch->region_read_start[g], r1 = batch->region_read_start[g + 1];
+        const int64_t A = batch->region_hap_start[g + 1] - batch->region_hap_start[g];
+        for (int64_t r = r0; r < r1; r++) out_base[(size_t)r] = n_pairs + (r - r0) * A;
+        n_pairs += (r1 - r0) * A;
+        if (sampled) {
+            for (int64_t sm = batch->region_sample_start[g]; sm < batch->region_sample_start[g + 1]; sm++) {
+                brs.push_back(batch->sample_read_start[sm]);
+                breg.push_back((int32_t)g);
+            }
+        } else {
+            brs.push_back(r0);
+        }
+    }
+    brs.push_back(n_reads);
+    if (n_reads == 0) return LK_OK;
+    if (n_pairs > 0 && (!likelihoods || !values)) return lk_fail(ctx, LK_ERR_INVALID, "null likelihoods / values");
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
+    cudaStream_t st = ctx->stream[0];
+    const int64_t q0 = batch->read_off[0], qn = batch->read_off[n_reads] - q0;
+    DevBuf d_off, d_qual, d_base, d_brs, d_breg, d_rhs, d_ref, d_lk, d_val, d_keep;
+    DevBuf *all[] = { &d_off, &d_qual, &d_base, &d_brs, &d_breg, &d_rhs, &d_ref, &d_lk, &d_val, &d_keep };
+    auto done = [&](lk_status r) { for (DevBuf *b : all) b->release(); return r; };
+    if ((e = upload(d_off, batch->read_off, (size_t)n_reads + 1, st)) != cudaSuccess ||
+        (e = upload(d_qual, batch->read_qual + q0, (size_t)qn, st)) != cudaSuccess ||
+        (e = upload(d_base, out_base.data(), (size_t)n_reads, st)) != cudaSuccess ||
+        (e = upload(d_brs, brs.data(), brs.size(), st)) != cudaSuccess ||
+        (e = upload(d_breg, breg.data(), breg.size(), st)) != cudaSuccess ||
+        (e = upload(d_rhs, batch->region_hap_start, (size_t)G + 1, st)) != cudaSuccess ||
+        (e = upload(d_ref, ref_allele_index, ref_allele_index ? (size_t)G : 0, st)) != cudaSuccess ||
+        (e = upload(d_lk, likelihoods, (size_t)n_pairs, st)) != cudaSuccess ||
+        (e = d_val.reserve((size_t)std::max<int64_t>(n_pairs, 1) * 8)) != cudaSuccess || (e = d_keep.reserve((size_t)n_reads)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "stage post-ops inputs"));
+    EngineDevArgs E;
+    memset(&E, 0, sizeof E);
+    E.qual_orig = (const uint8_t *)d_qual.p - q0;
+    E.read_off = (const int64_t *)d_off.p;
+    E.read_out_base = (const int64_t *)d_base.p;
+    E.block_read_start = (const int64_t *)d_brs.p;
+    E.block_region = sampled ? (const int32_t *)d_breg.p : nullptr;
+    E.region_hap_start = (const int64_t *)d_rhs.p;
+    E.ref_allele_index = ref_allele_index ? (const int32_t *)d_ref.p : nullptr;
+    E.lk = (const double *)d_lk.p;
+    E.values = (double *)d_val.p;
+    E.keep = (uint8_t *)d_keep.p;
+    E.cap_diff = args->log10_global_read_mismapping_rate;
+    E.expected_error_rate = args->expected_error_rate_per_base;
+    E.disq_scale = args->read_disqualification_scale;
+    E.symmetric = args->symmetrically_normalize_alleles_to_reference != 0;
+    E.dynamic_disq = args->dynamic_read_disqualification != 0;
+    if ((e = cudaMemsetAsync(d_keep.p, 0, (size_t)n_reads, st)) != cudaSuccess ||
+        (e = launch_engine_epilogue(E, (int64_t)brs.size() - 1, st)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "engine_epilogue"));
+    if (n_pairs > 0 && (e = cudaMemcpyAsync(values, d_val.p, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "D2H values"));
+    if (keep && (e = cudaMemcpyAsync(keep, d_keep.p, (size_t)n_reads, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+        return done(lk_cuda_fail(ctx, e, "D2H keep"));
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(lk_cuda_fail(ctx, e, "post-ops"));
+    return done(LK_OK);
+}

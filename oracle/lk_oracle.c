@@ -461,6 +461,13 @@ static int find_number_of_repetitions_main(const uint8_t *unit_full, int unit_of
     return num;
 }
 
+/* VariantContextUtils::find_number_of_repetitions, variant_context_utils.rs:240-257 (the wrapper the reference's own
+ * known answers call, tests/variant_context_utils_unit_tests.rs:22-140) */
+int lko_find_number_of_repetitions(const uint8_t *unit, int unit_len, const uint8_t *test, int test_len, int leading) {
+    if (test_len == 0) return 0;
+    return find_number_of_repetitions_main(unit, 0, unit_len, test, 0, test_len, leading);
+}
+
 int lko_find_tandem_repeat_length(const uint8_t *bases, int len, int offset) {
     /* :528-611 */
     int max_bw = 0;

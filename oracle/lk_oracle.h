@@ -94,6 +94,7 @@ int lko_last_index_of(const uint8_t *ref, int ref_len, const uint8_t *query, int
 /* :186-193 */
 uint8_t lko_pcr_error_model_adjusted_qual(int repeat_length, double rate_factor);
 /* :528-611, returns the repeat length (second tuple element) */
+int lko_find_number_of_repetitions(const uint8_t *unit, int unit_len, const uint8_t *test, int test_len, int leading);
 int lko_find_tandem_repeat_length(const uint8_t *bases, int len, int offset);
 /* :502-526; pcr_model = 0 None, 1 Hostile, 2 Aggressive, 3 Conservative */
 void lko_apply_pcr_error_model(const uint8_t *bases, int len, uint8_t *ins, uint8_t *del, int pcr_model);

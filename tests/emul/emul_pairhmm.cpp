@@ -217,3 +217,18 @@ extern "C" int emul_pairhmm_batch(const lk_pairhmm_batch *b, int use_tristate, i
     run_plain(A, counters[0]);
     return 0;
 }
+
+// Test hook: the six transition probabilities of one read position as the KERNELS see them, i.e. read out of the tables
+// host_model.cpp builds and lk_create uploads (qerr_d, triangular m2m) -- order of pair_hmm_model.rs:88-113:
+// match->match, indel->match, match->insertion, insertion->insertion, match->deletion, deletion->deletion.
+extern "C" void emul_model_trans_probs(int ins, int del, int gcp, double out[6]) {
+    static ModelTables T;
+    static bool built = false;
+    if (!built) { build_model_tables(T); built = true; }
+    out[0] = m2m_lookup(T.m2m.data(), ins, del);
+    out[1] = 1.0 - T.qerr_d[(size_t)gcp];
+    out[2] = T.qerr_d[(size_t)ins];
+    out[3] = T.qerr_d[(size_t)gcp];
+    out[4] = T.qerr_d[(size_t)del];
+    out[5] = T.qerr_d[(size_t)gcp];
+}

@@ -13,6 +13,8 @@ reference code is copied.  Sources:
   * tests/alignment_utils_unit_tests.rs:155-340 (create_read_aligned_to_ref known answers), :840-878
     (apply_cigar_to_cigar), :902-916 (append_clipped_elements...), :1017-1024 (read_start_on_reference_haplotype)
                                                      -> realign_cases.json
+  * tests/variant_context_utils_unit_tests.rs:22-140 (find_number_of_repetitions) -> find_number_of_repetitions.json
+  * tests/read_threading_graph_unit_tests.rs:667-685 (make_dangling_tails_data)  -> dangling_tail_cases.json
 """
 import argparse
 import json
@@ -113,6 +115,32 @@ def realign_cases(path):
     return out
 
 
+def find_number_of_repetitions_cases(path):
+    """assert_eq!(VariantContextUtils::find_number_of_repetitions("AT".as_bytes(), "GATAT".as_bytes(), false), 2)"""
+    src = open(path).read()
+    pat = re.compile(r'find_number_of_repetitions\(\s*"(\w*)"\.as_bytes\(\),\s*"(\w*)"\.as_bytes\(\),\s*(true|false),?\s*\),\s*(\d+)', re.S)
+    return [dict(unit=u, test=t, leading=(l == "true"), expected=int(e)) for u, t, l, e in pat.findall(src)]
+
+
+def dangling_tail_cases(path):
+    """test_dangling_tails(ref_end, alt_end, cigar, cigar_is_good, ...): the graph hands SmithWatermanAligner::align the path
+    bases from the last common vertex on, i.e. the last base of the common prefix ('T') + each end ("add 1M to the expected
+    CIGAR because it includes the previous (common) base too"), STANDARD_NGS, LeadingInDel, then remove_trailing_deletions
+    (read_threading_graph.rs:1408-1421).  Only cases whose alignment the reference test actually reaches are kept: for a
+    dangling path shorter than min_tail_path_length + 1 = 5 vertices the graph returns None before aligning, and the test then
+    only asserts !cigar_is_good, so the listed CIGAR of those two rows ("C", "CA") is never compared."""
+    src = open(path).read()
+    prefix = re.search(r'let common_prefix = "([ACGT]+)";', src).group(1)
+    seen, out = set(), []
+    for r, a, c, good in re.findall(r'test_dangling_tails\("(\w+)", "(\w+)", "(\w+)", (true|false),', src):
+        if (r, a) in seen:
+            continue
+        seen.add((r, a))
+        out.append(dict(ref=prefix[-1] + r, alt=prefix[-1] + a, cigar=c, params=[25, -50, -110, -6], reached=len(a) >= 4,
+                        cigar_is_good=(good == "true")))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -126,6 +154,11 @@ def main():
     json.dump(cc, open(os.path.join(HERE, "calculate_cigar_cases.json"), "w"), indent=1)
     rc = realign_cases(os.path.join(t, "alignment_utils_unit_tests.rs"))
     json.dump(rc, open(os.path.join(HERE, "realign_cases.json"), "w"), indent=1)
+    fr = find_number_of_repetitions_cases(os.path.join(t, "variant_context_utils_unit_tests.rs"))
+    json.dump(fr, open(os.path.join(HERE, "find_number_of_repetitions.json"), "w"), indent=1)
+    dt = dangling_tail_cases(os.path.join(t, "read_threading_graph_unit_tests.rs"))
+    json.dump(dt, open(os.path.join(HERE, "dangling_tail_cases.json"), "w"), indent=1)
+    print("find_number_of_repetitions cases:", len(fr), " dangling tail cases:", len(dt))
     print("realign cases:", {k: len(v) for k, v in rc.items()})
     print("pairhmm rows:", sum(1 for l in open(os.path.join(HERE, "pairhmm-testdata.txt")) if not l.startswith("#")))
     print("calculate_cigar cases:", len(cc))
