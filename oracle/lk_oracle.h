@@ -121,6 +121,17 @@ int lko_filter_poorly_modeled_evidence(double *values, int n_alleles, int n_read
                                        const double *thresholds, uint8_t *keep);
 
 /* ---- multi-threaded batch drivers (lk_oracle_mt.c) ---- */
+/* lk_oracle_simd.c: OUR fp32 SIMD stand-in for the un-vendored gkl AVX path (baseline infrastructure, not gkl) */
+void lko_simd_force_lanes(int lanes);
+int lko_simd_supported(int lanes);
+const char *lko_simd_isa(void);
+double lko_pairhmm_forward_vector(const uint8_t *hap, int hap_len, const uint8_t *read, const uint8_t *qual, const uint8_t *ins,
+                                  const uint8_t *del, const uint8_t *gcp, int read_len, int use_tristate, int *redone);
+int lko_pairhmm_batch_vector_mt(int n_regions, const int64_t *region_read_start, const int64_t *region_hap_start,
+                                const int64_t *read_off, const uint8_t *read_bases, const uint8_t *read_qual,
+                                const uint8_t *read_ins, const uint8_t *read_del, const uint8_t *read_gcp,
+                                const int64_t *hap_off, const uint8_t *hap_bases, const int64_t *out_off,
+                                int use_tristate, int n_threads, double *out);
 void lko_init(void); /* force lazy tables; call once before threads */
 /* One region per worker task (assembly_region_walker.rs:140).  Region g owns reads
  * [region_read_start[g], region_read_start[g+1]) and haplotypes likewise; its

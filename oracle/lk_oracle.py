@@ -30,7 +30,8 @@ def build(native=False, quiet=True):
         os.makedirs(out, exist_ok=True)
         so = os.path.join(out, "liblk_oracle_native.so")
         cmd = ["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fPIC", "-std=c11", "-D_GNU_SOURCE", "-shared",
-               "-o", so, os.path.join(HERE, "lk_oracle.c"), os.path.join(HERE, "lk_oracle_mt.c"), "-lm", "-lpthread"]
+               "-o", so, os.path.join(HERE, "lk_oracle.c"), os.path.join(HERE, "lk_oracle_mt.c"),
+               os.path.join(HERE, "lk_oracle_simd.c"), "-lm", "-lpthread"]
         subprocess.run(cmd, check=True, capture_output=quiet)
         return so
     subprocess.run(["make", "-C", HERE], check=True, capture_output=quiet)
@@ -184,3 +185,38 @@ def sw_batch(ref_off, refs, alt_off, alts, params, strategy, use_shortcut=True, 
                       strategy, 1 if use_shortcut else 0, max_ops, int(n_threads), _p(ops, u32p), _p(n_ops, i32p),
                       _p(offs, i32p))
     return ops, n_ops, offs
+
+
+def vector_isa(lib_path=None):
+    """ISA the SIMD stand-in picked on this CPU ("avx512 x16 fp32", "avx2+fma x8 fp32" or "sse2 x4 fp32")."""
+    L = lib(lib_path)
+    L.lko_simd_isa.restype = C.c_char_p
+    return L.lko_simd_isa().decode()
+
+
+def pairhmm_batch_vector(batch, use_tristate=True, n_threads=None, lib_path=None, force_lanes=0, want_redone=False):
+    """OUR fp32 SIMD stand-in for the reference's un-vendored gkl AVX path (lk_oracle_simd.c), same contract as
+    pairhmm_batch.  force_lanes in (16, 8, 4) pins the variant (tests)."""
+    L = lib(lib_path)
+    g = lambda k: batch[k] if isinstance(batch, dict) else getattr(batch, k)
+    rrs, rhs = np.ascontiguousarray(g("region_read_start"), np.int64), np.ascontiguousarray(g("region_hap_start"), np.int64)
+    roff, hoff = np.ascontiguousarray(g("read_off"), np.int64), np.ascontiguousarray(g("hap_off"), np.int64)
+    rb, rq, ri, rd, hb = (_u8(g(k)) for k in ("read_bases", "read_qual", "read_ins", "read_del", "hap_bases"))
+    gcp = batch["read_gcp"] if isinstance(batch, dict) else batch["read_gcp"]
+    gcp = _u8(gcp)
+    n_regions = len(rrs) - 1
+    pc = np.diff(rrs) * np.diff(rhs)
+    out_off = np.zeros(n_regions + 1, dtype=np.int64)
+    np.cumsum(pc, out=out_off[1:])
+    out = np.empty(int(out_off[-1]), dtype=np.float64)
+    if n_threads is None:
+        n_threads = os.cpu_count() or 1
+    L.lko_simd_force_lanes.restype = None
+    L.lko_simd_force_lanes(int(force_lanes))
+    L.lko_pairhmm_batch_vector_mt.restype = C.c_int
+    i64p = C.POINTER(C.c_int64)
+    redone = L.lko_pairhmm_batch_vector_mt(n_regions, _p(rrs, i64p), _p(rhs, i64p), _p(roff, i64p), _p(rb, u8p), _p(rq, u8p), _p(ri, u8p),
+                                           _p(rd, u8p), _p(gcp, u8p), _p(hoff, i64p), _p(hb, u8p), _p(out_off, i64p),
+                                           1 if use_tristate else 0, int(n_threads), _p(out, f64p))
+    L.lko_simd_force_lanes(0)
+    return (out, redone) if want_redone else out

@@ -124,3 +124,19 @@ def test_pcr_cache_values_match_survey_table():
     host = [OL.lko_pcr_error_model_adjusted_qual(n, 1.0) for n in range(13)]
     assert host == [40, 39, 39, 38, 37, 36, 34, 31, 28, 23, 16, 7, 6]
     assert OL.lko_pcr_error_model_adjusted_qual(30, 3.0) == 16 and OL.lko_pcr_error_model_adjusted_qual(100, 1.0) == 6
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """bench.py --impl reference builds its inputs through the generator library only: the process must never map
+    liblorikeet_b200.so (the driver records the libraries each arm loads)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from lorikeet_b200 import synth\n"
+            "from oracle import lk_oracle as O\n"
+            "b = synth.pairhmm_regions(2)\n"
+            "O.pairhmm_batch(b, n_threads=2); O.pairhmm_batch_vector(b, n_threads=2)\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'liblorikeet_b200_synth.so' in maps and 'liblk_oracle' in maps\n"
+            "assert 'liblorikeet_b200.so' not in maps, 'product library mapped'\n" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)
