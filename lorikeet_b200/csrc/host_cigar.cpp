@@ -310,6 +310,7 @@ extern "C" lk_status lk_calculate_cigar_finish(const uint8_t *ref, int64_t ref_l
 extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
                                               const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
                                               lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops) {
+    LK_ABI_GUARD_BEGIN
     if (!ctx) return LK_ERR_INVALID;
     if (n_pairs < 0 || !params || max_ops < 1) return lk_fail(ctx, LK_ERR_INVALID, "bad calculate_cigar arguments");
     if (n_pairs == 0) return LK_OK;
@@ -367,6 +368,7 @@ extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, cons
     });
     if (failed.load() != (int)LK_OK) return lk_fail(ctx, (lk_status)failed.load(), "calculate_cigar_finish failed");
     return LK_OK;
+    LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }
 
 // =================================================================================================
@@ -551,6 +553,7 @@ extern "C" lk_status lk_realign_finish(const uint8_t *read, int64_t read_len, co
 // realign_reads_to_their_best_haplotype for a batch of regions (assembly_based_caller_utils.rs:208-246).
 extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch *b, int32_t max_ops, int32_t *best_allele,
                                             uint8_t *informative, uint32_t *cigar_ops, int32_t *n_ops, int64_t *pos) {
+    LK_ABI_GUARD_BEGIN
     if (!ctx) return LK_ERR_INVALID;
     if (!b || max_ops < 1 || b->n_regions < 0) return lk_fail(ctx, LK_ERR_INVALID, "bad realign arguments");
     if (b->n_regions == 0) return LK_OK;
@@ -683,6 +686,7 @@ extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch 
     });
     if (failed.load() != (int)LK_OK) return lk_fail(ctx, (lk_status)failed.load(), "realign_finish failed");
     return LK_OK;
+    LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }
 
 // The alignment step of the read-threading graph's dangling-end merges (src/read_threading/read_threading_graph.rs:1370-1486:

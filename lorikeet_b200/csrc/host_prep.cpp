@@ -58,6 +58,7 @@ void build_prep(const lk_pairhmm_batch *b, int64_t g0, int64_t g1, int force_k, 
     int64_t w = 0;
     for (int64_t h = 0; h < n_haps; h++) {
         const int H = (int)(b->hap_off[hbase + h + 1] - b->hap_off[hbase + h]);
+        w = (w + 15) & ~(int64_t)15;  // every encoded haplotype (left guard band included) starts 16-byte aligned
         P.henc_off[(size_t)h] = w + HENC_PADL;
         w += H + HENC_PADL + HENC_PADR;
         P.h_max = std::max(P.h_max, H);

@@ -19,6 +19,7 @@
 
 #include "../../include/lorikeet_b200.h"
 #include "host_model.h"
+#include "host_parallel.h"
 #include "host_prep.h"
 #include "lk_api_internal.h"
 #include "lk_internal.h"
@@ -493,6 +494,7 @@ static lk_status download_locked(lk_ctx *ctx, lk_resident *R, double *out, uint8
 }
 
 extern "C" lk_status lk_pairhmm_upload(lk_ctx *ctx, const lk_pairhmm_batch *batch, lk_resident **out_res) {
+    LK_ABI_GUARD_BEGIN
     if (!ctx || !out_res) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
     *out_res = nullptr;
@@ -509,6 +511,7 @@ extern "C" lk_status lk_pairhmm_upload(lk_ctx *ctx, const lk_pairhmm_batch *batc
     if (st != LK_OK) { lk_resident_free(ctx, R); return st; }
     *out_res = R;
     return LK_OK;
+    LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }
 
 extern "C" lk_status lk_pairhmm_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms) {
@@ -551,6 +554,7 @@ extern "C" lk_status lk_pairhmm_batch_host(lk_ctx *ctx, const lk_pairhmm_batch *
 
 // With a hook the pipeline is the region driver: out / flags are ignored, hook->values / hook->keep are filled.
 lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double *out, uint8_t *flags, const lk_engine_hook *hook) {
+    LK_ABI_GUARD_BEGIN
     if (!ctx) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
     timespec ts_entry; clock_gettime(CLOCK_MONOTONIC, &ts_entry);
@@ -648,6 +652,7 @@ lk_status lk_pairhmm_pipeline(lk_ctx *ctx, const lk_pairhmm_batch *batch, double
     if (trace) fprintf(stderr, "[lk] drained (t=%.2f; entry -> first chunk %.2f ms)\n", now_ms() - t_begin, t_begin - t_entry);
     ctx->last_launch_count = launches;
     return st;
+    LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }
 
 extern "C" lk_status lk_pairhmm_forward(lk_ctx *ctx, const uint8_t *hap, int64_t hap_len, const uint8_t *read,
@@ -731,6 +736,7 @@ extern "C" lk_status lk_engine_modify_read_qualities_device(lk_ctx *ctx, const l
 extern "C" lk_status lk_engine_normalize_and_filter_device(lk_ctx *ctx, const lk_engine_args *args, const lk_pairhmm_batch *batch,
                                                            const int32_t *ref_allele_index, const double *likelihoods,
                                                            double *values, uint8_t *keep) {
+    LK_ABI_GUARD_BEGIN
     if (!ctx) return LK_ERR_INVALID;
     if (!args || !batch) return lk_fail(ctx, LK_ERR_INVALID, "null arguments");
     int64_t n_reads = 0, n_haps = 0;
@@ -805,4 +811,5 @@ extern "C" lk_status lk_engine_normalize_and_filter_device(lk_ctx *ctx, const lk
         return done(lk_cuda_fail(ctx, e, "D2H keep"));
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return done(lk_cuda_fail(ctx, e, "post-ops"));
     return done(LK_OK);
+    LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }

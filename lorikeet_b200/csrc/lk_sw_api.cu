@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "host_parallel.h"
 #include "lk_api_internal.h"
 #include "lk_internal.h"
 #include "sw_core.cuh"
@@ -207,10 +208,12 @@ lk_status sw_download_locked(lk_ctx *ctx, lk_resident *R, uint32_t *cigar_ops, i
 extern "C" lk_status lk_sw_upload(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
                                   const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
                                   lk_sw_overhang strategy, int32_t max_ops, lk_resident **out_res) {
+    LK_ABI_GUARD_BEGIN
     if (!ctx || !out_res) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
     *out_res = nullptr;
     return sw_upload_locked(ctx, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops, out_res);
+    LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }
 
 extern "C" lk_status lk_sw_run_resident(lk_ctx *ctx, lk_resident *res, float *kernel_ms) {
@@ -233,6 +236,7 @@ extern "C" lk_status lk_sw_batch_host(lk_ctx *ctx, int64_t n_pairs, const int64_
                                       const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
                                       lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops,
                                       int32_t *alignment_offset) {
+    LK_ABI_GUARD_BEGIN
     if (!ctx) return LK_ERR_INVALID;
     std::lock_guard<std::mutex> g(ctx->mu);
     lk_status st = sw_validate(ctx, n_pairs, ref_off, refs, alt_off, alts, params, strategy, max_ops);
@@ -284,6 +288,7 @@ extern "C" lk_status lk_sw_batch_host(lk_ctx *ctx, int64_t n_pairs, const int64_
     }
     ctx->last_launch_count = launches;
     return st;
+    LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }
 
 extern "C" lk_status lk_sw_align(lk_ctx *ctx, const uint8_t *ref, int64_t ref_len, const uint8_t *alt, int64_t alt_len,

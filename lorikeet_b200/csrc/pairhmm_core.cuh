@@ -41,7 +41,7 @@ namespace lk {
 // and >H unconditionally.  Read bases become a one-hot mask (encode_base: A=01 C=02 G=04 T=08, N=FF so
 // that it matches anything) when the prior table is built.  Any other byte flags the sequence
 // SEQ_EXOTIC, which routes its pairs to the byte-exact f64 pass.
-constexpr int HENC_PADL = 36;
+constexpr int HENC_PADL = 48;  // a multiple of 16: every encoded haplotype starts 16-byte aligned (host_prep.cpp), so a bulk copy can stage it
 constexpr int HENC_PADR = 44;
 
 // Slice of the per-warp prior table (fast kernel) a haplotype base selects.
@@ -57,11 +57,19 @@ LK_DEV uint8_t base_slice(uint8_t b) {
     }
 }
 // floats of per-warp shared memory pairhmm_fast_task<K> needs
-template <int K> struct FastTable { static constexpr int floats = N_PRIOR_SLICES * ((K + 3) / 4) * 32 * 4; };
+// LK_FAST_TMA = 1 (experiment, see DESIGN.md "why no TMA staging"): the fast kernel stages every encoded haplotype into
+// per-warp shared memory with cp.async.bulk + an mbarrier (double-buffered: haplotype h+1 is in flight while h is swept)
+// and reads its per-step table slice with LDS.U8 instead of LDG.U8.
+#ifndef LK_FAST_TMA
+#define LK_FAST_TMA 0
+#endif
+constexpr int FAST_TMA_BUF = 512;  // bytes per staged haplotype (pads included): H <= 420, enough for cfg#2
+constexpr int FAST_TMA_FLOATS = LK_FAST_TMA ? (2 * FAST_TMA_BUF + 16) / 4 : 0;
+template <int K> struct FastTable { static constexpr int floats = N_PRIOR_SLICES * ((K + 3) / 4) * 32 * 4 + FAST_TMA_FLOATS; };
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-constexpr int fast_table_floats(int K) { return N_PRIOR_SLICES * ((K + 3) / 4) * 32 * 4; }
+constexpr int fast_table_floats(int K) { return N_PRIOR_SLICES * ((K + 3) / 4) * 32 * 4 + FAST_TMA_FLOATS; }
 
 LK_DEV uint32_t encode_base(uint8_t b, bool &exotic) {
     uint32_t m;
@@ -310,9 +318,49 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id, float *ta
         h_first = h0 + th.begin;
         h_end = h_first + th.count;
     }
+#if LK_FAST_TMA && defined(__CUDA_ARCH__)
+    // ---- bulk-copy staging of the encoded haplotypes (experiment) ----
+    uint8_t *tma_buf = reinterpret_cast<uint8_t *>(tab + N_PRIOR_SLICES * KQ * 128);
+    const uint32_t tma_buf_s = (uint32_t)__cvta_generic_to_shared(tma_buf);
+    const uint32_t tma_bar_s = tma_buf_s + 2 * FAST_TMA_BUF;
+    auto tma_issue = [&](int64_t hh, int buf) {  // lane 0 only
+        const int HH = (int)(A.hap_off[hh + 1] - A.hap_off[hh]);
+        const uint32_t bytes = (uint32_t)((HENC_PADL + HH + HENC_PADR + 15) & ~15);
+        const uint8_t *src = A.hidx + A.henc_off[hh] - HENC_PADL;
+        const uint32_t bar = tma_bar_s + 8u * (uint32_t)buf;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tma_buf_s + (uint32_t)buf * FAST_TMA_BUF),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tma_bar_s) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tma_bar_s + 8u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (h_first < h_end) tma_issue(h_first, 0);
+    }
+    __syncwarp();
+    int tma_it = 0;
+#endif
     for (int64_t h = h_first; h < h_end; ++h) {
         const int H = (int)(A.hap_off[h + 1] - A.hap_off[h]);
+#if LK_FAST_TMA && defined(__CUDA_ARCH__)
+        const int tma_cur = tma_it & 1;
+        {
+            const uint32_t bar = tma_bar_s + 8u * (uint32_t)tma_cur, parity = (uint32_t)(tma_it >> 1) & 1u;
+            uint32_t ok;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            } while (!ok);
+        }
+        __syncwarp();  // every lane is past its last read of the other buffer (haplotype h-1)
+        if (lane == 0 && h + 1 < h_end) tma_issue(h + 1, tma_cur ^ 1);
+        tma_it++;
+        const uint8_t *hp = tma_buf + tma_cur * FAST_TMA_BUF + HENC_PADL - 1 - lig;  // hp[s] = table slice of column (s - lig), in shared memory
+#else
         const uint8_t *hp = A.hidx + A.henc_off[h] - 1 - lig;  // hp[s] = table slice of column (s - lig)
+#endif
         const float kinit = kcoef * (FAST_INIT / (float)H);
         float M[K], I[K], D[K];
 #pragma unroll
@@ -323,7 +371,11 @@ LK_DEV void pairhmm_fast_task(W &w, const PairHmmArgs &A, int task_id, float *ta
 
 LK_UNROLL_N(LK_FAST_UNROLL)
         for (int s = 1; s <= n_steps; ++s) {
+#if LK_FAST_TMA && defined(__CUDA_ARCH__)
+            const float *trow = tab + ((int)hp[s] * KQ * 32 + lane) * 4;
+#else
             const float *trow = tab + ((int)w.ldg(hp + s) * KQ * 32 + lane) * 4;
+#endif
             float sel[KQ * 4];
 #pragma unroll
             for (int q = 0; q < KQ; q++) w.lds4(sel + 4 * q, trow + q * 128);
@@ -368,6 +420,13 @@ LK_UNROLL_N(LK_FAST_UNROLL)
             }
         }
     }
+#if LK_FAST_TMA && defined(__CUDA_ARCH__)
+    __syncwarp();
+    if (lane == 0) {  // the warp's next task initialises the barriers afresh
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tma_bar_s) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tma_bar_s + 8u) : "memory");
+    }
+#endif
 }
 
 // =============================================================================================

@@ -20,9 +20,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         ms = [res.run() for _ in range(5)]
         out, flags = res.download(want_flags=True)
         best = min(ms)
-        print("K=%s regions=%d cells=%.3e best_ms=%.3f GCUPS=%.1f launches=%d rescued=%d" % (
+        import hashlib
+        print("K=%s regions=%d cells=%.3e best_ms=%.3f GCUPS=%.1f launches=%d rescued=%d sha=%s" % (
             os.environ.get("LK_FORCE_K", "auto"), n, res.n_cells, best, res.n_cells / best / 1e6, res.launch_count,
-            int(flags.sum())), flush=True)
+            int(flags.sum()), hashlib.sha1(out.tobytes()).hexdigest()[:12]), flush=True)
         t = time.time()
         ctx.pairhmm_batch(b)
         print("   e2e host call: %.1f ms" % ((time.time() - t) * 1e3), flush=True)
