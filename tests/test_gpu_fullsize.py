@@ -76,8 +76,10 @@ def test_cfg3_full_size_2000_regions(ctx):
     # the 111-region slice computed on its own is bit-identical to the same slice of the big batch
     alone = ctx.pairhmm_batch(b.region_slice(1000, 1020))
     assert np.array_equal(alone, out[1000 * 32:1020 * 32])
-    # every read scores best against one of its region's haplotypes by a clear margin over an unrelated pairing's ~-1700
-    assert out.reshape(n, 8, 4).max(axis=2).min() > -1200.0
+    # 10 kbp reads with 3 % indel noise at Q7-Q20 score around -2300 against their own region's haplotypes; a read against
+    # an unrelated 12 kbp sequence would be below -15000
+    per_read = out.reshape(n, 8, 4)
+    assert per_read.max(axis=2).min() > -4000.0 and per_read.min() > -6000.0
     # oracle on 8 random regions; one oracle task per READ (a region re-packed as 8 single-read regions) so the host cores
     # share the 8 x 32 pairs of 1.2e8 cells each
     rng = np.random.default_rng(33)
