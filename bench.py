@@ -368,21 +368,45 @@ class ShardedBench:
         self._keepalive.append(t)
         self.keep_t = torch.empty(n_reads, dtype=torch.uint8).pin_memory()
         stride = self.lay.stride
-        self.host_all = torch.empty(self.world * stride, dtype=torch.float64).pin_memory()  # every rank ends with the full set
+        # every rank ends every step with the full gathered set in its pinned host memory.  At N > 1 the collective and the
+        # D2H of the gathered set (N x the slab) run on a side stream, double-buffered, and overlap the NEXT step's H2D and
+        # kernels; the timed loop ends with e2e_finish(), which waits for the last step's copy.
+        self.host_bufs = [torch.empty(self.world * stride, dtype=torch.float64).pin_memory() for _ in range(2 if self.world > 1 else 1)]
+        self.host_all = self.host_bufs[0]
+        self.e_it = 0
         if self.world > 1:
-            self.e_slab = torch.zeros(stride, dtype=torch.float64, device="cuda")
-            self.e_gathered = torch.empty(self.world * stride, dtype=torch.float64, device="cuda")
+            self.e_slab = [torch.zeros(stride, dtype=torch.float64, device="cuda") for _ in range(2)]
+            self.e_gathered = [torch.empty(self.world * stride, dtype=torch.float64, device="cuda") for _ in range(2)]
+            self.e_side = torch.cuda.Stream()
+            self.e_done = [None, None]
         self.h2d = self.input_bytes + int(self.mapq.nbytes)
         self.d2h = int(self.host_all.numel() * 8 + self.keep_t.numel())
 
     def e2e_step(self):
+        torch = self.torch
         keep = self.keep_t.numpy()
         if self.world == 1:  # matrices straight into pinned host memory
             self.eng.compute_read_likelihoods(self.rbatch, self.mapq, values=self.host_all.numpy()[:self.n_mine], keep=keep)
-        else:                # matrices stay in HBM for the collective, the gathered set goes to the host
-            self.eng.compute_read_likelihoods(self.rbatch, self.mapq, keep=keep, values_device_ptr=self.e_slab.data_ptr())
-            self.sh.all_gather(self.e_slab, self.e_gathered)
-            self.host_all.copy_(self.e_gathered)  # synchronous D2H
+            return
+        b = self.e_it & 1
+        self.e_it += 1
+        if self.e_done[b] is not None:
+            self.e_done[b].synchronize()  # buffer pair b was last used two steps ago: its gather + copy must be through
+        # matrices stay in HBM for the collective (the call returns when this rank's slab is complete)
+        self.eng.compute_read_likelihoods(self.rbatch, self.mapq, keep=keep, values_device_ptr=self.e_slab[b].data_ptr())
+        with torch.cuda.stream(self.e_side):
+            self.sh.all_gather(self.e_slab[b], self.e_gathered[b])
+            self.host_bufs[b].copy_(self.e_gathered[b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.e_side)
+        self.e_done[b] = ev
+        self.host_all = self.host_bufs[b]
+
+    def e2e_finish(self):
+        if self.world > 1:
+            for ev in self.e_done:
+                if ev is not None:
+                    ev.synchronize()
 
     def verify_e2e(self):
         np = self.np
@@ -490,10 +514,12 @@ def main():
         ok_res, n_chk = sb.verify_resident() if world > 1 else (True, 0)
         sb.setup_e2e()
         sb.e2e_step()  # warm the staging buffers
+        sb.e2e_finish()
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             sb.e2e_step()
+        sb.e2e_finish()  # the last step's gathered set is in host memory
         barrier()
         e2e_s = time.perf_counter() - t0
         ok_e2e, n_chk2 = sb.verify_e2e() if world > 1 else (True, 0)
@@ -604,7 +630,8 @@ def main():
                     "ms_per_step": main_r["e2e_ms_per_step"],
                     "api": "lk_engine_compute_read_likelihoods = compute_read_likelihoods: raw reads + MAPQ in pinned host "
                            "buffers -> modify_read_qualities, PairHMM, normalise, filter on the device -> [allele][read] "
-                           "matrices + keep mask" + (" -> all_gather -> every rank's host" if world > 1 else " on the host")},
+                           "matrices + keep mask" + (" -> all_gather -> the full set in every rank's pinned host memory (collective + D2H "
+                                                     "on a side stream, overlapping the next step)" if world > 1 else " on the host")},
             "gpu_launches": main_r["launches"],
             "clocks": main_r["clocks"],
             "roofline": roofline,

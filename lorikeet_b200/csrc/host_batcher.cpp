@@ -32,6 +32,9 @@ struct Request {
     uint8_t *keep_or_flags;
     lk_status status = LK_OK;
     bool done = false;
+    // every caller sleeps on ITS OWN condition variable: with one shared one, each finished launch woke every blocked worker
+    // of every device (hundreds of threads, thousands of launches per second) just to find that it was not their turn
+    std::condition_variable cv;
 };
 
 }  // namespace
@@ -43,7 +46,7 @@ struct lk_batcher {
     int32_t max_regions = 256;
     int64_t max_wait_us = 200;
     std::mutex mu;
-    std::condition_variable cv_work, cv_done;
+    std::condition_variable cv_work;
     std::deque<Request *> queue;
     bool stop = false;
     // statistics
@@ -212,8 +215,7 @@ void lk_batcher::run(int dev, int w) {
         n_batches++;
         n_regions += (int64_t)reqs.size();
         me.last_batch = reqs.size();
-        for (Request *q : reqs) q->done = true;
-        cv_done.notify_all();
+        for (Request *q : reqs) { q->done = true; q->cv.notify_one(); }
     }
 }
 
@@ -301,7 +303,7 @@ extern "C" lk_status lk_batcher_wait(lk_batcher *b, lk_ticket *ticket) {
     lk_status st;
     {
         std::unique_lock<std::mutex> lock(b->mu);
-        b->cv_done.wait(lock, [&] { return ticket->q.done; });
+        ticket->q.cv.wait(lock, [&] { return ticket->q.done; });
         st = ticket->q.status;
     }
     delete ticket;

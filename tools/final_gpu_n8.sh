@@ -12,6 +12,7 @@ for d in 1 2 4 8; do
   tools/native/bench_batcher 8000 64 512 200 1 $d | tail -1
   tools/native/bench_batcher 8000 256 512 200 1 $d | tail -1
   tools/native/bench_batcher 8000 32 512 200 16 $d | tail -1
+  tools/native/bench_batcher 16000 64 512 200 64 $d | tail -1
 done
 } > gpurun_out/r02_pool_batcher_n$N.jsonl 2>&1
 cat gpurun_out/r02_pool_batcher_n$N.jsonl
