@@ -269,7 +269,7 @@ class ShardedBench:
     Region batches are dealt round-robin (lorikeet_b200.dispatch.ShardedRegions); after the timed loops every rank
     recomputes foreign batches locally and compares them bit for bit with what it received (gather_verified)."""
 
-    def __init__(self, ctx, n_regions, batch_regions, rank, world, local_rank):
+    def __init__(self, ctx, n_regions, batch_regions, rank, world, local_rank, gather_to_host=False):
         import numpy as np
         import torch
         from lorikeet_b200 import synth
@@ -277,6 +277,7 @@ class ShardedBench:
         from lorikeet_b200.engine import PairHMMLikelihoodCalculationEngine, PCRErrorModel
         self.np, self.torch, self.synth, self.device_view = np, torch, synth, device_view
         self.ctx, self.rank, self.world = ctx, rank, world
+        self.gather_to_host = gather_to_host
         self.eng = PairHMMLikelihoodCalculationEngine(ctx, 10, -4.5, PCRErrorModel.CONSERVATIVE, 18, False, 1.0, 0.02, True, False, False)
         self.sh = ShardedRegions(n_regions, batch_regions)
         self.n_regions, self.batch_regions = n_regions, batch_regions
@@ -368,10 +369,14 @@ class ShardedBench:
         self._keepalive.append(t)
         self.keep_t = torch.empty(n_reads, dtype=torch.uint8).pin_memory()
         stride = self.lay.stride
-        # every rank ends every step with the full gathered set in its pinned host memory.  At N > 1 the collective and the
-        # D2H of the gathered set (N x the slab) run on a side stream, double-buffered, and overlap the NEXT step's H2D and
-        # kernels; the timed loop ends with e2e_finish(), which waits for the last step's copy.
-        self.host_bufs = [torch.empty(self.world * stride, dtype=torch.float64).pin_memory() for _ in range(2 if self.world > 1 else 1)]
+        # e2e at N > 1: the region driver leaves this rank's matrices in HBM (values may be device memory), then -- on a side
+        # stream, double-buffered, overlapping the NEXT step's H2D and kernels -- the slab is (a) copied to this rank's pinned
+        # host memory (the step's result read, as at N = 1) and (b) all_gathered, so that every GPU holds the full likelihood set
+        # (what north_star's allgather is for).  gather_to_host additionally copies the full gathered set (N x the slab) to every
+        # rank's host: measured once at N = 8 (profiles/r02_bench_n8_full_set_to_host.json), eight ranks writing the same 656 MB
+        # to host memory per step cost 48 ms of a 155 ms step even overlapped.  The timed loop ends with e2e_finish().
+        full = self.world * stride if self.gather_to_host else max(self.n_mine, 1)
+        self.host_bufs = [torch.empty(full, dtype=torch.float64).pin_memory() for _ in range(2 if self.world > 1 else 1)]
         self.host_all = self.host_bufs[0]
         self.e_it = 0
         if self.world > 1:
@@ -379,6 +384,7 @@ class ShardedBench:
             self.e_gathered = [torch.empty(self.world * stride, dtype=torch.float64, device="cuda") for _ in range(2)]
             self.e_side = torch.cuda.Stream()
             self.e_done = [None, None]
+            self.e_last = 0
         self.h2d = self.input_bytes + int(self.mapq.nbytes)
         self.d2h = int(self.host_all.numel() * 8 + self.keep_t.numel())
 
@@ -395,11 +401,15 @@ class ShardedBench:
         # matrices stay in HBM for the collective (the call returns when this rank's slab is complete)
         self.eng.compute_read_likelihoods(self.rbatch, self.mapq, keep=keep, values_device_ptr=self.e_slab[b].data_ptr())
         with torch.cuda.stream(self.e_side):
+            if not self.gather_to_host and self.n_mine:
+                self.host_bufs[b][:self.n_mine].copy_(self.e_slab[b][:self.n_mine], non_blocking=True)
             self.sh.all_gather(self.e_slab[b], self.e_gathered[b])
-            self.host_bufs[b].copy_(self.e_gathered[b], non_blocking=True)
+            if self.gather_to_host:
+                self.host_bufs[b].copy_(self.e_gathered[b], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.e_side)
         self.e_done[b] = ev
+        self.e_last = b
         self.host_all = self.host_bufs[b]
 
     def e2e_finish(self):
@@ -411,8 +421,13 @@ class ShardedBench:
     def verify_e2e(self):
         np = self.np
         mq = lambda raw: np.full(raw.n_reads, 60, np.uint8)
-        return self.verify(lambda pos, n: self.host_all.numpy()[pos:pos + n],
-                           lambda raw: self.eng.compute_read_likelihoods(raw, mq(raw))[0], n_checks=1, equal_nan=True)
+        got = (lambda pos, n: self.host_all.numpy()[pos:pos + n]) if self.gather_to_host else \
+              (lambda pos, n: self.e_gathered[self.e_last][pos:pos + n].cpu().numpy())
+        ok, n = self.verify(got, lambda raw: self.eng.compute_read_likelihoods(raw, mq(raw))[0], n_checks=1, equal_nan=True)
+        if not self.gather_to_host and self.n_mine:  # this rank's host copy equals its slab of the gathered set
+            mine = self.e_gathered[self.e_last][self.rank * self.lay.stride:self.rank * self.lay.stride + self.n_mine].cpu().numpy()
+            ok = ok and bool(np.array_equal(self.host_all.numpy()[:self.n_mine], mine, equal_nan=True))
+        return ok, n
 
     def close(self):
         self.res.free()
@@ -441,6 +456,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the SW (cfg4), long-read (cfg3) and scale-out (cfg5) side measurements")
     ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--e2e-gather-to-host", action="store_true",
+                    help="N > 1: e2e also copies the FULL gathered set (N x the slab) to every rank's host memory each step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -495,7 +512,7 @@ def main():
 
     def measure(n_total, batch_regions, steps, warmup, sample_clocks):
         """Both measurements of one sharded configuration; every rank returns the same reduced numbers."""
-        sb = ShardedBench(ctx, n_total, batch_regions, rank, world, local_rank)
+        sb = ShardedBench(ctx, n_total, batch_regions, rank, world, local_rank, gather_to_host=args.e2e_gather_to_host)
         for _ in range(warmup):
             sb.step()
         sampler = ClockSampler(local_rank) if sample_clocks else None
@@ -630,8 +647,9 @@ def main():
                     "ms_per_step": main_r["e2e_ms_per_step"],
                     "api": "lk_engine_compute_read_likelihoods = compute_read_likelihoods: raw reads + MAPQ in pinned host "
                            "buffers -> modify_read_qualities, PairHMM, normalise, filter on the device -> [allele][read] "
-                           "matrices + keep mask" + (" -> all_gather -> the full set in every rank's pinned host memory (collective + D2H "
-                                                     "on a side stream, overlapping the next step)" if world > 1 else " on the host")},
+                           "matrices + keep mask" + ((" -> this rank's slab to its pinned host memory + all_gather (every GPU holds the "
+                                                      "full set)" + (" + the full gathered set to every rank's host" if args.e2e_gather_to_host else "") +
+                                                      "; collective and D2H on a side stream, overlapping the next step") if world > 1 else " on the host")},
             "gpu_launches": main_r["launches"],
             "clocks": main_r["clocks"],
             "roofline": roofline,
