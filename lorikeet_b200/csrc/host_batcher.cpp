@@ -194,7 +194,9 @@ void lk_batcher::run(int dev, int w) {
             cv_work.wait_for(lock, std::chrono::microseconds(max_wait_us),
                              [&] { return stop || (int32_t)queue.size() >= max_regions || queue.size() >= me.last_batch * (size_t)(n_dev > 1 ? idle_now : 1); });
         // several devices: leave the other idle devices their share of what is queued (a share below ~8 regions is not
-        // worth a launch of its own)
+        // worth a launch of its own).  Measured alternative (round 2, 4 GPUs): making every dispatcher of a pool wait for and
+        // take at least 32 regions -- fewer, fuller launches -- left 256 blocked threads and the asynchronous callers where
+        // they were (5.6 / 6.1 / 9.4 TCUPS) and cost 64 blocked threads a third (4.0 -> 2.7 TCUPS): dropped.
         size_t take = (size_t)max_regions;
         if (n_dev > 1 && w == 0 && idle_now > 1) {
             const size_t share = (queue.size() + (size_t)idle_now - 1) / (size_t)idle_now;
