@@ -177,6 +177,9 @@ LK_DEV int lk_popc(unsigned v) {
 #ifndef LK_BAND_UNROLL
 #define LK_BAND_UNROLL 4
 #endif
+#ifndef LK_BAND_BLOCK
+#define LK_BAND_BLOCK 16  // steps per lean block of the band kernel (= block-floating-point upkeep cadence)
+#endif
 #ifndef LK_BAND_ORDER
 #define LK_BAND_ORDER 0  // statement order of the band kernel's cell (ptxas schedules them differently)
 #endif
@@ -709,21 +712,23 @@ LK_DEV void pairhmm_band_pair(W &w, const PairHmmArgs &A, int read, int64_t h, B
             Mu = rm * al; Iu = ri * al; Du = rd * al;
         };
 
-        const int s_lean_end = (H >> 4) << 4;  // last step of the last block in which lane 0's column is still <= H
+        constexpr int BLK = LK_BAND_BLOCK;  // steps per lean block = upkeep cadence (16 or 32; must divide the 32-element ring)
+        static_assert(BLK == 16 || BLK == 32, "the ring holds 32 elements and the exponent groups follow the upkeep cadence");
+        const int s_lean_end = (H / BLK) * BLK;  // last step of the last block in which lane 0's column is still <= H
         int s = 1, gen_end = n_steps < 32 ? n_steps : 32;
         for (;;) {  // generic start-up, lean blocks, generic tail (one copy of the generic loop in the code)
             for (; s <= gen_end; ++s) {
-                if (s <= 32 || (s & 15) == 1) upkeep(s);
+                if (s <= 32 || (s & (BLK - 1)) == 1) upkeep(s);
                 step(s, hp + s, bw + s, ring + ((s - 1) & 31), GenericTag());
             }
             if (gen_end == n_steps) break;
-            while (s + 15 <= s_lean_end) {  // s = 1 (mod 16)
+            while (s + BLK - 1 <= s_lean_end) {  // s = 1 (mod BLK)
                 upkeep(s);
                 const Bnd4 *rp = ring + ((s - 1) & 31);
                 const uint8_t *hq = hp + s;
                 Bnd4 *bq = bw + s;
 #pragma unroll 1
-                for (int u4 = 0; u4 < 16 / LK_BAND_UNROLL; ++u4) {
+                for (int u4 = 0; u4 < BLK / LK_BAND_UNROLL; ++u4) {
 #pragma unroll
                     for (int u = 0; u < LK_BAND_UNROLL; ++u) step(s + u, hq + u, bq + u, rp + u, LeanTag());
                     hq += LK_BAND_UNROLL; bq += LK_BAND_UNROLL; rp += LK_BAND_UNROLL; s += LK_BAND_UNROLL;
