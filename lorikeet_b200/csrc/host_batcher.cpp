@@ -19,6 +19,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "../../include/lorikeet_b200.h"
 #include "lk_api_internal.h"
 
@@ -54,11 +56,37 @@ struct lk_batcher {
     int idle_primaries = 0;  // primary dispatchers (one per device) waiting for work: a waking one leaves them their share
     // gather buffers, one set per dispatcher thread, kept across batches (fresh vectors cost more in page faults than the
     // copies)
+    // The byte arenas a launch copies to the device, and the result buffers it copies back into, live in PINNED host memory
+    // (grow-only, portable across the pool's devices): a cudaMemcpyAsync from / to pageable memory is staged through the
+    // driver's own bounce buffer and blocks the dispatcher for the duration of the copy.
+    template <class T> struct PinVec {
+        T *p = nullptr;
+        size_t n = 0, cap = 0;
+        PinVec() = default;
+        PinVec(const PinVec &) = delete;
+        PinVec &operator=(const PinVec &) = delete;
+        ~PinVec() { if (p) cudaFreeHost(p); }
+        void reserve(size_t want) {
+            if (want <= cap) return;
+            const size_t c = want + want / 2 + 4096;
+            T *q = nullptr;
+            if (cudaHostAlloc((void **)&q, c * sizeof(T), cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); throw std::bad_alloc(); }
+            if (n) memcpy(q, p, n * sizeof(T));
+            if (p) cudaFreeHost(p);
+            p = q; cap = c;
+        }
+        void clear() { n = 0; }
+        void resize(size_t m) { reserve(m); n = m; }
+        void append(const T *src, size_t m) { reserve(n + m); memcpy(p + n, src, m * sizeof(T)); n += m; }
+        void append_fill(size_t m, T v) { reserve(n + m); for (size_t i = 0; i < m; i++) p[n + i] = v; n += m; }
+        T *data() { return p; }
+        size_t size() const { return n; }
+    };
     struct Scratch {
         std::vector<int64_t> rrs, rhs, read_off, hap_off, rss, srs;
-        std::vector<uint8_t> bases, qual, ins, del, gcp, haps, mapq, aux;
+        PinVec<uint8_t> bases, qual, ins, del, gcp, haps, mapq, aux;
         std::vector<int32_t> ref_idx;
-        std::vector<double> out;
+        PinVec<double> out;
     };
     // two dispatcher threads PER DEVICE: the device calls serialise on the context, but one thread gathers / scatters its
     // batch while the other's is on the GPU.  All dispatchers of all devices pull from the one queue, so the deal over
@@ -120,18 +148,18 @@ void lk_batcher::process(lk_ctx *ctx, std::vector<Request *> &reqs, Scratch &S) 
         const int64_t hb0 = nh ? b->hap_off[0] : 0, hb1 = nh ? b->hap_off[nh] : 0;
         for (int64_t r = 0; r < nr; r++) read_off.push_back(read_off.back() + (b->read_off[r + 1] - b->read_off[r]));
         for (int64_t h = 0; h < nh; h++) hap_off.push_back(hap_off.back() + (b->hap_off[h + 1] - b->hap_off[h]));
-        bases.insert(bases.end(), b->read_bases + rb0, b->read_bases + rb1);
-        qual.insert(qual.end(), b->read_qual + rb0, b->read_qual + rb1);
-        ins.insert(ins.end(), b->read_ins + rb0, b->read_ins + rb1);
-        del.insert(del.end(), b->read_del + rb0, b->read_del + rb1);
+        bases.append(b->read_bases + rb0, (size_t)(rb1 - rb0));
+        qual.append(b->read_qual + rb0, (size_t)(rb1 - rb0));
+        ins.append(b->read_ins + rb0, (size_t)(rb1 - rb0));
+        del.append(b->read_del + rb0, (size_t)(rb1 - rb0));
         if (any_gcp) {
-            if (b->read_gcp) gcp.insert(gcp.end(), b->read_gcp + rb0, b->read_gcp + rb1);
-            else gcp.insert(gcp.end(), (size_t)(rb1 - rb0), b->gcp_constant);
+            if (b->read_gcp) gcp.append(b->read_gcp + rb0, (size_t)(rb1 - rb0));
+            else gcp.append_fill((size_t)(rb1 - rb0), b->gcp_constant);
         }
-        haps.insert(haps.end(), b->hap_bases + hb0, b->hap_bases + hb1);
+        haps.append(b->hap_bases + hb0, (size_t)(hb1 - hb0));
         if (need_mapq && nr > 0) {
             if (!reqs[g]->read_mapq) { bad = LK_ERR_INVALID; break; }  // (rejected at submit; kept as a guard)
-            mapq.insert(mapq.end(), reqs[g]->read_mapq, reqs[g]->read_mapq + nr);
+            mapq.append(reqs[g]->read_mapq, (size_t)nr);
         }
         ref_idx[g] = reqs[g]->ref_allele_index;
     }
