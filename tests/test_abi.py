@@ -140,3 +140,15 @@ def test_reference_arm_does_not_map_the_product_library():
             "assert 'liblorikeet_b200_synth.so' in maps and 'liblk_oracle' in maps\n"
             "assert 'liblorikeet_b200.so' not in maps, 'product library mapped'\n" % ROOT)
     subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_pool_has_no_cpu_fallback_either():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    L = _lib.load()
+    h = C.c_void_p()
+    assert L.lk_pool_create(None, 0, C.byref(h)) == _lib.LK_ERR_CUDA and not h.value
+    from lorikeet_b200.engine import DevicePool
+    with pytest.raises(_lib.LorikeetError):
+        DevicePool()
