@@ -43,6 +43,7 @@ lk_status lk_cuda_fail(lk_ctx *ctx, cudaError_t e, const char *what) {
 }
 
 cudaError_t DevBuf::reserve(size_t bytes) {
+    if (view) { p = nullptr; cap = 0; view = false; }
     if (bytes <= cap) return cudaSuccess;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
     size_t want = bytes + bytes / 8 + 256;
@@ -52,8 +53,8 @@ cudaError_t DevBuf::reserve(size_t bytes) {
     return cudaSuccess;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
+    if (p && !view) cudaFree(p);
+    p = nullptr; cap = 0; view = false;
 }
 
 template <class T>
@@ -320,17 +321,24 @@ static lk_status stage_range(lk_ctx *ctx, const lk_pairhmm_batch *b, int64_t g0,
     R->band_blocks = ctx->n_sm * LK_BAND_MINB;
     R->band_stride = 2 * ((int64_t)P.h_max + 1);
     if (R->n_band > 0) { RS(band_scratch, (int64_t)R->band_blocks * (LK_BAND_THREADS / 32) * R->band_stride * 16); }
+    // All metadata arrays travel as ONE H2D copy of the pinned arena into one device block with the same layout (256-byte
+    // aligned pieces); the per-array DevBufs become views into it.  (One copy instead of fourteen: a small launch of the
+    // batcher is latency-bound, and every cudaMemcpyAsync costs a few microseconds on both sides.)  rescue_pairs is the
+    // exception: the kernels append to it, so it keeps its own, larger buffer.
+    if ((e = R->meta.reserve(total + 256)) != cudaSuccess) return lk_cuda_fail(ctx, e, "alloc metadata");
     size_t off = 0;
     for (const Piece &pc : pieces) {
-        if (pc.dst != &R->rescue_pairs && (e = pc.dst->reserve(std::max<size_t>(pc.bytes, 16))) != cudaSuccess)
-            return lk_cuda_fail(ctx, e, "alloc metadata");
-        if (pc.bytes) {
-            memcpy((char *)R->pinned.p + off, pc.src, pc.bytes);
-            if ((e = cudaMemcpyAsync(pc.dst->p, (char *)R->pinned.p + off, pc.bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        if (pc.bytes) memcpy((char *)R->pinned.p + off, pc.src, pc.bytes);
+        if (pc.dst == &R->rescue_pairs) {
+            if (pc.bytes && (e = cudaMemcpyAsync(pc.dst->p, (char *)R->pinned.p + off, pc.bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
                 return lk_cuda_fail(ctx, e, "metadata H2D");
+        } else {
+            pc.dst->set_view((char *)R->meta.p + off);
         }
         off += (pc.bytes + 255) & ~(size_t)255;
     }
+    if (total && (e = cudaMemcpyAsync(R->meta.p, R->pinned.p, total, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return lk_cuda_fail(ctx, e, "metadata H2D");
 #undef RS
     if ((e = cudaEventRecord(R->ev_staged, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "event record");
     // ---- byte arenas straight from the caller's memory ----
@@ -529,7 +537,7 @@ extern "C" lk_status lk_pairhmm_download(lk_ctx *ctx, lk_resident *res, double *
 static void release_buffers(lk_resident *R) {
     DevBuf *bufs[] = { &R->read_bases, &R->read_qual, &R->read_ins, &R->read_del, &R->read_gcp, &R->read_off,
                        &R->read_region, &R->read_out_base, &R->read_flags, &R->region_hap_start, &R->hap_off,
-                       &R->region_read_start, &R->block_region, &R->read_mapq, &R->ref_allele_index, &R->qual_orig, &R->values, &R->keep,
+                       &R->region_read_start, &R->block_region, &R->read_mapq, &R->ref_allele_index, &R->meta, &R->qual_orig, &R->values, &R->keep,
                        &R->hap_bases, &R->hidx, &R->henc_off, &R->hap_flags, &R->tasks, &R->task_haps, &R->groups, &R->out,
                        &R->flags, &R->counters, &R->rescue_pairs, &R->scratch, &R->band_pairs, &R->band_scratch,
                        &R->sw_refs, &R->sw_alts, &R->sw_ref_off, &R->sw_alt_off, &R->sw_bt, &R->sw_bt_off,

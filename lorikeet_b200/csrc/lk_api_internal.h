@@ -14,8 +14,10 @@
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool view = false;  // p points into another DevBuf (the merged metadata block): never freed here
     cudaError_t reserve(size_t bytes);
     void release();
+    void set_view(void *q) { if (!view && p) cudaFree(p); p = q; cap = 0; view = true; }
 };
 
 struct PinnedBuf {
@@ -75,6 +77,7 @@ struct lk_resident {
     DevBuf tasks, task_haps, groups, out, flags, counters, rescue_pairs, scratch, band_pairs, band_scratch;
     // engine pre/post-ops on the device (N3)
     DevBuf region_read_start, block_region, read_mapq, ref_allele_index, qual_orig, values, keep;
+    DevBuf meta;            // every metadata array of the staged chunk, one H2D copy; the DevBufs above are views into it
     int64_t n_blocks = 0;   // (region, sample) blocks of the staged chunk
     bool sampled = false;   // several samples per region: block_region is in use
     // ---- Smith-Waterman ----
