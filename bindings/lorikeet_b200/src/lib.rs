@@ -264,6 +264,71 @@ impl Drop for Context {
     }
 }
 
+/// `PairHMM` of `src/pair_hmm/pair_hmm.rs` with the GPU behind it: the same method names, argument meaning and asserts, so the
+/// `AVXMode::Gpu` arm can stand in for the struct the engine owns today.  There is nothing to allocate on this path
+/// (`initialize` / `quick_initialize` / `reinitialize` only book-keep the sizes, as the gkl arm does, `:63-207`); the
+/// haplotype-prefix caching arguments are accepted and ignored exactly as the gkl arm ignores them (`:442-496`).
+pub struct PairHMM<'a> {
+    ctx: &'a Context,
+    initialized: bool,
+    max_read_length: usize,
+    max_haplotype_length: usize,
+    haplotypes: Vec<Vec<u8>>,
+    log_likelihood_array: Vec<f64>,
+}
+
+impl<'a> PairHMM<'a> {
+    /// `PairHMM::initialize` (`:63-127`): keeps the haplotypes in list order and the maximum lengths.
+    pub fn initialize(ctx: &'a Context, haplotypes: &[&[u8]], max_read_length: usize) -> PairHMM<'a> {
+        let max_haplotype_length = haplotypes.iter().map(|h| h.len()).max().unwrap_or(0);
+        PairHMM { ctx, initialized: true, max_read_length, max_haplotype_length, haplotypes: haplotypes.iter().map(|h| h.to_vec()).collect(), log_likelihood_array: Vec::new() }
+    }
+    /// `PairHMM::quick_initialize` (`:130-168`): not initialised when both sizes are zero (`:138-141`).
+    pub fn quick_initialize(ctx: &'a Context, max_read_length: usize, haplotype_max_length: usize) -> PairHMM<'a> {
+        PairHMM { ctx, initialized: !(max_read_length == 0 && haplotype_max_length == 0), max_read_length, max_haplotype_length: haplotype_max_length, haplotypes: Vec::new(), log_likelihood_array: Vec::new() }
+    }
+    /// `PairHMM::reinitialize` (`:193-207`): sizes only, as the reference (its re-allocations are commented out).
+    pub fn reinitialize(&mut self, max_read_length: usize, haplotype_max_length: usize) {
+        self.max_read_length = max_read_length;
+        self.max_haplotype_length = haplotype_max_length;
+        self.initialized = true;
+    }
+    pub fn do_not_use_tristate_correction(&self) {
+        self.ctx.do_not_use_tristate_correction().unwrap()
+    }
+    /// `PairHMM::compute_log10_likelihoods` (`:217-341`) for one region: `m_log_likelihood_array[r * A + h]`.
+    pub fn compute_log10_likelihoods(&mut self, batch: &RegionBatch) -> &[f64] {
+        assert!(self.initialized, "Must call initialize before calling compute_log10_likelihoods");
+        self.log_likelihood_array = self.ctx.pairhmm_batch(batch).unwrap().0; // the reference unwraps at pair_hmm.rs:348,372
+        &self.log_likelihood_array
+    }
+    /// `PairHMM::compute_read_likelihood_given_haplotype_log10` (`:404-500`), same asserts and messages.
+    #[allow(clippy::too_many_arguments)]
+    pub fn compute_read_likelihood_given_haplotype_log10(&self, haplotype_bases: &[u8], read_bases: &[u8], read_quals: &[u8], insertion_gop: &[u8],
+                                                         deletion_gop: &[u8], overall_gcp: &[u8], _recache_read_values: bool, _next_haplotype_bases: Option<&[u8]>) -> f64 {
+        assert!(self.initialized, "Must call initialize before calling compute_read_likelihood_given_haplotype_log10");
+        assert!(haplotype_bases.len() <= self.max_haplotype_length, "Haplotype bases is too long");
+        assert!(read_quals.len() == read_bases.len(), "Read bases and read quals aren't the same size");
+        assert!(insertion_gop.len() == read_bases.len(), "Read bases and insertion gcp aren't the same size");
+        assert!(deletion_gop.len() == read_bases.len(), "Read bases and deletion gcp aren't the same size");
+        assert!(overall_gcp.len() == read_bases.len(), "Read bases and overal GCP aren't the same size");
+        let result = self.ctx.forward(haplotype_bases, read_bases, read_quals, insertion_gop, deletion_gop, overall_gcp).unwrap();
+        assert!(result <= 0.0, "PairHMM Log Probability cannot be greater than 0.0"); // :478-481
+        result
+    }
+    /// `PairHMM::get_log_likelihood_array` (`:377-379`)
+    pub fn get_log_likelihood_array(&self) -> &[f64] {
+        &self.log_likelihood_array
+    }
+    pub fn haplotypes(&self) -> &[Vec<u8>] {
+        &self.haplotypes
+    }
+    /// `PairHMM::find_first_position_where_haplotypes_differ` (`:706-717`)
+    pub fn find_first_position_where_haplotypes_differ(h1: &[u8], h2: &[u8]) -> usize {
+        h1.iter().zip(h2.iter()).position(|(a, b)| a != b).unwrap_or_else(|| h1.len().min(h2.len()))
+    }
+}
+
 fn pack_pairs(pairs: &[(&[u8], &[u8])]) -> (Vec<i64>, Vec<u8>, Vec<i64>, Vec<u8>) {
     let (mut ro, mut refs, mut ao, mut alts) = (vec![0i64], Vec::new(), vec![0i64], Vec::new());
     for (r, a) in pairs {
