@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -116,7 +117,10 @@ lk_status cut_chunks(const lk_pairhmm_batch *b, int n_dev, int chunks_per_device
     }
     const int64_t want = std::max<int64_t>(1, (int64_t)n_dev * chunks_per_device);
     // a chunk below ~1e9 cells (a quarter of a millisecond of one B200) costs more in launch latency than it balances
-    const int64_t target = std::max<int64_t>((n_cells + want - 1) / want, 1000000000LL);
+    // (LK_POOL_MIN_CHUNK_CELLS: test switch, so that small batches exercise the chunk views too)
+    const char *env_floor = getenv("LK_POOL_MIN_CHUNK_CELLS");
+    const int64_t floor_cells = env_floor ? std::max<int64_t>(1, atoll(env_floor)) : 1000000000LL;
+    const int64_t target = std::max<int64_t>((n_cells + want - 1) / want, floor_cells);
     chunks.clear();
     int64_t acc = 0, g0 = 0;
     for (int64_t g = 0; g < G; g++) {

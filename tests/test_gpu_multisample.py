@@ -196,8 +196,16 @@ def test_pool_and_batcher_carry_samples():
     mk = lambda c: PairHMMLikelihoodCalculationEngine(c, 10, -4.5, PCRErrorModel.CONSERVATIVE, 18, False, 1.0, 0.02, True, False, False)
     with lk.Context(0) as ctx:
         exp_v, exp_keep = mk(ctx).compute_read_likelihoods(b, mapq)
+    import os
     with DevicePool() as pool:
         pv, pk = pool.compute_read_likelihoods(mk(None), b, mapq)
+        assert _same(pv, exp_v) and np.array_equal(pk, exp_keep)
+        # the same with the batch cut into ~4-region chunks, so that the chunk views re-base the sample arrays
+        os.environ["LK_POOL_MIN_CHUNK_CELLS"] = "150000000"
+        try:
+            pv, pk = pool.compute_read_likelihoods(mk(None), b, mapq)
+        finally:
+            del os.environ["LK_POOL_MIN_CHUNK_CELLS"]
         assert _same(pv, exp_v) and np.array_equal(pk, exp_keep)
         got = [None] * b.n_regions
         with RegionBatcher(pool, mk(None), max_regions=16, max_wait_us=5000) as bt:
