@@ -135,6 +135,9 @@ extern "C" {
     pub fn lk_set_tristate_correction(ctx: *mut lk_ctx, use_tristate: c_int) -> lk_status;
     pub fn lk_set_force_f64(ctx: *mut lk_ctx, force_f64: c_int) -> lk_status;
 
+    pub fn lk_host_register(ptr: *mut c_void, bytes: usize) -> lk_status;
+    pub fn lk_host_unregister(ptr: *mut c_void) -> lk_status;
+
     // ---- PairHMM
     pub fn lk_pairhmm_batch_dims(batch: *const lk_pairhmm_batch, n_pairs: *mut i64, n_cells: *mut i64) -> lk_status;
     pub fn lk_pairhmm_batch_host(ctx: *mut lk_ctx, batch: *const lk_pairhmm_batch, out: *mut f64, flags: *mut u8) -> lk_status;

@@ -77,6 +77,11 @@ lk_status lk_set_tristate_correction(lk_ctx *ctx, int use_tristate);
  * 1: every pair in f64 with the reference's own operation order (slow; for validation). */
 lk_status lk_set_force_f64(lk_ctx *ctx, int force_f64);
 
+/* Optional: page-lock memory the caller owns (input arenas, result arrays) so that the host-buffer entry points copy by
+ * asynchronous DMA (cudaHostRegister, portable across the devices of a pool).  Pageable memory works everywhere too. */
+lk_status lk_host_register(void *ptr, size_t bytes);
+lk_status lk_host_unregister(void *ptr);
+
 /* ---------------------------------------------------------------- PairHMM */
 
 /*

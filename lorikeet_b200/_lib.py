@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "lk_cigar_append_clipped_elements", "lk_read_start_on_reference_haplotype",
     "lk_batcher_create", "lk_batcher_destroy", "lk_batcher_submit", "lk_batcher_stats", "lk_batcher_submit_async",
     "lk_batcher_wait",
-    "lk_engine_normalize_and_filter_device", "lk_dangling_end_sw_batch", "lk_find_number_of_repetitions",
+    "lk_host_register", "lk_host_unregister", "lk_engine_normalize_and_filter_device", "lk_dangling_end_sw_batch", "lk_find_number_of_repetitions",
     "lk_pool_create", "lk_pool_destroy", "lk_pool_device_count", "lk_pool_ctx", "lk_pool_last_error",
     "lk_pool_set_tristate_correction", "lk_pool_pairhmm_batch_host", "lk_pool_compute_read_likelihoods", "lk_pool_batcher_create",
     "lk_resident_pairs", "lk_resident_cells", "lk_resident_launch_count", "lk_resident_last_fast_ms",
@@ -200,6 +200,10 @@ def load():
     L.lk_batcher_stats.argtypes = [vp, i64p, i64p]
     L.lk_engine_normalize_and_filter_device.restype = C.c_int
     L.lk_engine_normalize_and_filter_device.argtypes = [vp, ep, bp, i32p, f64p, f64p, u8p]
+    L.lk_host_register.restype = C.c_int
+    L.lk_host_register.argtypes = [vp, C.c_size_t]
+    L.lk_host_unregister.restype = C.c_int
+    L.lk_host_unregister.argtypes = [vp]
     L.lk_dangling_end_sw_batch.restype = C.c_int
     L.lk_dangling_end_sw_batch.argtypes = [vp, C.c_int64, i64p, u8p, i64p, u8p, C.POINTER(SwParams), C.c_int32, u32p, i32p]
     L.lk_find_number_of_repetitions.restype = C.c_int64

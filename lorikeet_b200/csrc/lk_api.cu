@@ -821,3 +821,19 @@ extern "C" lk_status lk_engine_normalize_and_filter_device(lk_ctx *ctx, const lk
     return done(LK_OK);
     LK_ABI_GUARD_END(return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory"), return lk_fail(ctx, LK_ERR_INVALID, "internal error"))
 }
+
+// Page-lock memory the CALLER owns (its read / haplotype arenas, its result arrays) so that the copies of the host-buffer entry
+// points are true asynchronous DMA instead of being staged through the driver's bounce buffer; portable across the devices of
+// a pool.  Optional: every entry point works with pageable memory too.
+extern "C" lk_status lk_host_register(void *ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return LK_ERR_INVALID;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return e == cudaErrorMemoryAllocation ? LK_ERR_NOMEM : LK_ERR_CUDA; }
+    return LK_OK;
+}
+extern "C" lk_status lk_host_unregister(void *ptr) {
+    if (!ptr) return LK_ERR_INVALID;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return LK_ERR_CUDA; }
+    return LK_OK;
+}

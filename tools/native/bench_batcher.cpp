@@ -2,7 +2,8 @@
 // lk_batcher (what Lorikeet's Rayon workers would do through the Rust binding, assembly_region_walker.rs:140-277),
 // next to the same regions handed to lk_engine_compute_read_likelihoods in one call.
 //   (built by lorikeet_b200/csrc/build.sh into tools/native/bench_batcher)
-//   tools/native/bench_batcher [regions=4000] [threads=32] [max_regions=512] [max_wait_us=200] [in_flight=1] [devices=1] [first_device=0]
+//   tools/native/bench_batcher [regions=4000] [threads=32] [max_regions=512] [max_wait_us=200] [in_flight=1] [devices=1] [first_device=0] [pinned=0]
+// pinned = 1: the caller's arenas and result arrays are page-locked with lk_host_register (what an integrator would do once)
 // in_flight > 1: every thread keeps that many regions queued through lk_batcher_submit_async / lk_batcher_wait
 // devices: GPUs in the lk_pool (0 = every visible one); ONE process drives them all.  The last line is JSON.
 #include <atomic>
@@ -28,6 +29,7 @@ int main(int argc, char **argv) {
     const int depth = argc > 5 ? std::max(1, atoi(argv[5])) : 1;
     const int n_dev_arg = argc > 6 ? atoi(argv[6]) : 1;
     const int first_dev = argc > 7 ? atoi(argv[7]) : 0;
+    const int pinned = argc > 8 ? atoi(argv[8]) : 0;
     lk_synth_params p;
     memset(&p, 0, sizeof p);
     p.seed_base = 0x4C4B0000; p.n_reads = 64; p.read_len = 150; p.n_haps = 16; p.hap_len = 300; p.min_edits = 1; p.max_edits = 4;
@@ -58,6 +60,15 @@ int main(int argc, char **argv) {
     lk_pairhmm_batch_dims(&all, &n_pairs, &n_cells);
     std::vector<double> direct(n_pairs), viab(n_pairs);
     std::vector<uint8_t> keep_d(R), keep_b(R);
+    if (pinned) {
+        int bad_pin = 0;
+        bad_pin += lk_host_register(rb.data(), rb.size()) != LK_OK; bad_pin += lk_host_register(rq.data(), rq.size()) != LK_OK;
+        bad_pin += lk_host_register(ri.data(), ri.size()) != LK_OK; bad_pin += lk_host_register(rd.data(), rd.size()) != LK_OK;
+        bad_pin += lk_host_register(hb.data(), hb.size()) != LK_OK; bad_pin += lk_host_register(mapq.data(), mapq.size()) != LK_OK;
+        bad_pin += lk_host_register(direct.data(), direct.size() * 8) != LK_OK; bad_pin += lk_host_register(viab.data(), viab.size() * 8) != LK_OK;
+        bad_pin += lk_host_register(keep_d.data(), keep_d.size()) != LK_OK; bad_pin += lk_host_register(keep_b.data(), keep_b.size()) != LK_OK;
+        if (bad_pin) { fprintf(stderr, "lk_host_register failed\n"); return 7; }
+    }
     // ---- one call ----
     double best = 1e30;
     for (int it = 0; it < 3; it++) {
@@ -122,8 +133,8 @@ int main(int argc, char **argv) {
     const bool same = pool_same && memcmp(single.data(), viab.data(), n_pairs * 8) == 0 && memcmp(keep_s.data(), keep_b.data(), R) == 0;
     printf("pooled one-call and batcher results %s the single-device one-call results\n", same ? "are bit-identical to" : "DIFFER from");
     printf("{\"devices\": %d, \"threads\": %d, \"in_flight\": %d, \"regions\": %lld, \"one_call_gcups\": %.1f, \"batcher_gcups\": %.1f, "
-           "\"regions_per_launch\": %.1f, \"bit_identical\": %s}\n", n_dev, T, depth, (long long)G, one_call_gcups, n_cells / best / 1e6,
-           (double)nr / (double)nb, same ? "true" : "false");
+           "\"regions_per_launch\": %.1f, \"bit_identical\": %s, \"pinned\": %d}\n", n_dev, T, depth, (long long)G, one_call_gcups, n_cells / best / 1e6,
+           (double)nr / (double)nb, same ? "true" : "false", pinned);
     lk_batcher_destroy(bt);
     lk_pool_destroy(pool);
     return same ? 0 : 6;
