@@ -122,6 +122,7 @@ extern "C" void lk_destroy(lk_ctx *ctx) {
     for (int i = 0; i < LK_PIPE_DEPTH; i++)
         if (ctx->sw_ws[i]) { lk_resident_free(nullptr, ctx->sw_ws[i]); ctx->sw_ws[i] = nullptr; }
     ctx->d_qerr_f.release(); ctx->d_qerr_d.release(); ctx->d_m2m.release();
+    ctx->d_ba_blocks.release(); ctx->d_ba_prio.release(); ctx->d_ba_best.release(); ctx->d_ba_info.release();
     delete ctx;
 }
 

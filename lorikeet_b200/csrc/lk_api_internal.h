@@ -42,6 +42,7 @@ struct lk_ctx {
     int64_t split_target_tasks = 0;  // launches with fewer warp tasks are cut along the haplotype axis (build_prep)
     int32_t last_launch_count = 0;
     DevBuf d_qerr_f, d_qerr_d, d_m2m;
+    DevBuf d_ba_blocks, d_ba_prio, d_ba_best, d_ba_info;  // grow-only buffers of the device best-allele search (N2)
     // reusable workspaces of lk_pairhmm_batch_host's chunk pipeline, one per stream.  Three, not two: chunk i+2's H2D then
     // waits on chunk i-1 (long finished) instead of chunk i, whose small f64 pass can be held back behind chunk i+1's
     // main kernel and would otherwise delay the copy, and with it chunk i+2's kernels, past the end of chunk i+1.

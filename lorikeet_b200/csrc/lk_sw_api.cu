@@ -328,8 +328,8 @@ lk_status lk_best_alleles_device(lk_ctx *ctx, const double *d_values, const lk::
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "cudaSetDevice");
     cudaStream_t st = ctx->stream[0];
-    DevBuf d_blocks, d_prio, d_best, d_info;
-    auto done = [&](lk_status r) { d_blocks.release(); d_prio.release(); d_best.release(); d_info.release(); return r; };
+    DevBuf &d_blocks = ctx->d_ba_blocks, &d_prio = ctx->d_ba_prio, &d_best = ctx->d_ba_best, &d_info = ctx->d_ba_info;  // kept across calls
+    auto done = [&](lk_status r) { return r; };
     if ((e = d_blocks.reserve((size_t)n_blocks * sizeof(lk::BestAlleleBlock))) != cudaSuccess || (e = d_prio.reserve((size_t)std::max<int64_t>(n_priorities, 1) * 4)) != cudaSuccess ||
         (e = d_best.reserve((size_t)n_reads * 4)) != cudaSuccess || (e = d_info.reserve((size_t)n_reads)) != cudaSuccess)
         return done(lk_cuda_fail(ctx, e, "alloc best-allele buffers"));

@@ -232,3 +232,45 @@ def test_pool_and_batcher_carry_samples():
             else:
                 assert _same(v, exp_v[pbase:pbase + n]) and np.array_equal(keep, exp_keep[r0:r1])
             pbase += n
+
+
+def test_engine_to_realign_chain_keeps_the_matrices_on_the_device():
+    """N2 as a resident chain: lk_engine_compute_read_likelihoods leaves `values` in HBM, lk_realign_reads_batch picks the best
+    haplotype of every surviving read with a kernel on those matrices and aligns the read to it; same answers as the chain
+    through host memory."""
+    import torch
+    from lorikeet_b200 import synth
+    from lorikeet_b200.engine import PairHMMLikelihoodCalculationEngine, PCRErrorModel
+    b = synth.pairhmm_regions(20, first_region=555, pcr_model=0, base_quality_score_threshold=0)
+    rng = np.random.default_rng(2)
+    for r in rng.choice(b.n_reads, 30, replace=False):  # some reads the filter removes
+        a, e = int(b.read_off[r]), int(b.read_off[r + 1])
+        b.read_bases[a:e] = rng.choice(np.frombuffer(b"ACGT", np.uint8), e - a)
+    mapq = np.full(b.n_reads, 60, np.uint8)
+    with lk.Context(0) as ctx:
+        eng = PairHMMLikelihoodCalculationEngine(ctx, 10, -4.5, PCRErrorModel.CONSERVATIVE, 18, False, 1.0, 0.02, True, False, False)
+        host_values, keep = eng.compute_read_likelihoods(b, mapq)
+        dev_values = torch.empty(b.n_pairs, dtype=torch.float64, device="cuda")
+        _, keep2 = eng.compute_read_likelihoods(b, mapq, values_device_ptr=dev_values.data_ptr())
+        assert np.array_equal(keep, keep2) and _same(dev_values.cpu().numpy(), host_values)
+        # realignment inputs: per region the surviving reads first (the order of the compacted matrix columns), every haplotype
+        # aligned to the region's first one with an all-match CIGAR of its own length
+        haps, hcig, hstart, reads, rcig, n_ev, rstart = [], [], [], [], [], [], []
+        for g in range(b.n_regions):
+            for h in range(int(b.region_hap_start[g]), int(b.region_hap_start[g + 1])):
+                seq = b.hap_bases[int(b.hap_off[h]):int(b.hap_off[h + 1])]
+                haps.append(seq); hcig.append("%dM" % len(seq)); hstart.append(0)
+            r0, r1 = int(b.region_read_start[g]), int(b.region_read_start[g + 1])
+            order = [r for r in range(r0, r1) if keep[r]] + [r for r in range(r0, r1) if not keep[r]]
+            for r in order:
+                seq = b.read_bases[int(b.read_off[r]):int(b.read_off[r + 1])]
+                reads.append(seq); rcig.append("%dM" % len(seq))
+            n_ev.append(int(keep[r0:r1].sum())); rstart.append(1000 * (g + 1))
+        common = dict(hap_seqs=haps, hap_cigars=hcig, hap_start_wrt_ref=hstart, read_seqs=reads, read_cigars=rcig, reference_start=rstart,
+                      region_n_evidence=n_ev)
+        via_host = lk.RealignBatch(b.region_read_start, b.region_hap_start, host_values, **common)
+        via_dev = lk.RealignBatch(b.region_read_start, b.region_hap_start, None, values_device_ptr=dev_values.data_ptr(), **common)
+        hb, hi, hc, hp = ctx.realign_reads_batch(via_host)
+        db, di, dc, dp = ctx.realign_reads_batch(via_dev)
+    assert np.array_equal(hb, db) and np.array_equal(hi, di) and hc == dc and np.array_equal(hp, dp)
+    assert (hb >= 0).sum() == int(keep.sum()) and (hb < 0).sum() == int((keep == 0).sum())
