@@ -202,8 +202,8 @@ def run_extras(ctx, args, peak_fp32):
 
 # figures read from the committed ncu capture of the SW kernel (never measured inside the bench)
 SW_NCU = {"instr_per_cell": 17.9, "dram_bytes_per_cell": 0.80,
-          "source": "profiles/r02_sw_kernel_k17_metrics.txt (20 000 cfg4 pairs: 9.67e10 thread instructions, 3.07 GB written + "
-                    "1.28 GB read over 5.408e9 cells)"}
+          "source": "profiles/r02_sw_kernel_k17_metrics_v2.txt (20 000 cfg4 pairs: 9.70e10 thread instructions in 3.36e9 warp "
+                    "instructions, 3.05 GB written + 1.25 GB read over 5.408e9 cells)"}
 
 
 def run_reference(args, rank):

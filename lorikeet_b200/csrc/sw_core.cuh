@@ -219,9 +219,20 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
     // best cell of the last column (scan top->bottom with >=, :301-307)
     int32_t col_max = (int32_t)(-2147483647 - 1);
     int col_p1 = 0;
+    // Bottom alignment (the strategies that search the bottom row, SoftClip / Ignore): the rows are shifted down so that the
+    // matrix's LAST row is always register K-1 of lane 31 of the last band -- its value is then the `h_last` the step hands
+    // on anyway, instead of a register picked by a run-time index.  The pad_top rows this leaves above row 1 are VIRTUAL rows
+    // with weight 0 against every column: they reproduce the top row exactly (H = max(0 + 0, open, open) = 0 for open < 0) and
+    // hand row 1 a vertical-gap state of `open` instead of i32::MIN/2, which row 1 cannot tell apart as long as extend < 0
+    // (max(0 + open, open + extend) = open = max(0 + open, MIN/2 + extend), gap opened either way).  The traceback never enters
+    // them (it stops at row 0).
+    // Only when it costs at most two extra lanes of skew (a reference that nearly fills its 32 x K rows, e.g. 520 of 544): a short
+    // reference would pay more in additional wavefront steps than the picked register costs.
+    const bool bottom_align = need_bottom && use_table && wo < 0 && we < 0 && (n_bands * BAND - n) < 2 * K;
+    const int pad_top = bottom_align ? n_bands * BAND - n : 0;
 
     for (int band = 0; band < n_bands; band++) {
-        const int row0 = band * BAND;  // rows row0+1 .. row0+rows (1-based)
+        const int row0 = band * BAND - pad_top;  // rows row0+1 .. row0+rows (1-based matrix rows; <= 0: virtual rows above row 1)
         const int rows = (n - row0 < BAND) ? (n - row0) : BAND;
         const int lanes = (rows + K - 1) / K;
         uint32_t rb[K];
@@ -229,7 +240,7 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const int i = row0 + lane * K + k + 1;  // 1-based matrix row
-            rb[k] = (i <= n) ? (uint32_t)ref[i - 1] : 0x100u;
+            rb[k] = (i >= 1 && i <= n) ? (uint32_t)ref[i - 1] : (i < 1 ? 0x200u : 0x100u);  // 0x200: virtual row, 0x100: row past the reference
             H[k] = edge_gaps ? (wo + (i - 1) * we) : 0;  // sw[i][0]
             E[k] = SW_LOW_INIT;                           // best_gap_h[i]
         }
@@ -238,13 +249,14 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
 #pragma unroll
         for (int k = 0; k < KQ * 4; k++) {
             const int cls_of_row = (k < K) ? sw_byte_class(rb[k < K ? k : 0]) : SW_N_CLASSES;
+            const bool virt = (k < K) && rb[k < K ? k : 0] == 0x200u;  // a virtual row scores 0 against every column
 #pragma unroll
-            for (int c = 0; c < SW_N_CLASSES; c++) wtab[((c * KQ + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = (cls_of_row == c) ? wm : wx;
+            for (int c = 0; c < SW_N_CLASSES; c++) wtab[((c * KQ + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = virt ? 0 : ((cls_of_row == c) ? wm : wx);
         }
         w.sync();
         // column 0 of the row above this lane's strip
-        const int i_above = row0 + lane * K;  // matrix row index of the row above (0 = top row)
-        const int32_t hd0 = (i_above == 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
+        const int i_above = row0 + lane * K;  // matrix row index of the row above (<= 0: the top row or a virtual row, both 0 in column 0)
+        const int32_t hd0 = (i_above <= 0) ? 0 : (edge_gaps ? (wo + (i_above - 1) * we) : 0);
         int32_t Hd = hd0;
         // (Hu, Fu) = the row above at this lane's column of the coming step.  Lane 0's comes from the matrix top row (band 0:
         // sw[0][c] = 0, or open + (c-1) extend for the edge-gap strategies, :146-179) or from the previous band's last row.
@@ -328,11 +340,11 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
 #pragma unroll
                     for (int k = 0; k < K; k++) {
                         const int i = row0 + lane * K + k + 1;
-                        if (i <= n && H[k] >= col_max) { col_max = H[k]; col_p1 = i; }
+                        if (i >= 1 && i <= n && H[k] >= col_max) { col_max = H[k]; col_p1 = i; }
                     }
                 }
                 // the matrix's bottom row goes to scratch, one value per column; its summary (:316-329) is taken after the fill
-                if (keeps_bottom) botH[c] = sw_pick<K>(H, bottom_k);
+                if (keeps_bottom) botH[c] = bottom_align ? h_last : sw_pick<K>(H, bottom_k);
                 if (writes_bnd) { bndH[c] = h_last; bndF[c] = f_last; }
             }
             // hand the strip's last row to the next lane; keep this step's "up" as next step's diagonal
@@ -408,7 +420,8 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
     // ---- traceback (:335-442), warp-cooperative: 32 cells of a run are fetched per round trip -----
     // nibble of matrix cell (i, j), 1-based: bits 0-1 move (0 diagonal, 1 horizontal, 2 vertical), bit 2 ho, bit 3 vo
     auto nibble = [&](int i, int j) -> uint32_t {
-        const int band = (i - 1) / BAND, r = (i - 1) % BAND, ln = r / K, k = r % K;
+        const int ii = i - 1 + pad_top;  // position among the rows the bands cover (virtual rows first)
+        const int band = ii / BAND, r = ii % BAND, ln = r / K, k = r % K;
         const uint32_t *bb = bt + (int64_t)band * band_words;
         const int64_t el = (int64_t)(j + ln) * 32 + ln;  // the cell was written at step j + ln by lane ln
         uint32_t pd, pr, ho, vo;
