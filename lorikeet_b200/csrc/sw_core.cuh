@@ -36,6 +36,12 @@
 #define LK_HD inline
 #endif
 
+#ifndef LK_SW_LEAN_UNROLL
+#define LK_SW_LEAN_UNROLL 1
+#endif
+#define LK_SW_PRAGMA_(x) _Pragma(#x)
+#define LK_SW_PRAGMA(x) LK_SW_PRAGMA_(x)
+
 namespace lk {
 
 enum : int { SW_SOFTCLIP = 0, SW_INDEL = 1, SW_LEADING_INDEL = 2, SW_IGNORE = 3 };
@@ -366,8 +372,12 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
         for (;;) {  // generic start-up, lean middle, generic tail (one copy of the generic loop in the code)
             for (; s <= gen_end; ++s) step(s, SwGenericTag(), band == 0);
             if (gen_end == n_steps) break;
-            if (band == 0) { for (; s <= s_lean_end; ++s) step(s, SwLeanTag(), true); }
-            else { for (; s <= s_lean_end; ++s) step(s, SwLeanTag(), false); }
+            if (band == 0) {
+LK_SW_PRAGMA(unroll LK_SW_LEAN_UNROLL)
+                for (; s <= s_lean_end; ++s) step(s, SwLeanTag(), true);
+            } else {
+                for (; s <= s_lean_end; ++s) step(s, SwLeanTag(), false);
+            }
             gen_end = n_steps;
         }
         w.sync();
