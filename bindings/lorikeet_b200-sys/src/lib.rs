@@ -149,6 +149,7 @@ extern "C" {
     pub fn lk_resident_cells(res: *const lk_resident) -> i64;
     pub fn lk_resident_launch_count(res: *const lk_resident) -> i32;
     pub fn lk_resident_last_fast_ms(res: *const lk_resident) -> f32;
+    pub fn lk_resident_sw_packed_pairs(res: *const lk_resident) -> i64;
     pub fn lk_resident_out_device_ptr(res: *const lk_resident) -> *mut c_void;
     pub fn lk_debug_last_launch_count(ctx: *const lk_ctx) -> i32;
     pub fn lk_measure_fp32_fma_tflops(ctx: *mut lk_ctx, duration_ms: f64, tflops: *mut f64) -> lk_status;

@@ -149,6 +149,8 @@ float lk_resident_last_fast_ms(const lk_resident *res);       /* device time of 
                                                                  TIMED run (kernel_ms != NULL): fp32 wavefront + band */
 void *lk_resident_out_device_ptr(const lk_resident *res);     /* device address of the f64 result block [n_pairs], so
                                                                  the results can be handed to a collective in place   */
+int64_t lk_resident_sw_packed_pairs(const lk_resident *res);  /* SW pairs of the last run that the packed two-pairs-per-warp
+                                                                 kernel took (-1: not an SW batch)                      */
 int32_t lk_debug_last_launch_count(const lk_ctx *ctx);        /* kernels launched by the last host-buffer call on ctx */
 /* FFMA-only microbenchmark on the context's device for `duration_ms`: the measured fp32 roofline denominator. */
 lk_status lk_measure_fp32_fma_tflops(lk_ctx *ctx, double duration_ms, double *tflops);

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "lk_host_register", "lk_host_unregister", "lk_engine_normalize_and_filter_device", "lk_dangling_end_sw_batch", "lk_find_number_of_repetitions",
     "lk_pool_create", "lk_pool_destroy", "lk_pool_device_count", "lk_pool_ctx", "lk_pool_last_error",
     "lk_pool_set_tristate_correction", "lk_pool_pairhmm_batch_host", "lk_pool_compute_read_likelihoods", "lk_pool_batcher_create",
-    "lk_resident_pairs", "lk_resident_cells", "lk_resident_launch_count", "lk_resident_last_fast_ms",
+    "lk_resident_pairs", "lk_resident_cells", "lk_resident_launch_count", "lk_resident_last_fast_ms", "lk_resident_sw_packed_pairs",
     "lk_resident_out_device_ptr", "lk_debug_last_launch_count", "lk_measure_fp32_fma_tflops",
 ]
 
@@ -234,6 +234,8 @@ def load():
     L.lk_resident_cells.argtypes = [vp]
     L.lk_resident_pairs.restype = C.c_int64
     L.lk_resident_pairs.argtypes = [vp]
+    L.lk_resident_sw_packed_pairs.restype = C.c_int64
+    L.lk_resident_sw_packed_pairs.argtypes = [vp]
     L.lk_resident_last_fast_ms.restype = C.c_float
     L.lk_resident_last_fast_ms.argtypes = [vp]
     L.lk_resident_out_device_ptr.restype = C.c_void_p

@@ -316,6 +316,11 @@ class ResidentSw:
         self.ctx._check(self.ctx._L.lk_sw_run_resident(self.ctx._h, self._r, C.byref(ms)))
         return ms.value
 
+    @property
+    def packed_pairs(self):
+        """Pairs of the last run() that the packed two-pairs-per-warp kernel took."""
+        return int(self.ctx._L.lk_resident_sw_packed_pairs(self._r))
+
     def download(self):
         ops = np.zeros((self.n, self.max_ops), dtype=np.uint32)
         n_ops = np.zeros(self.n, dtype=np.int32)

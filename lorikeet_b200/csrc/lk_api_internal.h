@@ -82,11 +82,11 @@ struct lk_resident {
     int64_t n_blocks = 0;   // (region, sample) blocks of the staged chunk
     bool sampled = false;   // several samples per region: block_region is in use
     // ---- Smith-Waterman ----
-    struct SwLaunch { int K; int32_t first; int32_t count; bool clamp; };
+    struct SwLaunch { int K; int32_t first; int32_t count; bool clamp; bool duo; };
     std::vector<SwLaunch> sw_launches;
     int sw_blocks = 0;
     int64_t sw_scratch_words = 0;
-    int64_t sw_n_pairs = 0, sw_cells = 0;
+    int64_t sw_n_pairs = 0, sw_cells = 0, sw_packed_pairs = 0;
     int32_t sw_max_ops = 0, sw_strategy = 0;
     lk_sw_params sw_params = { 0, 0, 0, 0 };
     int64_t sw_ref_byte0 = 0, sw_alt_byte0 = 0;  // first arena bytes staged: device base pointers are biased by these

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -16,7 +17,7 @@
 #include "host_parallel.h"
 #include "lk_api_internal.h"
 #include "lk_internal.h"
-#include "sw_core.cuh"
+#include "sw16_core.cuh"
 
 using namespace lk;
 
@@ -24,6 +25,12 @@ namespace {
 
 const int kSwKs[] = { LK_SW_KS };
 constexpr int kNumSwKs = (int)(sizeof(kSwKs) / sizeof(kSwKs[0]));
+
+// LK_SW_DUO=0 in the environment keeps every pair on the one-pair-per-warp kernel (A/B measurements)
+bool sw_duo_enabled() {
+    static const bool on = [] { const char *e = getenv("LK_SW_DUO"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 int sw_choose_k(int n) {
     for (int i = 0; i < kNumSwKs; i++)
@@ -56,8 +63,8 @@ lk_status sw_stage_range(lk_ctx *ctx, lk_resident *R, int64_t p0, int64_t p1, co
     order.resize((size_t)n_pairs);
     std::vector<uint8_t> cls((size_t)n_pairs);
     std::vector<int64_t> cells((size_t)n_pairs);
-    int64_t max_words = 64, nm_max[kNumSwKs], cells_max[kNumSwKs], count[kNumSwKs];
-    for (int ki = 0; ki < kNumSwKs; ki++) { nm_max[ki] = 0; cells_max[ki] = 1; count[ki] = 0; }
+    int64_t max_words = 64, nm_max[kNumSwKs], cells_max[kNumSwKs], count[kNumSwKs], m_max[kNumSwKs];
+    for (int ki = 0; ki < kNumSwKs; ki++) { nm_max[ki] = 0; cells_max[ki] = 1; count[ki] = 0; m_max[ki] = 0; }
     R->sw_cells = 0;
     for (int64_t i = 0; i < n_pairs; i++) {
         const int64_t p = p0 + i;
@@ -71,25 +78,46 @@ lk_status sw_stage_range(lk_ctx *ctx, lk_resident *R, int64_t p0, int64_t p1, co
         count[ki]++;
         nm_max[ki] = std::max<int64_t>(nm_max[ki], (int64_t)n + m);
         cells_max[ki] = std::max(cells_max[ki], cells[(size_t)i]);
+        m_max[ki] = std::max<int64_t>(m_max[ki], m);
         if (n > 0 && m > 0) max_words = std::max(max_words, sw_scratch_words(n, m, K));
     }
     // order array: one contiguous run per K class, longest pairs first inside a class (better tail balance of the
-    // persistent grid).  A counting sort over 256 size buckets: the order only has to be roughly descending.
+    // persistent grid), by a counting sort: the order only has to be roughly descending.  A class the packed kernel serves
+    // (sw16_core.cuh: two consecutive pairs of the order per warp when their references have the same length) is ordered by
+    // reference length first, then by alternate length in 16 steps, so that neighbours qualify; the others by cell count
+    // in 256 steps.
     {
-        constexpr int NB = 256;
-        std::vector<int32_t> slot((size_t)kNumSwKs * NB + 1, 0);
+        const bool duo_weights = sw_duo_enabled() && sw16_weights_ok(params->match_value, params->mismatch_penalty,
+                                                                     params->gap_open_penalty, params->gap_extend_penalty);
+        bool duo[kNumSwKs];
+        int nb[kNumSwKs], first_bucket[kNumSwKs + 1];
+        first_bucket[0] = 0;
+        for (int ki = 0; ki < kNumSwKs; ki++) {
+            const bool clamp = !sw_clamp_inactive(nm_max[ki], params->match_value, params->mismatch_penalty, params->gap_open_penalty, params->gap_extend_penalty);
+            duo[ki] = duo_weights && !clamp && sw_duo_has_k(kSwKs[ki]) && count[ki] > 1;
+            nb[ki] = duo[ki] ? (32 * kSwKs[ki] + 2) * 16 : 256;
+            first_bucket[ki + 1] = first_bucket[ki] + nb[ki];
+        }
+        std::vector<int32_t> slot((size_t)first_bucket[kNumSwKs] + 1, 0);
         auto bucket = [&](int64_t i) {
             const int ki = cls[(size_t)i];
-            return ki * NB + (NB - 1 - (int)(cells[(size_t)i] * (NB - 1) / cells_max[ki]));
+            if (!duo[ki]) return first_bucket[ki] + (255 - (int)(cells[(size_t)i] * 255 / cells_max[ki]));
+            const int64_t p = p0 + i;
+            const int64_t n = ref_off[p + 1] - ref_off[p], m = alt_off[p + 1] - alt_off[p];
+            const int rows = 32 * kSwKs[ki];
+            const int n_slot = n > rows ? 0 : (int)(rows + 1 - n);  // banded references first, then longest first
+            return first_bucket[ki] + n_slot * 16 + (15 - (int)(m * 15 / std::max<int64_t>(1, m_max[ki])));
         };
         for (int64_t i = 0; i < n_pairs; i++) slot[(size_t)bucket(i) + 1]++;
         for (size_t k = 1; k < slot.size(); k++) slot[k] += slot[k - 1];
         for (int64_t i = 0; i < n_pairs; i++) order[(size_t)slot[(size_t)bucket(i)]++] = (int32_t)i;
         int32_t first = 0;
         for (int ki = 0; ki < kNumSwKs; ki++) {
-            if (count[ki] > 0)
-                R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)count[ki],
-                        !sw_clamp_inactive(nm_max[ki], params->match_value, params->mismatch_penalty, params->gap_open_penalty, params->gap_extend_penalty) });
+            if (count[ki] > 0) {
+                const bool clamp = !sw_clamp_inactive(nm_max[ki], params->match_value, params->mismatch_penalty, params->gap_open_penalty, params->gap_extend_penalty);
+                R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)count[ki], clamp, duo[ki] });
+                if (duo[ki]) max_words = std::max(max_words, sw16_scratch_words((int)m_max[ki], kSwKs[ki]));
+            }
             first += (int32_t)count[ki];
         }
     }
@@ -158,13 +186,17 @@ lk_status sw_enqueue(lk_ctx *ctx, lk_resident *R, cudaStream_t st) {
     A.strategy = R->sw_strategy; A.max_ops = R->sw_max_ops;
     A.cigar_ops = (uint32_t *)R->sw_ops.p; A.n_ops = (int32_t *)R->sw_nops.p; A.offsets = (int32_t *)R->sw_offsets.p;
     A.scratch = (uint32_t *)R->sw_bt.p; A.scratch_words = R->sw_scratch_words;
+    A.one = 1u; A.mone = 0xffffffffu; A.two16 = 65536u;
+    A.packed_count = (int32_t *)R->counters.p + 15;
     if ((e = cudaMemsetAsync(R->counters.p, 0, 64, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "memset");
     int li = 0;
     for (const auto &L : R->sw_launches) {
         A.order = (const int32_t *)R->sw_order.p + L.first;
         A.n_order = L.count;
         A.cursor = (int32_t *)R->counters.p + li++;
-        if ((e = launch_sw(L.K, L.clamp, A, R->sw_blocks, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
+        // the packed kernel runs three blocks per SM (its two weight tables per warp), the one-pair kernel four
+        e = L.duo ? launch_sw_duo(L.K, A, std::min(R->sw_blocks, ctx->n_sm * 3), st) : launch_sw(L.K, L.clamp, A, R->sw_blocks, st);
+        if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
         R->launch_count++;
     }
     return LK_OK;
@@ -186,6 +218,8 @@ lk_status sw_run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
     }
     if (rs != LK_OK) return rs;
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "sw kernels");
+    int32_t packed = 0;
+    if (cudaMemcpy(&packed, (const int32_t *)R->counters.p + 15, 4, cudaMemcpyDeviceToHost) == cudaSuccess) R->sw_packed_pairs = packed;
     return LK_OK;
 }
 
@@ -204,6 +238,8 @@ lk_status sw_download_locked(lk_ctx *ctx, lk_resident *R, uint32_t *cigar_ops, i
 }
 
 }  // namespace
+
+extern "C" int64_t lk_resident_sw_packed_pairs(const lk_resident *r) { return (r && r->kind == 1) ? r->sw_packed_pairs : -1; }
 
 extern "C" lk_status lk_sw_upload(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
                                   const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,

@@ -55,6 +55,7 @@ struct SwArgs {
     const int32_t *order;      // pair ids this launch works through (dynamic, via cursor)
     int32_t n_order;
     int32_t *cursor;
+    int32_t *packed_count;     // pairs the packed kernel (sw16_core.cuh) took, for introspection
     int32_t w_match, w_mismatch, w_open, w_extend;
     int32_t strategy;
     int32_t max_ops;
@@ -63,6 +64,7 @@ struct SwArgs {
     int32_t *offsets;          // [pair]
     uint32_t *scratch;         // per-warp backtrack + band boundary
     int64_t scratch_words;     // words per warp
+    uint32_t one, mone, two16; // 1, 0xffffffff and 65536 as run-time values (sw16_core.cuh: adds issued as IMADs)
 };
 
 LK_DEV uint32_t sw_cigar_el(uint32_t op, int32_t len) { return ((uint32_t)len << 4) | op; }
@@ -156,9 +158,10 @@ LK_HD int64_t sw_scratch_words(int n, int m, int K) {
 struct SwLeanTag { static constexpr bool value = true; };
 struct SwGenericTag { static constexpr bool value = false; };
 
-template <class Wp, int K, bool CLAMP = true>
-LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, int32_t *wtab) {
-    constexpr int KQ = (K + 3) / 4;
+// Empty inputs (:65-68) and the exact-substring shortcut, AlignmentUtils::last_index_of (alignment_utils.rs:717-735): true
+// when the pair is finished without a matrix.
+template <class Wp>
+LK_DEV bool sw_prologue(Wp &w, const SwArgs &A, int pair) {
     const int lane = w.lane();
     const uint8_t *ref = A.refs + A.ref_off[pair];
     const uint8_t *alt = A.alts + A.alt_off[pair];
@@ -167,11 +170,9 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
     uint32_t *ops_out = A.cigar_ops + (int64_t)pair * A.max_ops;
     if (n <= 0 || m <= 0) {  // :65-68 assert
         if (lane == 0) { A.n_ops[pair] = -1; A.offsets[pair] = 0; }
-        return;
+        return true;
     }
     const int strategy = A.strategy;
-
-    // ---- exact-substring shortcut, AlignmentUtils::last_index_of (alignment_utils.rs:717-735) ----
     if ((strategy == SW_SOFTCLIP || strategy == SW_IGNORE) && m <= n) {
         int found = -1;
         for (int base = n - m; base >= 0 && found < 0; base -= 32) {
@@ -191,9 +192,155 @@ LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, i
                 else { ops_out[0] = sw_cigar_el(CIG_M, m); A.n_ops[pair] = 1; }
                 A.offsets[pair] = found;
             }
-            return;
+            return true;
         }
     }
+    return false;
+}
+
+// ---- bottom row summary (:316-329): the reference scans it left->right taking a cell if it is strictly better, or equal
+// and closer to the diagonal than the current best.  Its outcome depends only on the row maximum and on the maximal cell
+// closest to the diagonal (leftmost on ties): every lane scans its columns in that order, then the lanes are combined. ----
+template <class Wp>
+LK_DEV void sw_bottom_summary(Wp &w, const int32_t *botH, int n, int m, int32_t &bot_max, int &bot_j) {
+    const int lane = w.lane();
+    bot_max = (int32_t)(-2147483647 - 1);
+    bot_j = 0;
+    for (int c = lane + 1; c <= m; c += 32) {
+        const int32_t cur = botH[c];
+        const int dj = (n > c) ? (n - c) : (c - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
+        if (cur > bot_max || (cur == bot_max && dj < db)) { bot_max = cur; bot_j = c; }
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        const int32_t ov = w.shfl_xor(bot_max, d);
+        const int oj = w.shfl_xor(bot_j, d);
+        const int dj = (n > oj) ? (n - oj) : (oj - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
+        if (ov > bot_max || (ov == bot_max && (dj < db || (dj == db && oj < bot_j)))) { bot_max = ov; bot_j = oj; }
+    }
+}
+
+// ---- start cell (:288-333), traceback (:335-442) and output.  col_max / col_p1: every lane's best cell of the last column
+// among its own rows (scanned top -> bottom with >=); bot_max / bot_j: the bottom-row summary.  nibble(i, j) returns the
+// backtrack bits stored for matrix cell (i, j), 1-based: bits 0-1 move (0 diagonal, 1 horizontal, 2 vertical), bit 2 ho,
+// bit 3 vo.  FLAG_SHIFT = 0: ho / vo describe the gap ENDING at the cell they are stored with; 1: the horizontal gap of
+// (i, j + 1) / the vertical gap of (i + 1, j) (the packed kernel computes them one cell early). ----
+template <int FLAG_SHIFT, class Wp, class Nib>
+LK_DEV void sw_finish(Wp &w, const SwArgs &A, int pair, int n, int m, int32_t col_max, int col_p1, int32_t bot_max, int bot_j,
+                      Nib nibble) {
+    const int lane = w.lane();
+    const int strategy = A.strategy;
+    uint32_t *ops_out = A.cigar_ops + (int64_t)pair * A.max_ops;
+    // ---- start cell (:288-333) -------------------------------------------------------------------
+    // last column: every lane scanned its own rows with >=; combine so the LARGEST row among maxima wins
+    for (int d = 16; d >= 1; d >>= 1) {
+        const int32_t ov = w.shfl_xor(col_max, d);
+        const int op = w.shfl_xor(col_p1, d);
+        if (ov > col_max || (ov == col_max && op > col_p1)) { col_max = ov; col_p1 = op; }
+    }
+    int p1, p2;
+    int32_t segment_length = 0;
+    if (strategy == SW_INDEL) { p1 = n; p2 = m; }
+    else {
+        p1 = col_p1; p2 = m;
+        if (strategy != SW_LEADING_INDEL) {
+            // The reference scans the bottom row left->right taking a cell if it is strictly better, or equal and
+            // closer to the diagonal than the current best.  Its outcome depends only on the row maximum and on the
+            // maximal cell closest to the diagonal (leftmost on ties), which is what (bot_max, bot_j) track.
+            const int d_best = (p1 > p2) ? (p1 - p2) : (p2 - p1);
+            const int d_bot = (n > bot_j) ? (n - bot_j) : (bot_j - n);
+            if (bot_max > col_max || (bot_max == col_max && d_bot < d_best)) {
+                p1 = n; p2 = bot_j;
+                segment_length = m - bot_j;
+            }
+        }
+    }
+
+    // ---- traceback (:335-442), warp-cooperative: 32 cells of a run are fetched per round trip -----
+    int n_out = 0;
+    bool overflow = false;
+    auto push = [&](uint32_t el) {
+        if (n_out < A.max_ops) { if (lane == 0) ops_out[n_out] = el; }
+        else overflow = true;
+        n_out++;
+    };
+    if (segment_length > 0 && strategy == SW_SOFTCLIP) { push(sw_cigar_el(CIG_S, segment_length)); segment_length = 0; }
+    int state = 0;  // 0 match, 1 insertion, 2 deletion
+    auto op_of = [](int st) -> uint32_t { return st == 0 ? CIG_M : (st == 1 ? CIG_I : CIG_D); };
+    for (;;) {
+        // how many consecutive diagonal moves start at (p1, p2)?
+        const int lim = (p1 < p2) ? p1 : p2;  // cells available along the diagonal
+        int run = 0;
+        uint32_t stop_nib = 0;
+        for (;;) {
+            const int t = run + lane;
+            uint32_t nb = 0xFFu;
+            if (t < lim) nb = nibble(p1 - t, p2 - t);
+            const unsigned nd = w.ballot(t >= lim || (nb & 3u) != 0u);
+            if (nd == 0) { run += 32; continue; }
+            const int f = w.ffs(nd) - 1;
+            run += f;
+            stop_nib = w.shfl(nb, f);
+            break;
+        }
+        if (run > 0) {  // `run` diagonal steps
+            if (state == 0) segment_length += run;
+            else { if (segment_length > 0) push(sw_cigar_el(op_of(state), segment_length)); segment_length = run; state = 0; }
+            p1 -= run; p2 -= run;
+            if (p1 <= 0 || p2 <= 0) break;
+        }
+        // (p1, p2) holds a gap move; recover its length = distance back to the cell where the gap was opened
+        const uint32_t mv = stop_nib & 3u;
+        int glen = 0;
+        for (;;) {
+            const int t = glen + lane;
+            bool opened;
+            if (mv == 1u) { opened = (p2 - t <= 1) ? true : ((nibble(p1, p2 - t - FLAG_SHIFT) & 4u) != 0u); }
+            else { opened = (p1 - t <= 1) ? true : ((nibble(p1 - t - FLAG_SHIFT, p2) & 8u) != 0u); }
+            const unsigned b = w.ballot(opened);
+            if (b == 0) { glen += 32; continue; }
+            glen += w.ffs(b);  // inclusive
+            break;
+        }
+        const int new_state = (mv == 1u) ? 1 : 2;
+        if (new_state == 1) p2 -= glen; else p1 -= glen;
+        if (new_state == state) segment_length += glen;
+        else { if (segment_length > 0) push(sw_cigar_el(op_of(state), segment_length)); segment_length = glen; state = new_state; }
+        if (p1 <= 0 || p2 <= 0) break;
+    }
+    int32_t alignment_offset;
+    if (strategy == SW_SOFTCLIP) {          // :413-419
+        push(sw_cigar_el(op_of(state), segment_length));
+        if (p2 > 0) push(sw_cigar_el(CIG_S, p2));
+        alignment_offset = p1;
+    } else if (strategy == SW_IGNORE) {     // :420-423
+        push(sw_cigar_el(op_of(state), segment_length + p2));
+        alignment_offset = p1 - p2;
+    } else {                                // :424-436
+        push(sw_cigar_el(op_of(state), segment_length));
+        if (p1 > 0) push(sw_cigar_el(CIG_D, p1));
+        else if (p2 > 0) push(sw_cigar_el(CIG_I, p2));
+        alignment_offset = 0;
+    }
+    w.sync();
+    if (lane == 0) {
+        if (overflow) A.n_ops[pair] = -2;
+        else {
+            for (int a = 0, b = n_out - 1; a < b; a++, b--) { const uint32_t t = ops_out[a]; ops_out[a] = ops_out[b]; ops_out[b] = t; }  // :440
+            A.n_ops[pair] = n_out;
+        }
+        A.offsets[pair] = alignment_offset;
+    }
+}
+
+template <class Wp, int K, bool CLAMP = true>
+LK_DEV void sw_dp_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, int32_t *wtab) {
+    constexpr int KQ = (K + 3) / 4;
+    const int lane = w.lane();
+    const uint8_t *ref = A.refs + A.ref_off[pair];
+    const uint8_t *alt = A.alts + A.alt_off[pair];
+    const int n = (int)(A.ref_off[pair + 1] - A.ref_off[pair]);
+    const int m = (int)(A.alt_off[pair + 1] - A.alt_off[pair]);
+    const int strategy = A.strategy;
 
     // ---- fill -----------------------------------------------------------------------------------
     const int32_t wm = A.w_match, wx = A.w_mismatch, wo = A.w_open, we = A.w_extend;
@@ -383,51 +530,10 @@ LK_SW_PRAGMA(unroll LK_SW_LEAN_UNROLL)
         w.sync();
     }
 
-    // ---- bottom row summary (:316-329): the reference scans it left->right taking a cell if it is strictly better, or equal
-    // and closer to the diagonal than the current best.  Its outcome depends only on the row maximum and on the maximal cell
-    // closest to the diagonal (leftmost on ties): every lane scans its columns in that order, then the lanes are combined. ----
     int32_t bot_max = (int32_t)(-2147483647 - 1);
     int bot_j = 0;
-    if (need_bottom) {
-        for (int c = lane + 1; c <= m; c += 32) {
-            const int32_t cur = botH[c];
-            const int dj = (n > c) ? (n - c) : (c - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
-            if (cur > bot_max || (cur == bot_max && dj < db)) { bot_max = cur; bot_j = c; }
-        }
-        for (int d = 16; d >= 1; d >>= 1) {
-            const int32_t ov = w.shfl_xor(bot_max, d);
-            const int oj = w.shfl_xor(bot_j, d);
-            const int dj = (n > oj) ? (n - oj) : (oj - n), db = (n > bot_j) ? (n - bot_j) : (bot_j - n);
-            if (ov > bot_max || (ov == bot_max && (dj < db || (dj == db && oj < bot_j)))) { bot_max = ov; bot_j = oj; }
-        }
-    }
+    if (need_bottom) sw_bottom_summary(w, botH, n, m, bot_max, bot_j);
 
-    // ---- start cell (:288-333) -------------------------------------------------------------------
-    // last column: every lane scanned its own rows with >=; combine so the LARGEST row among maxima wins
-    for (int d = 16; d >= 1; d >>= 1) {
-        const int32_t ov = w.shfl_xor(col_max, d);
-        const int op = w.shfl_xor(col_p1, d);
-        if (ov > col_max || (ov == col_max && op > col_p1)) { col_max = ov; col_p1 = op; }
-    }
-    int p1, p2;
-    int32_t segment_length = 0;
-    if (strategy == SW_INDEL) { p1 = n; p2 = m; }
-    else {
-        p1 = col_p1; p2 = m;
-        if (strategy != SW_LEADING_INDEL) {
-            // The reference scans the bottom row left->right taking a cell if it is strictly better, or equal and
-            // closer to the diagonal than the current best.  Its outcome depends only on the row maximum and on the
-            // maximal cell closest to the diagonal (leftmost on ties), which is what (bot_max, bot_j) track.
-            const int d_best = (p1 > p2) ? (p1 - p2) : (p2 - p1);
-            const int d_bot = (n > bot_j) ? (n - bot_j) : (bot_j - n);
-            if (bot_max > col_max || (bot_max == col_max && d_bot < d_best)) {
-                p1 = n; p2 = bot_j;
-                segment_length = m - bot_j;
-            }
-        }
-    }
-
-    // ---- traceback (:335-442), warp-cooperative: 32 cells of a run are fetched per round trip -----
     // nibble of matrix cell (i, j), 1-based: bits 0-1 move (0 diagonal, 1 horizontal, 2 vertical), bit 2 ho, bit 3 vo
     auto nibble = [&](int i, int j) -> uint32_t {
         const int ii = i - 1 + pad_top;  // position among the rows the bands cover (virtual rows first)
@@ -448,80 +554,13 @@ LK_SW_PRAGMA(unroll LK_SW_LEAN_UNROLL)
         const uint32_t mv = pd ? (pr ? 2u : 1u) : 0u;
         return mv | (ho << 2) | (vo << 3);
     };
-    int n_out = 0;
-    bool overflow = false;
-    auto push = [&](uint32_t el) {
-        if (n_out < A.max_ops) { if (lane == 0) ops_out[n_out] = el; }
-        else overflow = true;
-        n_out++;
-    };
-    if (segment_length > 0 && strategy == SW_SOFTCLIP) { push(sw_cigar_el(CIG_S, segment_length)); segment_length = 0; }
-    int state = 0;  // 0 match, 1 insertion, 2 deletion
-    auto op_of = [](int st) -> uint32_t { return st == 0 ? CIG_M : (st == 1 ? CIG_I : CIG_D); };
-    for (;;) {
-        // how many consecutive diagonal moves start at (p1, p2)?
-        const int lim = (p1 < p2) ? p1 : p2;  // cells available along the diagonal
-        int run = 0;
-        uint32_t stop_nib = 0;
-        for (;;) {
-            const int t = run + lane;
-            uint32_t nb = 0xFFu;
-            if (t < lim) nb = nibble(p1 - t, p2 - t);
-            const unsigned nd = w.ballot(t >= lim || (nb & 3u) != 0u);
-            if (nd == 0) { run += 32; continue; }
-            const int f = w.ffs(nd) - 1;
-            run += f;
-            stop_nib = w.shfl(nb, f);
-            break;
-        }
-        if (run > 0) {  // `run` diagonal steps
-            if (state == 0) segment_length += run;
-            else { if (segment_length > 0) push(sw_cigar_el(op_of(state), segment_length)); segment_length = run; state = 0; }
-            p1 -= run; p2 -= run;
-            if (p1 <= 0 || p2 <= 0) break;
-        }
-        // (p1, p2) holds a gap move; recover its length = distance back to the cell where the gap was opened
-        const uint32_t mv = stop_nib & 3u;
-        int glen = 0;
-        for (;;) {
-            const int t = glen + lane;
-            bool opened;
-            if (mv == 1u) { opened = (p2 - t <= 1) ? true : ((nibble(p1, p2 - t) & 4u) != 0u); }
-            else { opened = (p1 - t <= 1) ? true : ((nibble(p1 - t, p2) & 8u) != 0u); }
-            const unsigned b = w.ballot(opened);
-            if (b == 0) { glen += 32; continue; }
-            glen += w.ffs(b);  // inclusive
-            break;
-        }
-        const int new_state = (mv == 1u) ? 1 : 2;
-        if (new_state == 1) p2 -= glen; else p1 -= glen;
-        if (new_state == state) segment_length += glen;
-        else { if (segment_length > 0) push(sw_cigar_el(op_of(state), segment_length)); segment_length = glen; state = new_state; }
-        if (p1 <= 0 || p2 <= 0) break;
-    }
-    int32_t alignment_offset;
-    if (strategy == SW_SOFTCLIP) {          // :413-419
-        push(sw_cigar_el(op_of(state), segment_length));
-        if (p2 > 0) push(sw_cigar_el(CIG_S, p2));
-        alignment_offset = p1;
-    } else if (strategy == SW_IGNORE) {     // :420-423
-        push(sw_cigar_el(op_of(state), segment_length + p2));
-        alignment_offset = p1 - p2;
-    } else {                                // :424-436
-        push(sw_cigar_el(op_of(state), segment_length));
-        if (p1 > 0) push(sw_cigar_el(CIG_D, p1));
-        else if (p2 > 0) push(sw_cigar_el(CIG_I, p2));
-        alignment_offset = 0;
-    }
-    w.sync();
-    if (lane == 0) {
-        if (overflow) A.n_ops[pair] = -2;
-        else {
-            for (int a = 0, b = n_out - 1; a < b; a++, b--) { const uint32_t t = ops_out[a]; ops_out[a] = ops_out[b]; ops_out[b] = t; }  // :440
-            A.n_ops[pair] = n_out;
-        }
-        A.offsets[pair] = alignment_offset;
-    }
+    sw_finish<0>(w, A, pair, n, m, col_max, col_p1, bot_max, bot_j, nibble);
+}
+
+template <class Wp, int K, bool CLAMP = true>
+LK_DEV void sw_align_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, int32_t *wtab) {
+    if (sw_prologue(w, A, pair)) return;
+    sw_dp_pair<Wp, K, CLAMP>(w, A, pair, scratch, wtab);
 }
 
 }  // namespace lk

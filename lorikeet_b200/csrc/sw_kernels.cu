@@ -3,7 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "lk_internal.h"
-#include "sw_core.cuh"
+#include "sw16_core.cuh"
 
 namespace lk {
 
@@ -28,6 +28,10 @@ struct SwDevWarp {
         const int4 v = *reinterpret_cast<const int4 *>(src);
         dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
+    __device__ __forceinline__ void lds4u(uint32_t *dst, const uint32_t *src) const {
+        const uint4 v = *reinterpret_cast<const uint4 *>(src);
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
     __device__ __forceinline__ void load4(const uint32_t *p, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) const {
         const uint4 v = *reinterpret_cast<const uint4 *>(p);
         a = v.x; b = v.y; c = v.z; d = v.w;
@@ -49,6 +53,62 @@ __global__ void __launch_bounds__(LK_SW_THREADS) sw_kernel(const SwArgs A) {
         sw_align_pair<SwDevWarp, K, CLAMP>(w, A, A.order[idx], scratch, wtab);
         __syncwarp();
     }
+}
+
+// Two pairs per warp (sw16_core.cuh) wherever two consecutive pairs of the order qualify, one at a time (sw_core.cuh)
+// otherwise.  Three blocks per SM: the two packed weight tables of a warp take 17 KB of shared memory.
+template <int K> struct SwDuoSmem { static constexpr int words = Sw16Table<K>::words > SwTable<K>::words ? Sw16Table<K>::words : SwTable<K>::words; };
+
+template <int K>
+__global__ void __launch_bounds__(LK_SW_THREADS, 3) sw_duo_kernel(const SwArgs A) {
+    extern __shared__ int4 lk_sw_smem[];
+    int32_t *wtab = reinterpret_cast<int32_t *>(lk_sw_smem) + (threadIdx.x >> 5) * SwDuoSmem<K>::words;
+    SwDevWarp w;
+    const int warp_in_grid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    uint32_t *scratch = A.scratch + (int64_t)warp_in_grid * A.scratch_words;
+    for (;;) {
+        int idx = 0;
+        if (w.lane() == 0) idx = atomicAdd(A.cursor, 2);
+        idx = w.shfl(idx, 0);
+        if (idx >= A.n_order) break;
+        const int pa = A.order[idx], pb = (idx + 1 < A.n_order) ? A.order[idx + 1] : -1;
+        const bool done_a = sw_prologue(w, A, pa), done_b = (pb < 0) || sw_prologue(w, A, pb);
+        if (!done_a && !done_b) {
+            const int64_t na = A.ref_off[pa + 1] - A.ref_off[pa], nb = A.ref_off[pb + 1] - A.ref_off[pb];
+            if (na == nb && na <= 32 * K && sw16_align_duo<SwDevWarp, K>(w, A, pa, pb, scratch, wtab)) {
+                if (w.lane() == 0) atomicAdd(A.packed_count, 2);
+                __syncwarp();
+                continue;
+            }
+        }
+        if (!done_a) { sw_dp_pair<SwDevWarp, K, false>(w, A, pa, scratch, wtab); __syncwarp(); }
+        if (!done_b) { sw_dp_pair<SwDevWarp, K, false>(w, A, pb, scratch, wtab); __syncwarp(); }
+    }
+}
+
+template <int K>
+static cudaError_t launch_sw_duo_k(const SwArgs &A, int n_blocks, cudaStream_t st) {
+    const int smem = (LK_SW_THREADS / 32) * SwDuoSmem<K>::words * (int)sizeof(int32_t);
+    static bool configured_on[64] = { false };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool &configured = configured_on[dev & 63];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(sw_duo_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    sw_duo_kernel<K><<<n_blocks, LK_SW_THREADS, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+// K classes the packed kernel is built for (references of 257..544 rows); the launcher falls back to launch_sw otherwise
+bool sw_duo_has_k(int K) { return K == 16 || K == 17; }
+cudaError_t launch_sw_duo(int K, const SwArgs &A, int n_blocks, cudaStream_t st) {
+    if (A.n_order == 0) return cudaSuccess;
+    if (K == 16) return launch_sw_duo_k<16>(A, n_blocks, st);
+    if (K == 17) return launch_sw_duo_k<17>(A, n_blocks, st);
+    return cudaErrorInvalidValue;
 }
 
 template <int K, bool CLAMP>

@@ -72,3 +72,31 @@ def sw_batch(ref_off, refs, alt_off, alts, params, strategy, max_ops=64, force_k
                          p(offs, _lib.i32p))
     assert rc == 0
     return ops, n_ops, offs
+
+
+def sw_duo_batch(ref_off, refs, alt_off, alts, params, strategy, max_ops=64, force_k=0):
+    """Consecutive pairs (2i, 2i+1) through the packed two-pairs-per-warp routine with sw_duo_kernel's dispatch; also returns
+    which pairs actually took the packed path."""
+    from oracle.lk_oracle import SW_STRATEGY
+    L = lib()
+    L.emul_sw_duo_batch.restype = C.c_int
+    L.emul_sw_duo_batch.argtypes = [C.c_int64, _lib.i64p, _lib.u8p, _lib.i64p, _lib.u8p, _lib.i32p, C.c_int, C.c_int, C.c_int,
+                                    _lib.u32p, _lib.i32p, _lib.i32p, _lib.u8p]
+    ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+    alt_off = np.ascontiguousarray(alt_off, dtype=np.int64)
+    refs = np.ascontiguousarray(refs, dtype=np.uint8)
+    alts = np.ascontiguousarray(alts, dtype=np.uint8)
+    n = len(ref_off) - 1
+    if isinstance(strategy, str):
+        strategy = SW_STRATEGY[strategy]
+    prm = np.asarray(params, dtype=np.int32)
+    ops = np.zeros((n, max_ops), dtype=np.uint32)
+    n_ops = np.zeros(n, dtype=np.int32)
+    offs = np.zeros(n, dtype=np.int32)
+    took = np.zeros(n, dtype=np.uint8)
+    p = lambda a, t: a.ctypes.data_as(t)
+    rc = L.emul_sw_duo_batch(n, p(ref_off, _lib.i64p), p(refs, _lib.u8p), p(alt_off, _lib.i64p), p(alts, _lib.u8p),
+                             p(prm, _lib.i32p), strategy, max_ops, force_k, p(ops, _lib.u32p), p(n_ops, _lib.i32p),
+                             p(offs, _lib.i32p), p(took, _lib.u8p))
+    assert rc == 0, rc
+    return ops, n_ops, offs, took

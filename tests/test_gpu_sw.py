@@ -165,3 +165,59 @@ def test_bytes_outside_acgtn_and_clamped_form(ctx):
     for params, strategy in ((SC.NEW_SW_PARAMETERS, "SoftClip"), (SC.STANDARD_NGS, "InDel"), ([900000, -700000, -800000, -100000], "SoftClip"),
                              ([900000, -700000, -800000, -100000], "LeadingInDel")):
         _compare(ctx, pairs, params, strategy)
+
+
+def test_packed_two_pairs_per_warp_kernel(ctx):
+    """References of equal length in the 257..544-row classes go two to a warp (sw16_core.cuh, 16-bit difference arithmetic):
+    same (offset, CIGAR) as the oracle for every strategy and parameter set, alternates of different lengths inside a duo,
+    N pads as calculate_cigar adds them, and pairs that do not qualify (other lengths, bytes outside ACGTN, exact-substring
+    hits) mixed in."""
+    rng = np.random.default_rng(77)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    pad = np.frombuffer(b"N" * 10, np.uint8)
+
+    def mutate(ref, n_edits, max_indel):
+        alt = ref.copy()
+        for _ in range(n_edits):
+            p = int(rng.integers(5, len(alt) - 5))
+            t = rng.integers(0, 3)
+            if t == 0:
+                alt[p] = rng.choice(acgt)
+            elif t == 1:
+                alt = np.delete(alt, slice(p, p + int(rng.integers(1, max_indel + 1))))
+            else:
+                alt = np.insert(alt, p, rng.choice(acgt, int(rng.integers(1, max_indel + 1))))
+        return alt
+
+    pairs = []
+    for n in (260, 300, 411, 500, 512, 513, 520, 524, 544):
+        for _ in range(6):
+            ref = rng.choice(acgt, n - 20)
+            mode = int(rng.integers(0, 4))
+            alt = mutate(ref, int(rng.integers(1, 6)), 25)
+            if mode == 1:
+                alt = alt[int(rng.integers(1, 60)):]
+            if mode == 2:
+                alt = rng.choice(acgt, int(rng.integers(n // 2, n)))
+            pairs.append((np.concatenate([pad, ref, pad]), np.concatenate([pad, alt, pad])))
+    ref = rng.choice(acgt, 400)
+    pairs += [(ref, ref[20:380].copy()), (ref, mutate(ref, 3, 9)),                       # substring hit next to a real one
+              (ref, np.concatenate([mutate(ref, 2, 5), np.frombuffer(b"RY", np.uint8)])),  # bytes outside ACGTN
+              (ref, mutate(ref, 2, 5)), (rng.choice(acgt, 700), rng.choice(acgt, 650))]    # and a banded reference
+    for strategy in SC.STRATEGIES:
+        _compare(ctx, pairs, SC.NEW_SW_PARAMETERS, strategy, max_ops=512)
+    _compare(ctx, pairs, SC.STANDARD_NGS, "LeadingInDel", max_ops=512)
+    _compare(ctx, pairs, SC.ALIGNMENT_TO_BEST_HAPLOTYPE, "SoftClip", max_ops=512)
+    _compare(ctx, pairs, SC.ORIGINAL_DEFAULT, "InDel", max_ops=512)
+    # the packed kernel is what ran: all 54 equal-length pairs under InDel (no substring shortcut), minus odd leftovers
+    ro, refs, ao, alts = SC.pack(pairs)
+    r = ctx.sw_upload(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, "InDel", max_ops=512)
+    r.run()
+    assert r.packed_pairs >= 50, r.packed_pairs
+    # weights outside the packed kernel's range keep the one-pair kernel, with the same answers
+    big = [2000, -1500, -2600, -110]
+    _compare(ctx, pairs[:12], big, "SoftClip", max_ops=512)
+    r2 = ctx.sw_upload(ro, refs, ao, alts, big, "InDel", max_ops=512)
+    r2.run()
+    assert r2.packed_pairs == 0
+    r.free(); r2.free()

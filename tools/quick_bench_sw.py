@@ -1,4 +1,5 @@
 """Developer check: kernel-only GCUPS of the Smith-Waterman path on the cfg#4 generator."""
+import hashlib
 import os
 import sys
 import time
@@ -17,7 +18,10 @@ with lk.Context(0) as ctx:
         for _ in range(2):
             res.run()
         ms = min(res.run() for _ in range(5))
-        print("SW %s pairs=%d cells=%.3e best_ms=%.3f GCUPS=%.1f" % (strategy, n, res.n_cells, ms, res.n_cells / ms / 1e6), flush=True)
+        ops, n_ops, offs = res.download()
+        valid = np.arange(64)[None, :] < n_ops[:, None]
+        sha = hashlib.sha256(ops[valid].tobytes() + n_ops.tobytes() + offs.tobytes()).hexdigest()[:12]
+        print("SW %s pairs=%d cells=%.3e best_ms=%.3f GCUPS=%.1f packed_pairs=%d sha=%s" % (strategy, n, res.n_cells, ms, res.n_cells / ms / 1e6, res.packed_pairs, sha), flush=True)
         outs = (np.zeros((n, 64), np.uint32), np.zeros(n, np.int32), np.zeros(n, np.int32))
         for _ in range(3):
             t = time.time()
