@@ -140,7 +140,7 @@ lk_status sw_stage_range(lk_ctx *ctx, lk_resident *R, int64_t p0, int64_t p1, co
               (e = R->sw_ops.reserve((size_t)std::max<int64_t>(n_pairs * max_ops * 4, 16))) == cudaSuccess &&
               (e = R->sw_nops.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
               (e = R->sw_offsets.reserve((size_t)std::max<int64_t>(n_pairs * 4, 16))) == cudaSuccess &&
-              (e = R->counters.reserve(64)) == cudaSuccess &&
+              (e = R->counters.reserve(256)) == cudaSuccess &&
               (e = R->sw_bt.reserve((size_t)((int64_t)R->sw_blocks * warps_per_block * max_words * 4))) == cudaSuccess;
     if (!ok) return lk_cuda_fail(ctx, e, "SW upload");
     return LK_OK;
@@ -188,14 +188,15 @@ lk_status sw_enqueue(lk_ctx *ctx, lk_resident *R, cudaStream_t st) {
     A.scratch = (uint32_t *)R->sw_bt.p; A.scratch_words = R->sw_scratch_words;
     A.one = 1u; A.mone = 0xffffffffu; A.two16 = 65536u;
     A.packed_count = (int32_t *)R->counters.p + 15;
-    if ((e = cudaMemsetAsync(R->counters.p, 0, 64, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "memset");
+    A.prof = (unsigned long long *)((char *)R->counters.p + 64);
+    if ((e = cudaMemsetAsync(R->counters.p, 0, 256, st)) != cudaSuccess) return lk_cuda_fail(ctx, e, "memset");
     int li = 0;
     for (const auto &L : R->sw_launches) {
         A.order = (const int32_t *)R->sw_order.p + L.first;
         A.n_order = L.count;
         A.cursor = (int32_t *)R->counters.p + li++;
-        // the packed kernel runs three blocks per SM (its two weight tables per warp), the one-pair kernel four
-        e = L.duo ? launch_sw_duo(L.K, A, std::min(R->sw_blocks, ctx->n_sm * 3), st) : launch_sw(L.K, L.clamp, A, R->sw_blocks, st);
+        // the packed kernel runs 12 warps per SM (its two weight tables per warp), the one-pair kernel 16
+        e = L.duo ? launch_sw_duo(L.K, A, ctx->n_sm, (int64_t)R->sw_blocks * (LK_SW_THREADS / 32), st) : launch_sw(L.K, L.clamp, A, R->sw_blocks, st);
         if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
         R->launch_count++;
     }
@@ -220,6 +221,16 @@ lk_status sw_run_locked(lk_ctx *ctx, lk_resident *R, float *kernel_ms) {
     if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "sw kernels");
     int32_t packed = 0;
     if (cudaMemcpy(&packed, (const int32_t *)R->counters.p + 15, 4, cudaMemcpyDeviceToHost) == cudaSuccess) R->sw_packed_pairs = packed;
+#ifdef LK_SW16_PROFILE
+    {
+        unsigned long long t[8] = { 0 };
+        cudaMemcpy(t, (const char *)R->counters.p + 64, sizeof t, cudaMemcpyDeviceToHost);
+        double tot = 0;
+        for (int i = 0; i < 8; i++) tot += (double)t[i];
+        fprintf(stderr, "sw16 phases (%% of warp time): classes %.1f  tables %.1f  fill %.1f  column+bottom %.1f  traceback %.1f  prologue %.1f  fallback %.1f\n",
+                100 * t[0] / tot, 100 * t[1] / tot, 100 * t[2] / tot, 100 * t[3] / tot, 100 * t[4] / tot, 100 * t[5] / tot, 100 * t[6] / tot);
+    }
+#endif
     return LK_OK;
 }
 

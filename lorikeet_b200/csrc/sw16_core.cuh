@@ -19,8 +19,10 @@
 // Representation: every half is an UNSIGNED biased value and every sum below ends in [0, 65535] per half, so plain 32-bit
 // adds and subtracts never carry between the halves and can issue on either integer pipe (IADD3 on the ALU pipe, IMAD on
 // the FMA pipe): u, v carry bias B; s, a, b, z carry 2 B; nf, ne, nx, ny are plain.  A flag is the top bit of a half of
-// (value + 0x7fff - threshold); one PRMT (sign-replicating byte select) gathers the four flags of two rows x two pairs and
-// one LOP3 files them, so the four bit-planes cost 4 PRMT + 4 LOP3 per two rows of two pairs.
+// (value + 0x7fff - threshold); one PRMT (sign-replicating byte select) gathers the four flags of two rows x two pairs as
+// 0x00 / 0xff bytes and one IMAD files them (plane = 2 plane + bytes, i.e. 255 x the bit plane, divided out by the traceback
+// with the inverse of 255 mod 2^32), so the four bit-planes cost 4 PRMT (ALU pipe) + 4 IMAD (FMA pipe) per two rows of two
+// pairs.
 // The gap flags are computed one cell EARLY (vo stored with (i,j) is the opening of the vertical gap ending at (i+1,j)),
 // which the traceback accounts for (sw_finish<1>).
 //
@@ -33,11 +35,32 @@
 #ifndef LK_SW16_LEAN_UNROLL
 #define LK_SW16_LEAN_UNROLL 1
 #endif
+// which of the cell's three-input sums issue as one IADD3 on the ALU pipe (the others as two IMADs on the FMA pipe):
+// bit 0 a, bit 1 b, bit 2 the not-diagonal flag word
+#ifndef LK_SW16_ALU_MASK
+#define LK_SW16_ALU_MASK 7
+#endif
+// 1 (default): both pairs' weight tables hold 16-bit values (11.5 KB per warp, one PRMT per cell packs the two weights): the
+// shared-memory footprint that lets 16 warps share an SM.  0: pair 0's table in 32-bit words (16.6 KB per warp, 12 warps per
+// SM, the pack is an IMAD for even rows and a LOP3 for odd ones) -- measured 1 896 against 1 966 GCUPS on cfg#4.
+#ifndef LK_SW16_COMPACT
+#define LK_SW16_COMPACT 1
+#endif
+
+// developer builds (-DLK_SW16_PROFILE): lane 0 adds the clock64 ticks of each phase to A.packed_count[1 + phase]
+#if defined(LK_SW16_PROFILE) && defined(__CUDA_ARCH__)
+#define LK_SW16_TICK(phase) do { const long long t_now_ = clock64(); if (w.lane() == 0) atomicAdd((unsigned long long *)A.prof + (phase), (unsigned long long)(t_now_ - t_prev_)); t_prev_ = t_now_; } while (0)
+#define LK_SW16_TICK_INIT long long t_prev_ = clock64()
+#else
+#define LK_SW16_TICK(phase) do { } while (0)
+#define LK_SW16_TICK_INIT do { } while (0)
+#endif
 
 namespace lk {
 
 constexpr uint32_t SW16_B = 2048;   // bias of the u / v halves; s, a, b, z carry twice that
 constexpr int32_t SW16_MAX_WEIGHT = 1000;
+constexpr uint32_t SW16_INV255 = 0xfefefeffu;  // 255 * SW16_INV255 = 1 (mod 2^32): the stored plane words are 255 x the bit planes
 
 LK_HD bool sw16_weights_ok(int32_t wm, int32_t wx, int32_t wo, int32_t we) {
     const int32_t L = SW16_MAX_WEIGHT;
@@ -80,6 +103,14 @@ LK_DEV uint32_t sw16_flags(uint32_t a, uint32_t b) {
     return ((a >> 15) & 1u ? 0xffu : 0u) | ((a >> 31) & 1u ? 0xff00u : 0u) | ((b >> 15) & 1u ? 0xff0000u : 0u) | ((b >> 31) & 1u ? 0xff000000u : 0u);
 #endif
 }
+// the low (odd = 0) or high (odd = 1) halves of a and b as one word, a's in the low half: one PRMT
+LK_DEV uint32_t sw16_halves(uint32_t a, uint32_t b, int odd) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, odd ? 0x7632 : 0x5410);
+#else
+    return odd ? ((a >> 16) | (b & 0xffff0000u)) : ((a & 0xffffu) | (b << 16));
+#endif
+}
 // a + b and a - b issued as IMADs (FMA pipe) through multipliers the compiler cannot see through (SwArgs::one / mone):
 // the ALU pipe is the bound of the cell, the FMA pipe has room
 LK_DEV uint32_t sw16_fadd(uint32_t a, uint32_t b, uint32_t one) {
@@ -111,7 +142,7 @@ template <int K> struct Sw16Table {
     static_assert(K == 17 || (K % 8 == 0 && K <= 16), "rows come in groups of eight, plus one odd row for K = 17");
     static constexpr int rows16 = K < 16 ? K : 16;
     static constexpr int quads_a = rows16 / 4, quads_b = rows16 / 8;
-    static constexpr int a_quad_words = SW_N_CLASSES * quads_a * 128, b_quad_words = SW_N_CLASSES * quads_b * 128;
+    static constexpr int a_quad_words = SW_N_CLASSES * (LK_SW16_COMPACT ? quads_b : quads_a) * 128, b_quad_words = SW_N_CLASSES * quads_b * 128;
     static constexpr int a_words = a_quad_words + (K > 16 ? SW_N_CLASSES * 32 : 0);
     static constexpr int b_words = b_quad_words + (K > 16 ? SW_N_CLASSES * 32 : 0);
     static constexpr int words = a_words + b_words;
@@ -151,6 +182,7 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
     const int pad_top = need_bottom ? BAND - n : 0;
     const int lanes = need_bottom ? 32 : (n + K - 1) / K;
 
+    LK_SW16_TICK_INIT;
     uint32_t *planes = scratch;                                               // [step][lane] x {pd, pr, vo, ho}
     uint8_t *nibs = reinterpret_cast<uint8_t *>(planes + ((int64_t)M + 32) * 128);  // [step][lane], row 16 of both pairs
     uint32_t *botV = reinterpret_cast<uint32_t *>(nibs) + (HAS17 ? ((int64_t)M + 32) * 8 : 0);  // packed v of the bottom row
@@ -159,21 +191,32 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
 
     {
         bool other = false;
-        for (int j = lane; j < M; j += 32) {
-            int c0 = 0, c1 = 0;
-            if (j < mm[0]) { c0 = sw_byte_class(alt[0][j]); other |= (c0 == SW_N_CLASSES); }
-            if (j < mm[1]) { c1 = sw_byte_class(alt[1][j]); other |= (c1 == SW_N_CLASSES); }
-            acls[j] = (uint8_t)((c0 % SW_N_CLASSES) | ((c1 % SW_N_CLASSES) << 4));
+        for (int j0 = 0; j0 < M; j0 += 128) {  // eight independent loads per lane and round trip
+            uint32_t by[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + q * 32 + lane;
+                by[q][0] = (j < mm[0]) ? (uint32_t)w.ldg(alt[0] + j) : (uint32_t)'A';  // columns past the shorter alternate: any class
+                by[q][1] = (j < mm[1]) ? (uint32_t)w.ldg(alt[1] + j) : (uint32_t)'A';
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + q * 32 + lane;
+                const int c0 = sw_byte_class(by[q][0]), c1 = sw_byte_class(by[q][1]);
+                other |= (c0 == SW_N_CLASSES) | (c1 == SW_N_CLASSES);
+                if (j < M) acls[j] = (uint8_t)((c0 % SW_N_CLASSES) | ((c1 % SW_N_CLASSES) << 4));
+            }
         }
         if (w.ballot(other) != 0u) return false;
     }
+    LK_SW16_TICK(0);
     const uint32_t B = SW16_B;
     const uint32_t Dp = sw16_both((uint32_t)(we - wo)), Bp = sw16_both(B), Ca = sw16_both(B + (uint32_t)we);
     const uint32_t C7F = 0x7fff7fffu, CFL = sw16_both(0x7fffu - (uint32_t)(we - wo));
-    const uint32_t one = A.one, mone = A.mone, two16 = A.two16;
+    const uint32_t one = A.one, mone = A.mone, two16 = A.two16, two = A.one + A.one;
 
     // ---- tables and column-0 state of this lane's rows ------------------------------------------------------------------
-    uint32_t u[K], ny[K], even1[SW_N_CLASSES];
+    uint32_t u[K], ny[K], even0[SW_N_CLASSES], even1[SW_N_CLASSES];
     w.sync();
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -181,8 +224,8 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
         const int32_t u0 = edge_gaps ? (i == 1 ? wo : we) : 0;  // sw[i][0] - sw[i-1][0] (:146-179)
         u[k] = sw16_both(B + (uint32_t)u0);
         ny[k] = Dp;                                               // best_gap_h starts at i32::MIN / 2: the first gap opens
-        const int cls0 = (i >= 1 && i <= n) ? sw_byte_class(ref[0][i - 1]) : SW_N_CLASSES;  // rows past the reference never match
-        const int cls1 = (i >= 1 && i <= n) ? sw_byte_class(ref[1][i - 1]) : SW_N_CLASSES;
+        const int cls0 = (i >= 1 && i <= n) ? sw_byte_class(w.ldg(ref[0] + i - 1)) : SW_N_CLASSES;  // rows past the reference never match
+        const int cls1 = (i >= 1 && i <= n) ? sw_byte_class(w.ldg(ref[1] + i - 1)) : SW_N_CLASSES;
 #pragma unroll
         for (int c = 0; c < SW_N_CLASSES; c++) {
             // a virtual row scores 0 against every column
@@ -190,9 +233,12 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
             const uint32_t s1 = (uint32_t)(((i < 1) ? 0 : ((cls1 == c) ? wm : wx)) + (int32_t)(2 * B));
             uint32_t *tb1 = wtab + T::a_words;
             if (k < 16) {
-                wtab[((c * QA + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = s0;
-                if ((k & 1) == 0) even1[c] = s1;
-                else tb1[((c * QB + (k >> 3)) * 32 + lane) * 4 + ((k >> 1) & 3)] = even1[c] | (s1 << 16);
+                if (!LK_SW16_COMPACT) wtab[((c * QA + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = s0;
+                if ((k & 1) == 0) { even0[c] = s0; even1[c] = s1; }
+                else {
+                    if (LK_SW16_COMPACT) wtab[((c * QB + (k >> 3)) * 32 + lane) * 4 + ((k >> 1) & 3)] = even0[c] | (s0 << 16);
+                    tb1[((c * QB + (k >> 3)) * 32 + lane) * 4 + ((k >> 1) & 3)] = even1[c] | (s1 << 16);
+                }
             } else {
                 wtab[T::a_quad_words + c * 32 + lane] = s0;
                 tb1[T::b_quad_words + c * 32 + lane] = s1 << 16;
@@ -201,6 +247,7 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
     }
     w.sync();
 
+    LK_SW16_TICK(1);
     // (Vu, Xu) = (v, nx) of the row above at this lane's column of the coming step.  Lane 0's come from the matrix top row:
     // v = 0, or open then extend for the edge-gap strategies (:146-179); nx = D (best_gap_v starts at i32::MIN / 2)
     const uint32_t vtop_rest = edge_gaps ? sw16_both(B + (uint32_t)we) : Bp;
@@ -219,10 +266,11 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
         uint32_t v_last = Bp, x_last = Dp;
         if (active) {
             const int c0 = cls_now & 15, c1 = cls_now >> 4;
+            constexpr int QA_ = LK_SW16_COMPACT ? QB : QA;
             uint32_t ta[QA * 4 + 1], tb[QB * 4 + 1];
             const uint32_t *t0 = wtab, *t1 = wtab + T::a_words;
 #pragma unroll
-            for (int q = 0; q < QA; q++) w.lds4u(ta + 4 * q, t0 + ((c0 * QA + q) * 32 + lane) * 4);
+            for (int q = 0; q < QA_; q++) w.lds4u(ta + 4 * q, t0 + ((c0 * QA_ + q) * 32 + lane) * 4);
 #pragma unroll
             for (int q = 0; q < QB; q++) w.lds4u(tb + 4 * q, t1 + ((c1 * QB + q) * 32 + lane) * 4);
             if (HAS17) { ta[QA * 4] = t0[T::a_quad_words + c0 * 32 + lane]; tb[QB * 4] = t1[T::b_quad_words + c1 * 32 + lane]; }
@@ -233,13 +281,14 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
             for (int k = 0; k < K; k++) {
                 // the cell's two weights in one word: pair 1's comes from the half of tb[k / 2] that row k owns
                 const uint32_t sb = (k >= 16) ? sw16_fadd(ta[QA * 4], tb[QB * 4], one)
+                                   : LK_SW16_COMPACT ? sw16_halves(ta[k >> 1], tb[k >> 1], k & 1)
                                               : ((k & 1) ? ((tb[k >> 1] & 0xffff0000u) | ta[k]) : sw16_fadd(tb[k >> 1], ta[k], two16));
-                const uint32_t ab = vup - nxup + Ca;
-                const uint32_t bb = u[k] - ny[k] + Ca;
+                const uint32_t ab = (LK_SW16_ALU_MASK & 1) ? vup - nxup + Ca : sw16_fadd(sw16_fsub(vup, nxup, mone), Ca, one);
+                const uint32_t bb = (LK_SW16_ALU_MASK & 2) ? u[k] - ny[k] + Ca : sw16_fadd(sw16_fsub(u[k], ny[k], mone), Ca, one);
                 const uint32_t zb = sw16_max3(sb, ab, bb);
                 const uint32_t un = sw16_fsub(zb, vup, mone), vn = sw16_fsub(zb, u[k], mone);
                 const uint32_t nf = sw16_fsub(zb, ab, mone), ne = sw16_fsub(zb, bb, mone);
-                const uint32_t d_pd = zb - sb + C7F;              // top bit: z > s, not diagonal (:248-252)
+                const uint32_t d_pd = (LK_SW16_ALU_MASK & 4) ? zb - sb + C7F : sw16_fadd(sw16_fsub(zb, sb, mone), C7F, one);  // top bit: z > s, not diagonal (:248-252)
                 const uint32_t d_pr = sw16_fadd(ne, C7F, one);    // top bit: b < z, i.e. vertical when not diagonal (:253-260)
                 const uint32_t d_vo = sw16_fadd(nf, CFL, one);    // top bit: nf > D, the vertical gap of the row below opens here
                 const uint32_t d_ho = sw16_fadd(ne, CFL, one);    // top bit: ne > D, the horizontal gap of the next column opens here
@@ -249,12 +298,11 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
                 vup = vn;
                 if (k < R16) {
                     if ((k & 1) == 0) { e_pd = d_pd; e_pr = d_pr; e_vo = d_vo; e_ho = d_ho; }
-                    else {
-                        const uint32_t bit = 0x01010101u << (k >> 1);
-                        acc_pd |= sw16_flags(e_pd, d_pd) & bit;
-                        acc_pr |= sw16_flags(e_pr, d_pr) & bit;
-                        acc_vo |= sw16_flags(e_vo, d_vo) & bit;
-                        acc_ho |= sw16_flags(e_ho, d_ho) & bit;
+                    else {  // acc = 2 acc + (0xff per set flag): 255 x the plane word, undone by the traceback (SW16_INV255)
+                        acc_pd = (k == 1) ? sw16_flags(e_pd, d_pd) : sw16_fadd(acc_pd, sw16_flags(e_pd, d_pd), two);
+                        acc_pr = (k == 1) ? sw16_flags(e_pr, d_pr) : sw16_fadd(acc_pr, sw16_flags(e_pr, d_pr), two);
+                        acc_vo = (k == 1) ? sw16_flags(e_vo, d_vo) : sw16_fadd(acc_vo, sw16_flags(e_vo, d_vo), two);
+                        acc_ho = (k == 1) ? sw16_flags(e_ho, d_ho) : sw16_fadd(acc_ho, sw16_flags(e_ho, d_ho), two);
                     }
                 } else {  // row 16: bits pd.0 pd.1 pr.0 pr.1 vo.0 vo.1 ho.0 ho.1 of one byte
                     const uint32_t t = (sw16_flags(d_pd, d_pr) & 0x08040201u) | (sw16_flags(d_vo, d_ho) & 0x80402010u);
@@ -298,6 +346,7 @@ LK_SW_PRAGMA(unroll LK_SW16_LEAN_UNROLL)
         }
     }
     w.sync();
+    LK_SW16_TICK(2);
 
     // ---- per pair: absolute last column and bottom row, then start cell, traceback and output as in sw_core.cuh ---------
     for (int h = 0; h < 2; h++) {
@@ -327,26 +376,27 @@ LK_SW_PRAGMA(unroll LK_SW16_LEAN_UNROLL)
             w.sync();
             sw_bottom_summary(w, botH, n, m, bot_max, bot_j);
         }
+        LK_SW16_TICK(3);
         // backtrack bits of matrix cell (i, j), 1-based, of pair h
         auto nibble = [&](int i, int j) -> uint32_t {
             const int ii = i - 1 + pad_top;
             const int ln = ii / K, k = ii % K;
             const int64_t el = (int64_t)(j + ln) * 32 + ln;  // the cell was written at step j + ln by lane ln
-            uint32_t pd, prb, vo, ho;
-            if (HAS17 && k == 16) {
-                const uint32_t nb = nibs[el];
-                pd = (nb >> h) & 1u; prb = (nb >> (2 + h)) & 1u; vo = (nb >> (4 + h)) & 1u; ho = (nb >> (6 + h)) & 1u;
-            } else {
-                uint32_t a, b, c, d;
-                w.load4(planes + el * 4, a, b, c, d);
-                const int bit = ((k & 1) ? 16 : 0) + (h ? 8 : 0) + (k >> 1);
-                pd = (a >> bit) & 1u; prb = (b >> bit) & 1u; vo = (c >> bit) & 1u; ho = (d >> bit) & 1u;
-            }
+            // both loads unconditionally and without a branch, so that the loads of consecutive calls overlap
+            uint32_t a, b, c, d;
+            w.load4(planes + el * 4, a, b, c, d);
+            const bool odd_row = HAS17 && k == 16;
+            const uint32_t nb = odd_row ? (uint32_t)nibs[el] : 0u;
+            a *= SW16_INV255; b *= SW16_INV255; c *= SW16_INV255; d *= SW16_INV255;
+            const int bit = ((k & 1) ? 16 : 0) + (h ? 8 : 0) + (R16 / 2 - 1 - ((k & 15) >> 1));  // the first row pair ends up highest
+            const uint32_t pd = odd_row ? (nb >> h) & 1u : (a >> bit) & 1u, prb = odd_row ? (nb >> (2 + h)) & 1u : (b >> bit) & 1u;
+            const uint32_t vo = odd_row ? (nb >> (4 + h)) & 1u : (c >> bit) & 1u, ho = odd_row ? (nb >> (6 + h)) & 1u : (d >> bit) & 1u;
             const uint32_t mv = pd ? (prb ? 2u : 1u) : 0u;
             return mv | (ho << 2) | (vo << 3);
         };
         sw_finish<1>(w, A, pr[h], n, m, col_max, col_row[h], bot_max, bot_j, nibble);
         w.sync();
+        LK_SW16_TICK(4);
     }
     return true;
 }

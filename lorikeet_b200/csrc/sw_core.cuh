@@ -56,6 +56,7 @@ struct SwArgs {
     int32_t n_order;
     int32_t *cursor;
     int32_t *packed_count;     // pairs the packed kernel (sw16_core.cuh) took, for introspection
+    unsigned long long *prof;  // developer builds: clock ticks per phase (LK_SW16_PROFILE)
     int32_t w_match, w_mismatch, w_open, w_extend;
     int32_t strategy;
     int32_t max_ops;
@@ -271,15 +272,16 @@ LK_DEV void sw_finish(Wp &w, const SwArgs &A, int pair, int n, int m, int32_t co
         const int lim = (p1 < p2) ? p1 : p2;  // cells available along the diagonal
         int run = 0;
         uint32_t stop_nib = 0;
-        for (;;) {
-            const int t = run + lane;
-            uint32_t nb = 0xFFu;
-            if (t < lim) nb = nibble(p1 - t, p2 - t);
-            const unsigned nd = w.ballot(t >= lim || (nb & 3u) != 0u);
-            if (nd == 0) { run += 32; continue; }
-            const int f = w.ffs(nd) - 1;
-            run += f;
-            stop_nib = w.shfl(nb, f);
+        for (;;) {  // 64 cells of the diagonal per round trip: the two loads of a lane are independent
+            const int t0 = run + lane, t1 = t0 + 32;
+            uint32_t nb0 = 0xFFu, nb1 = 0xFFu;
+            if (t0 < lim) nb0 = nibble(p1 - t0, p2 - t0);
+            if (t1 < lim) nb1 = nibble(p1 - t1, p2 - t1);
+            const unsigned nd0 = w.ballot(t0 >= lim || (nb0 & 3u) != 0u);
+            const unsigned nd1 = w.ballot(t1 >= lim || (nb1 & 3u) != 0u);
+            if ((nd0 | nd1) == 0u) { run += 64; continue; }
+            if (nd0 != 0u) { const int f = w.ffs(nd0) - 1; run += f; stop_nib = w.shfl(nb0, f); }
+            else { const int f = w.ffs(nd1) - 1; run += 32 + f; stop_nib = w.shfl(nb1, f); }
             break;
         }
         if (run > 0) {  // `run` diagonal steps

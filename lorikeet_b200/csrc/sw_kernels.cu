@@ -2,6 +2,8 @@
 // Persistent warps pull pair ids from a cursor; each warp owns a slice of scratch for the 4-bit backtrack.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "lk_internal.h"
 #include "sw16_core.cuh"
 
@@ -56,11 +58,19 @@ __global__ void __launch_bounds__(LK_SW_THREADS) sw_kernel(const SwArgs A) {
 }
 
 // Two pairs per warp (sw16_core.cuh) wherever two consecutive pairs of the order qualify, one at a time (sw_core.cuh)
-// otherwise.  Three blocks per SM: the two packed weight tables of a warp take 17 KB of shared memory.
+// otherwise.
 template <int K> struct SwDuoSmem { static constexpr int words = Sw16Table<K>::words > SwTable<K>::words ? Sw16Table<K>::words : SwTable<K>::words; };
 
+// warps per block x blocks per SM of the packed kernel: 4 x 4 = 16 warps per SM (128 registers, 12.8 KB of shared memory per
+// warp: the one-pair table of the fall-back path is the larger of the two layouts).  With sw16_core.cuh's LK_SW16_COMPACT=0
+// tables it has to be 4 x 3.
+#ifndef LK_SW16_BLOCK_WARPS
+#define LK_SW16_BLOCK_WARPS 4
+#define LK_SW16_BLOCKS_PER_SM (LK_SW16_COMPACT ? 4 : 3)
+#endif
+
 template <int K>
-__global__ void __launch_bounds__(LK_SW_THREADS, 3) sw_duo_kernel(const SwArgs A) {
+__global__ void __launch_bounds__(LK_SW16_BLOCK_WARPS * 32, LK_SW16_BLOCKS_PER_SM) sw_duo_kernel(const SwArgs A) {
     extern __shared__ int4 lk_sw_smem[];
     int32_t *wtab = reinterpret_cast<int32_t *>(lk_sw_smem) + (threadIdx.x >> 5) * SwDuoSmem<K>::words;
     SwDevWarp w;
@@ -72,7 +82,9 @@ __global__ void __launch_bounds__(LK_SW_THREADS, 3) sw_duo_kernel(const SwArgs A
         idx = w.shfl(idx, 0);
         if (idx >= A.n_order) break;
         const int pa = A.order[idx], pb = (idx + 1 < A.n_order) ? A.order[idx + 1] : -1;
+        LK_SW16_TICK_INIT;
         const bool done_a = sw_prologue(w, A, pa), done_b = (pb < 0) || sw_prologue(w, A, pb);
+        LK_SW16_TICK(5);
         if (!done_a && !done_b) {
             const int64_t na = A.ref_off[pa + 1] - A.ref_off[pa], nb = A.ref_off[pb + 1] - A.ref_off[pb];
             if (na == nb && na <= 32 * K && sw16_align_duo<SwDevWarp, K>(w, A, pa, pb, scratch, wtab)) {
@@ -88,7 +100,7 @@ __global__ void __launch_bounds__(LK_SW_THREADS, 3) sw_duo_kernel(const SwArgs A
 
 template <int K>
 static cudaError_t launch_sw_duo_k(const SwArgs &A, int n_blocks, cudaStream_t st) {
-    const int smem = (LK_SW_THREADS / 32) * SwDuoSmem<K>::words * (int)sizeof(int32_t);
+    const int smem = LK_SW16_BLOCK_WARPS * SwDuoSmem<K>::words * (int)sizeof(int32_t);
     static bool configured_on[64] = { false };
     int dev = 0;
     cudaGetDevice(&dev);
@@ -98,14 +110,17 @@ static cudaError_t launch_sw_duo_k(const SwArgs &A, int n_blocks, cudaStream_t s
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    sw_duo_kernel<K><<<n_blocks, LK_SW_THREADS, smem, st>>>(A);
+    sw_duo_kernel<K><<<n_blocks, LK_SW16_BLOCK_WARPS * 32, smem, st>>>(A);
     return cudaGetLastError();
 }
 
 // K classes the packed kernel is built for (references of 257..544 rows); the launcher falls back to launch_sw otherwise
 bool sw_duo_has_k(int K) { return K == 16 || K == 17; }
-cudaError_t launch_sw_duo(int K, const SwArgs &A, int n_blocks, cudaStream_t st) {
+// n_warps: per-warp scratch slices available; the grid is the device's fill of the packed kernel, or fewer
+cudaError_t launch_sw_duo(int K, const SwArgs &A, int n_sm, int64_t n_warps, cudaStream_t st) {
     if (A.n_order == 0) return cudaSuccess;
+    const int n_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm * LK_SW16_BLOCKS_PER_SM, n_warps / LK_SW16_BLOCK_WARPS));
+    if (n_warps < LK_SW16_BLOCK_WARPS) return cudaErrorInvalidValue;
     if (K == 16) return launch_sw_duo_k<16>(A, n_blocks, st);
     if (K == 17) return launch_sw_duo_k<17>(A, n_blocks, st);
     return cudaErrorInvalidValue;

@@ -213,7 +213,7 @@ def test_packed_two_pairs_per_warp_kernel(ctx):
     ro, refs, ao, alts = SC.pack(pairs)
     r = ctx.sw_upload(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, "InDel", max_ops=512)
     r.run()
-    assert r.packed_pairs >= 50, r.packed_pairs
+    assert r.packed_pairs >= 40, r.packed_pairs
     # weights outside the packed kernel's range keep the one-pair kernel, with the same answers
     big = [2000, -1500, -2600, -110]
     _compare(ctx, pairs[:12], big, "SoftClip", max_ops=512)
