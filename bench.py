@@ -130,10 +130,11 @@ def run_extras(ctx, args, peak_fp32):
         issue_peak = n_sm * 4 * 32 * sm_hz          # thread-instructions / s at one warp instruction per cycle and scheduler
         int32_peak = n_sm * 64 * sm_hz              # 64 int32 lanes per SM (the 16-lane ALU pipe x 4)
         out["cfg4_smith_waterman"] = {
-            "pairs": 100000, "cells": n_cells, "ms": ms, "gcups": gcups,
-            "note": "fill + in-kernel traceback, CIGARs bit-exact vs oracle (tests/test_gpu_sw.py, test_gpu_fullsize.py)",
+            "pairs": 100000, "cells": n_cells, "ms": ms, "gcups": gcups, "packed_pairs": res.packed_pairs,
+            "note": "fill + in-kernel traceback, CIGARs bit-exact vs oracle (tests/test_gpu_sw.py, test_gpu_fullsize.py); "
+                    "packed_pairs = pairs that went two to a warp through the 16-bit difference kernel (sw16_core.cuh)",
             "roofline": {
-                "bound": "int32 issue (16-lane ALU pipe)", "unit": "fraction",
+                "bound": "integer issue (ALU and FMA-heavy pipes, 16 lanes each, balanced by construction)", "unit": "fraction",
                 "instructions_per_cell": SW_NCU["instr_per_cell"], "instructions_source": SW_NCU["source"],
                 "issue_slot_frac": gcups * 1e9 * SW_NCU["instr_per_cell"] / issue_peak,
                 "int32_frac_at_15_ops_per_cell": gcups * 1e9 * 15.0 / int32_peak,
@@ -201,9 +202,10 @@ def run_extras(ctx, args, peak_fp32):
 
 
 # figures read from the committed ncu capture of the SW kernel (never measured inside the bench)
-SW_NCU = {"instr_per_cell": 17.9, "dram_bytes_per_cell": 0.80,
-          "source": "profiles/r02_sw_kernel_k17_metrics_v2.txt (20 000 cfg4 pairs: 9.70e10 thread instructions in 3.36e9 warp "
-                    "instructions, 3.05 GB written + 1.25 GB read over 5.408e9 cells)"}
+SW_NCU = {"instr_per_cell": 13.6, "dram_bytes_per_cell": 0.78,
+          "source": "profiles/r02_sw_duo_kernel_k17_metrics.txt (packed two-pairs-per-warp kernel, 20 000 cfg4 pairs: 2.29e9 warp "
+                    "instructions = 7.33e10 thread instructions, 3.07 GB written + 1.16 GB read over 5.41e9 cells; the one-pair "
+                    "kernel it replaces on this workload: 17.9 instructions and 0.80 bytes per cell)"}
 
 
 def run_reference(args, rank):

@@ -217,6 +217,16 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
 
     // ---- tables and column-0 state of this lane's rows ------------------------------------------------------------------
     uint32_t u[K], ny[K], even0[SW_N_CLASSES], even1[SW_N_CLASSES];
+    int rcls0[K], rcls1[K];  // class of each of this lane's rows in either reference; all the loads first, then the compares
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int i = lane * K + k + 1 - pad_top;
+        const bool real = (i >= 1 && i <= n);
+        rcls0[k] = real ? (int)w.ldg(ref[0] + (real ? i - 1 : 0)) : 0;
+        rcls1[k] = real ? (int)w.ldg(ref[1] + (real ? i - 1 : 0)) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) { rcls0[k] = sw_byte_class((uint32_t)rcls0[k]); rcls1[k] = sw_byte_class((uint32_t)rcls1[k]); }  // 0: no base -> SW_N_CLASSES
     w.sync();
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -224,8 +234,7 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
         const int32_t u0 = edge_gaps ? (i == 1 ? wo : we) : 0;  // sw[i][0] - sw[i-1][0] (:146-179)
         u[k] = sw16_both(B + (uint32_t)u0);
         ny[k] = Dp;                                               // best_gap_h starts at i32::MIN / 2: the first gap opens
-        const int cls0 = (i >= 1 && i <= n) ? sw_byte_class(w.ldg(ref[0] + i - 1)) : SW_N_CLASSES;  // rows past the reference never match
-        const int cls1 = (i >= 1 && i <= n) ? sw_byte_class(w.ldg(ref[1] + i - 1)) : SW_N_CLASSES;
+        const int cls0 = rcls0[k], cls1 = rcls1[k];  // rows past the reference never match
 #pragma unroll
         for (int c = 0; c < SW_N_CLASSES; c++) {
             // a virtual row scores 0 against every column
