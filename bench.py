@@ -138,6 +138,8 @@ def run_extras(ctx, args, peak_fp32):
                 "instructions_per_cell": SW_NCU["instr_per_cell"], "instructions_source": SW_NCU["source"],
                 "issue_slot_frac": gcups * 1e9 * SW_NCU["instr_per_cell"] / issue_peak,
                 "int32_frac_at_15_ops_per_cell": gcups * 1e9 * 15.0 / int32_peak,
+                "int32_frac_note": "against 64 32-bit integer lanes per SM at the reference's 15 ops per cell; above 1 because the "
+                                   "packed kernel serves two cells with every 32-bit lane operation",
                 "dram_bytes_per_cell": SW_NCU["dram_bytes_per_cell"],
                 "hbm_frac": gcups * 1e9 * SW_NCU["dram_bytes_per_cell"] / ((measured_peaks() or {}).get("hbm_gbs", 6550.0) * 1e9),
                 "algorithmic_bytes_per_cell": float(refs.nbytes + alts.nbytes + 100000 * (64 * 4 + 8)) / n_cells,
