@@ -46,6 +46,14 @@
 #ifndef LK_SW16_COMPACT
 #define LK_SW16_COMPACT 1
 #endif
+// latency-bound set-up phases: how many of a lane's reference rows / alternate columns are loaded per round trip (all the
+// rows at once measured best: 2 011 GCUPS against 1 940 in batches of six)
+#ifndef LK_SW16_ROW_BATCH
+#define LK_SW16_ROW_BATCH 32
+#endif
+#ifndef LK_SW16_CLASS_BATCH
+#define LK_SW16_CLASS_BATCH 4
+#endif
 
 // developer builds (-DLK_SW16_PROFILE): lane 0 adds the clock64 ticks of each phase to A.packed_count[1 + phase]
 #if defined(LK_SW16_PROFILE) && defined(__CUDA_ARCH__)
@@ -191,16 +199,17 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
 
     {
         bool other = false;
-        for (int j0 = 0; j0 < M; j0 += 128) {  // eight independent loads per lane and round trip
-            uint32_t by[4][2];
+        constexpr int CB = LK_SW16_CLASS_BATCH;
+        for (int j0 = 0; j0 < M; j0 += 32 * CB) {  // 2 CB independent loads per lane and round trip
+            uint32_t by[CB][2];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < CB; q++) {
                 const int j = j0 + q * 32 + lane;
                 by[q][0] = (j < mm[0]) ? (uint32_t)w.ldg(alt[0] + j) : (uint32_t)'A';  // columns past the shorter alternate: any class
                 by[q][1] = (j < mm[1]) ? (uint32_t)w.ldg(alt[1] + j) : (uint32_t)'A';
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < CB; q++) {
                 const int j = j0 + q * 32 + lane;
                 const int c0 = sw_byte_class(by[q][0]), c1 = sw_byte_class(by[q][1]);
                 other |= (c0 == SW_N_CLASSES) | (c1 == SW_N_CLASSES);
@@ -217,40 +226,45 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
 
     // ---- tables and column-0 state of this lane's rows ------------------------------------------------------------------
     uint32_t u[K], ny[K], even0[SW_N_CLASSES], even1[SW_N_CLASSES];
-    int rcls0[K], rcls1[K];  // class of each of this lane's rows in either reference; all the loads first, then the compares
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        const int i = lane * K + k + 1 - pad_top;
-        const bool real = (i >= 1 && i <= n);
-        rcls0[k] = real ? (int)w.ldg(ref[0] + (real ? i - 1 : 0)) : 0;
-        rcls1[k] = real ? (int)w.ldg(ref[1] + (real ? i - 1 : 0)) : 0;
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++) { rcls0[k] = sw_byte_class((uint32_t)rcls0[k]); rcls1[k] = sw_byte_class((uint32_t)rcls1[k]); }  // 0: no base -> SW_N_CLASSES
     w.sync();
+    constexpr int RB = LK_SW16_ROW_BATCH < K ? LK_SW16_ROW_BATCH : K;  // rows per batch of reference loads: that many x 2 loads in flight, then their compares and table stores
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-        const int i = lane * K + k + 1 - pad_top;  // 1-based matrix row; < 1: virtual row
-        const int32_t u0 = edge_gaps ? (i == 1 ? wo : we) : 0;  // sw[i][0] - sw[i-1][0] (:146-179)
-        u[k] = sw16_both(B + (uint32_t)u0);
-        ny[k] = Dp;                                               // best_gap_h starts at i32::MIN / 2: the first gap opens
-        const int cls0 = rcls0[k], cls1 = rcls1[k];  // rows past the reference never match
+    for (int k0 = 0; k0 < K; k0 += RB) {
+        int rcls0[RB], rcls1[RB];  // class of a row in either reference (SW_N_CLASSES: no base, never matches)
 #pragma unroll
-        for (int c = 0; c < SW_N_CLASSES; c++) {
-            // a virtual row scores 0 against every column
-            const uint32_t s0 = (uint32_t)(((i < 1) ? 0 : ((cls0 == c) ? wm : wx)) + (int32_t)(2 * B));
-            const uint32_t s1 = (uint32_t)(((i < 1) ? 0 : ((cls1 == c) ? wm : wx)) + (int32_t)(2 * B));
-            uint32_t *tb1 = wtab + T::a_words;
-            if (k < 16) {
-                if (!LK_SW16_COMPACT) wtab[((c * QA + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = s0;
-                if ((k & 1) == 0) { even0[c] = s0; even1[c] = s1; }
-                else {
-                    if (LK_SW16_COMPACT) wtab[((c * QB + (k >> 3)) * 32 + lane) * 4 + ((k >> 1) & 3)] = even0[c] | (s0 << 16);
-                    tb1[((c * QB + (k >> 3)) * 32 + lane) * 4 + ((k >> 1) & 3)] = even1[c] | (s1 << 16);
+        for (int kk = 0; kk < RB; kk++) {
+            const int i = lane * K + k0 + kk + 1 - pad_top;
+            const bool real = (k0 + kk < K) && (i >= 1 && i <= n);
+            rcls0[kk] = real ? (int)w.ldg(ref[0] + (real ? i - 1 : 0)) : 0;
+            rcls1[kk] = real ? (int)w.ldg(ref[1] + (real ? i - 1 : 0)) : 0;
+        }
+#pragma unroll
+        for (int kk = 0; kk < RB; kk++) {
+            const int k = k0 + kk;
+            if (k < K) {
+                const int i = lane * K + k + 1 - pad_top;  // 1-based matrix row; < 1: virtual row
+                const int32_t u0 = edge_gaps ? (i == 1 ? wo : we) : 0;  // sw[i][0] - sw[i-1][0] (:146-179)
+                u[k < K ? k : 0] = sw16_both(B + (uint32_t)u0);
+                ny[k < K ? k : 0] = Dp;                                  // best_gap_h starts at i32::MIN / 2: the first gap opens
+                const int cls0 = sw_byte_class((uint32_t)rcls0[kk]), cls1 = sw_byte_class((uint32_t)rcls1[kk]);
+#pragma unroll
+                for (int c = 0; c < SW_N_CLASSES; c++) {
+                    // a virtual row scores 0 against every column
+                    const uint32_t s0 = (uint32_t)(((i < 1) ? 0 : ((cls0 == c) ? wm : wx)) + (int32_t)(2 * B));
+                    const uint32_t s1 = (uint32_t)(((i < 1) ? 0 : ((cls1 == c) ? wm : wx)) + (int32_t)(2 * B));
+                    uint32_t *tb1 = wtab + T::a_words;
+                    if (k < 16) {
+                        if (!LK_SW16_COMPACT) wtab[((c * QA + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = s0;
+                        if ((k & 1) == 0) { even0[c] = s0; even1[c] = s1; }
+                        else {
+                            if (LK_SW16_COMPACT) wtab[((c * QB + (k >> 3)) * 32 + lane) * 4 + ((k >> 1) & 3)] = even0[c] | (s0 << 16);
+                            tb1[((c * QB + (k >> 3)) * 32 + lane) * 4 + ((k >> 1) & 3)] = even1[c] | (s1 << 16);
+                        }
+                    } else {
+                        wtab[T::a_quad_words + c * 32 + lane] = s0;
+                        tb1[T::b_quad_words + c * 32 + lane] = s1 << 16;
+                    }
                 }
-            } else {
-                wtab[T::a_quad_words + c * 32 + lane] = s0;
-                tb1[T::b_quad_words + c * 32 + lane] = s1 << 16;
             }
         }
     }

@@ -39,6 +39,10 @@
 #ifndef LK_SW_LEAN_UNROLL
 #define LK_SW_LEAN_UNROLL 1
 #endif
+// independent loads per lane and round trip of the traceback's diagonal scan
+#ifndef LK_SW_TRACE_LOADS
+#define LK_SW_TRACE_LOADS 2
+#endif
 #define LK_SW_PRAGMA_(x) _Pragma(#x)
 #define LK_SW_PRAGMA(x) LK_SW_PRAGMA_(x)
 
@@ -272,16 +276,32 @@ LK_DEV void sw_finish(Wp &w, const SwArgs &A, int pair, int n, int m, int32_t co
         const int lim = (p1 < p2) ? p1 : p2;  // cells available along the diagonal
         int run = 0;
         uint32_t stop_nib = 0;
-        for (;;) {  // 64 cells of the diagonal per round trip: the two loads of a lane are independent
-            const int t0 = run + lane, t1 = t0 + 32;
-            uint32_t nb0 = 0xFFu, nb1 = 0xFFu;
-            if (t0 < lim) nb0 = nibble(p1 - t0, p2 - t0);
-            if (t1 < lim) nb1 = nibble(p1 - t1, p2 - t1);
-            const unsigned nd0 = w.ballot(t0 >= lim || (nb0 & 3u) != 0u);
-            const unsigned nd1 = w.ballot(t1 >= lim || (nb1 & 3u) != 0u);
-            if ((nd0 | nd1) == 0u) { run += 64; continue; }
-            if (nd0 != 0u) { const int f = w.ffs(nd0) - 1; run += f; stop_nib = w.shfl(nb0, f); }
-            else { const int f = w.ffs(nd1) - 1; run += 32 + f; stop_nib = w.shfl(nb1, f); }
+        for (;;) {  // 32 NL cells of the diagonal per round trip: the NL loads of a lane are independent
+            constexpr int NL = LK_SW_TRACE_LOADS;
+            uint32_t nb[NL];
+            unsigned nd[NL], any = 0u;
+#pragma unroll
+            for (int q = 0; q < NL; q++) {
+                const int t = run + 32 * q + lane;
+                nb[q] = (t < lim) ? nibble(p1 - t, p2 - t) : 0xFFu;
+            }
+#pragma unroll
+            for (int q = 0; q < NL; q++) {
+                const int t = run + 32 * q + lane;
+                nd[q] = w.ballot(t >= lim || (nb[q] & 3u) != 0u);
+                any |= nd[q];
+            }
+            if (any == 0u) { run += 32 * NL; continue; }
+            bool found = false;
+#pragma unroll
+            for (int q = 0; q < NL; q++) {
+                if (!found && nd[q] != 0u) {
+                    const int f = w.ffs(nd[q]) - 1;
+                    run += 32 * q + f;
+                    stop_nib = w.shfl(nb[q], f);
+                    found = true;
+                }
+            }
             break;
         }
         if (run > 0) {  // `run` diagonal steps

@@ -114,13 +114,14 @@ static cudaError_t launch_sw_duo_k(const SwArgs &A, int n_blocks, cudaStream_t s
     return cudaGetLastError();
 }
 
-// K classes the packed kernel is built for (references of 257..544 rows); the launcher falls back to launch_sw otherwise
-bool sw_duo_has_k(int K) { return K == 16 || K == 17; }
+// K classes the packed kernel is built for (references of 129..544 rows); the launcher falls back to launch_sw otherwise
+bool sw_duo_has_k(int K) { return K == 8 || K == 16 || K == 17; }
 // n_warps: per-warp scratch slices available; the grid is the device's fill of the packed kernel, or fewer
 cudaError_t launch_sw_duo(int K, const SwArgs &A, int n_sm, int64_t n_warps, cudaStream_t st) {
     if (A.n_order == 0) return cudaSuccess;
     const int n_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm * LK_SW16_BLOCKS_PER_SM, n_warps / LK_SW16_BLOCK_WARPS));
     if (n_warps < LK_SW16_BLOCK_WARPS) return cudaErrorInvalidValue;
+    if (K == 8) return launch_sw_duo_k<8>(A, n_blocks, st);
     if (K == 16) return launch_sw_duo_k<16>(A, n_blocks, st);
     if (K == 17) return launch_sw_duo_k<17>(A, n_blocks, st);
     return cudaErrorInvalidValue;

@@ -66,13 +66,21 @@ def _compare(pairs, params, strategy, max_ops=256, force_k=0, expect_duo=None):
 
 
 @pytest.mark.parametrize("strategy", SC.STRATEGIES)
-def test_small_equal_length_references_all_params(strategy):
-    # short references under K = 16: up to 31 of the 32 lanes hold virtual rows (SoftClip / Ignore) or stay idle (InDel)
+@pytest.mark.parametrize("force_k", [8, 16])
+def test_small_equal_length_references_all_params(strategy, force_k):
+    # short references under K = 8 / 16: up to 31 of the 32 lanes hold virtual rows (SoftClip / Ignore) or stay idle (InDel)
     pairs = equal_n_pairs(24, seed=len(strategy), min_len=3, max_len=90)
     taken = 0
     for params in SC.ALL_PARAMS:
-        taken += int(_compare(pairs, params, strategy, force_k=16).sum())
+        taken += int(_compare(pairs, params, strategy, force_k=force_k).sum())
     assert taken > 0
+
+
+def test_k8_class_sizes():
+    # the class the host gives K = 8: references of 129..256 rows
+    pairs = equal_n_pairs(6, seed=88, min_len=129, max_len=256, max_indel=15)
+    for strategy in SC.STRATEGIES:
+        _compare(pairs, SC.NEW_SW_PARAMETERS, strategy, max_ops=512, force_k=8)
 
 
 @pytest.mark.parametrize("force_k", [16, 17])
