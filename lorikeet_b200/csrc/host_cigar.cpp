@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -307,6 +308,29 @@ extern "C" lk_status lk_calculate_cigar_finish(const uint8_t *ref, int64_t ref_l
 
 // CigarUtils::calculate_cigar for a batch of (reference, alternate) pairs: shortcuts on the host, every remaining pair
 // padded with 10 x 'N' and aligned in ONE lk_sw_batch_host call, CIGAR surgery on the host.
+namespace {
+// The context's page-locked staging for one assembled SW batch (see lk_ctx::stage_*): held for the duration of the batch.
+struct SwStage {
+    std::unique_lock<std::mutex> lock;
+    uint8_t *refs = nullptr, *alts = nullptr;
+    uint32_t *ops = nullptr;
+    int32_t *n = nullptr, *off = nullptr;
+    bool reserve(lk_ctx *ctx, size_t ref_bytes, size_t alt_bytes, size_t pairs, size_t max_ops) {
+        lock = std::unique_lock<std::mutex>(ctx->stage_mu);
+        cudaSetDevice(ctx->device);
+        const bool ok = ctx->stage_refs.reserve(std::max<size_t>(ref_bytes, 16)) == cudaSuccess &&
+                        ctx->stage_alts.reserve(std::max<size_t>(alt_bytes, 16)) == cudaSuccess &&
+                        ctx->stage_ops.reserve(std::max<size_t>(pairs * max_ops * 4, 16)) == cudaSuccess &&
+                        ctx->stage_n.reserve(std::max<size_t>(pairs * 4, 16)) == cudaSuccess &&
+                        ctx->stage_off.reserve(std::max<size_t>(pairs * 4, 16)) == cudaSuccess;
+        if (!ok) { (void)cudaGetLastError(); return false; }
+        refs = (uint8_t *)ctx->stage_refs.p; alts = (uint8_t *)ctx->stage_alts.p; ops = (uint32_t *)ctx->stage_ops.p;
+        n = (int32_t *)ctx->stage_n.p; off = (int32_t *)ctx->stage_off.p;
+        return true;
+    }
+};
+}  // namespace
+
 extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, const int64_t *ref_off, const uint8_t *refs,
                                               const int64_t *alt_off, const uint8_t *alts, const lk_sw_params *params,
                                               lk_sw_overhang strategy, int32_t max_ops, uint32_t *cigar_ops, int32_t *n_ops) {
@@ -337,23 +361,22 @@ extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, cons
         pro[(size_t)i + 1] = pro[(size_t)i] + (ref_off[p + 1] - ref_off[p]) + 2 * kSwPad;
         pao[(size_t)i + 1] = pao[(size_t)i] + (alt_off[p + 1] - alt_off[p]) + 2 * kSwPad;
     }
-    std::unique_ptr<uint8_t[]> prefs(new (std::nothrow) uint8_t[(size_t)pro.back()]), palts(new (std::nothrow) uint8_t[(size_t)pao.back()]);
-    if (!prefs || !palts) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    const int64_t sw_max_ops = std::max<int64_t>(8, (int64_t)max_ops + 8);
+    SwStage stage;
+    if (!stage.reserve(ctx, (size_t)pro.back(), (size_t)pao.back(), (size_t)T, (size_t)sw_max_ops)) return lk_fail(ctx, LK_ERR_NOMEM, "out of page-locked host memory");
+    uint8_t *const prefs = stage.refs, *const palts = stage.alts;
+    uint32_t *const sw_ops = stage.ops;
+    int32_t *const sw_n = stage.n, *const sw_off = stage.off;
     lk::parallel_for(T, kGrain, [&](int64_t i_begin, int64_t i_end) {
         for (int64_t i = i_begin; i < i_end; i++) {
             const int64_t p = todo[(size_t)i];
             const int64_t rl = ref_off[p + 1] - ref_off[p], al = alt_off[p + 1] - alt_off[p];
-            uint8_t *r = prefs.get() + pro[(size_t)i], *a = palts.get() + pao[(size_t)i];
+            uint8_t *r = prefs + pro[(size_t)i], *a = palts + pao[(size_t)i];
             memset(r, 'N', (size_t)kSwPad); memcpy(r + kSwPad, refs + ref_off[p], (size_t)rl); memset(r + kSwPad + rl, 'N', (size_t)kSwPad);
             memset(a, 'N', (size_t)kSwPad); memcpy(a + kSwPad, alts + alt_off[p], (size_t)al); memset(a + kSwPad + al, 'N', (size_t)kSwPad);
         }
     });
-    const int64_t sw_max_ops = std::max<int64_t>(8, (int64_t)max_ops + 8);
-    std::unique_ptr<uint32_t[]> sw_ops(new (std::nothrow) uint32_t[(size_t)T * (size_t)sw_max_ops]);
-    if (!sw_ops) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
-    std::vector<int32_t> sw_n((size_t)T), sw_off((size_t)T);
-    lk_status st = lk_sw_batch_host(ctx, T, pro.data(), prefs.get(), pao.data(), palts.get(), params, strategy,
-                                    (int32_t)sw_max_ops, sw_ops.get(), sw_n.data(), sw_off.data());
+    lk_status st = lk_sw_batch_host(ctx, T, pro.data(), prefs, pao.data(), palts, params, strategy, (int32_t)sw_max_ops, sw_ops, sw_n, sw_off);
     if (st != LK_OK) return st;
     std::atomic<int> failed{ (int)LK_OK };
     lk::parallel_for(T, kGrain, [&](int64_t i_begin, int64_t i_end) {
@@ -361,7 +384,7 @@ extern "C" lk_status lk_calculate_cigar_batch(lk_ctx *ctx, int64_t n_pairs, cons
             const int64_t p = todo[(size_t)i];
             if (sw_n[(size_t)i] == -2) { n_ops[p] = -2; continue; }
             const lk_status fs = lk_calculate_cigar_finish(refs + ref_off[p], ref_off[p + 1] - ref_off[p], alts + alt_off[p],
-                                                           alt_off[p + 1] - alt_off[p], sw_ops.get() + (size_t)i * (size_t)sw_max_ops,
+                                                           alt_off[p + 1] - alt_off[p], sw_ops + (size_t)i * (size_t)sw_max_ops,
                                                            sw_n[(size_t)i], sw_off[(size_t)i], max_ops, cigar_ops + p * max_ops, &n_ops[p]);
             if (fs != LK_OK) failed.store((int)fs);
         }
@@ -651,23 +674,22 @@ extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch 
         }
     }
     constexpr int64_t kGrain = 2048;
-    std::unique_ptr<uint8_t[]> refs(new (std::nothrow) uint8_t[(size_t)std::max<int64_t>(ro.back(), 1)]),
-                               alts(new (std::nothrow) uint8_t[(size_t)std::max<int64_t>(ao.back(), 1)]);
-    if (!refs || !alts) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
+    const lk_sw_params prm = { 10, -15, -30, -5 };  // ALIGNMENT_TO_BEST_HAPLOTYPE_SW_PARAMETERS, smith_waterman_aligner.rs:22-25
+    const int32_t sw_max_ops = std::max<int32_t>(max_ops, 64);
+    SwStage stage;
+    if (!stage.reserve(ctx, (size_t)std::max<int64_t>(ro.back(), 1), (size_t)std::max<int64_t>(ao.back(), 1), (size_t)T, (size_t)sw_max_ops))
+        return lk_fail(ctx, LK_ERR_NOMEM, "out of page-locked host memory");
+    uint8_t *const refs = stage.refs, *const alts = stage.alts;
+    uint32_t *const sw_ops = stage.ops;
+    int32_t *const sw_n = stage.n, *const sw_off = stage.off;
     lk::parallel_for(T, kGrain, [&](int64_t i_begin, int64_t i_end) {
         for (int64_t i = i_begin; i < i_end; i++) {
             const int64_t r = todo[(size_t)i], h = hap_of[(size_t)i];
-            memcpy(alts.get() + ao[(size_t)i], b->read_bases + b->read_off[r], (size_t)(b->read_off[r + 1] - b->read_off[r]));
-            memcpy(refs.get() + ro[(size_t)i], b->hap_bases + b->hap_off[h], (size_t)(b->hap_off[h + 1] - b->hap_off[h]));
+            memcpy(alts + ao[(size_t)i], b->read_bases + b->read_off[r], (size_t)(b->read_off[r + 1] - b->read_off[r]));
+            memcpy(refs + ro[(size_t)i], b->hap_bases + b->hap_off[h], (size_t)(b->hap_off[h + 1] - b->hap_off[h]));
         }
     });
-    const lk_sw_params prm = { 10, -15, -30, -5 };  // ALIGNMENT_TO_BEST_HAPLOTYPE_SW_PARAMETERS, smith_waterman_aligner.rs:22-25
-    const int32_t sw_max_ops = std::max<int32_t>(max_ops, 64);
-    std::unique_ptr<uint32_t[]> sw_ops(new (std::nothrow) uint32_t[(size_t)T * (size_t)sw_max_ops]);
-    if (!sw_ops) return lk_fail(ctx, LK_ERR_NOMEM, "out of host memory");
-    std::vector<int32_t> sw_n((size_t)T), sw_off((size_t)T);
-    lk_status st = lk_sw_batch_host(ctx, T, ro.data(), refs.get(), ao.data(), alts.get(), &prm, LK_SW_SOFTCLIP,
-                                    sw_max_ops, sw_ops.get(), sw_n.data(), sw_off.data());
+    lk_status st = lk_sw_batch_host(ctx, T, ro.data(), refs, ao.data(), alts, &prm, LK_SW_SOFTCLIP, sw_max_ops, sw_ops, sw_n, sw_off);
     if (st != LK_OK) return st;
     // ---- CIGAR composition per read (host, spread over the cores for large batches) ----
     std::atomic<int> failed{ (int)LK_OK };
@@ -678,7 +700,7 @@ extern "C" lk_status lk_realign_reads_batch(lk_ctx *ctx, const lk_realign_batch 
             const lk_status fs = lk_realign_finish(
                 b->read_bases + b->read_off[r], b->read_off[r + 1] - b->read_off[r], b->read_cigars + b->read_cigar_off[r],
                 (int32_t)(b->read_cigar_off[r + 1] - b->read_cigar_off[r]), b->read_orig_len[r],
-                sw_ops.get() + (size_t)i * (size_t)sw_max_ops, sw_n[(size_t)i], sw_off[(size_t)i], b->hap_cigars + b->hap_cigar_off[h],
+                sw_ops + (size_t)i * (size_t)sw_max_ops, sw_n[(size_t)i], sw_off[(size_t)i], b->hap_cigars + b->hap_cigar_off[h],
                 (int32_t)(b->hap_cigar_off[h + 1] - b->hap_cigar_off[h]), b->hap_start_wrt_ref[h], b->hap_bases + b->hap_off[href],
                 b->hap_off[href + 1] - b->hap_off[href], b->reference_start[g], max_ops, cigar_ops + r * (int64_t)max_ops, &n_ops[r], &pos[r]);
             if (fs != LK_OK) failed.store((int)fs);

@@ -123,6 +123,7 @@ extern "C" void lk_destroy(lk_ctx *ctx) {
         if (ctx->sw_ws[i]) { lk_resident_free(nullptr, ctx->sw_ws[i]); ctx->sw_ws[i] = nullptr; }
     ctx->d_qerr_f.release(); ctx->d_qerr_d.release(); ctx->d_m2m.release();
     ctx->d_ba_blocks.release(); ctx->d_ba_prio.release(); ctx->d_ba_best.release(); ctx->d_ba_info.release();
+    ctx->stage_refs.release(); ctx->stage_alts.release(); ctx->stage_ops.release(); ctx->stage_n.release(); ctx->stage_off.release();
     delete ctx;
 }
 

@@ -48,6 +48,10 @@ struct lk_ctx {
     // main kernel and would otherwise delay the copy, and with it chunk i+2's kernels, past the end of chunk i+1.
     lk_resident *ws[3] = { nullptr, nullptr, nullptr };
     lk_resident *sw_ws[3] = { nullptr, nullptr, nullptr };  // same for lk_sw_batch_host
+    // page-locked, grow-only staging of the SW batches the callers in host_cigar.cpp assemble (padded pairs in, raw CIGARs out),
+    // so that lk_sw_batch_host's chunk copies are truly asynchronous; one such batch at a time per context
+    std::mutex stage_mu;
+    PinnedBuf stage_refs, stage_alts, stage_ops, stage_n, stage_off;
 };
 
 struct lk_resident {
