@@ -204,9 +204,9 @@ def run_extras(ctx, args, peak_fp32):
 
 
 # figures read from the committed ncu capture of the SW kernel (never measured inside the bench)
-SW_NCU = {"instr_per_cell": 13.6, "dram_bytes_per_cell": 0.78,
-          "source": "profiles/r02_sw_duo_kernel_k17_metrics.txt (packed two-pairs-per-warp kernel, 20 000 cfg4 pairs: 2.29e9 warp "
-                    "instructions = 7.33e10 thread instructions, 3.07 GB written + 1.16 GB read over 5.41e9 cells; the one-pair "
+SW_NCU = {"instr_per_cell": 12.2, "dram_bytes_per_cell": 0.77,
+          "source": "profiles/r02_sw_duo_kernel_k17_metrics.txt (packed two-pairs-per-warp kernel, 20 000 cfg4 pairs: 6.58e10 thread "
+                    "instructions in 2.28e9 warp instructions, 2.93 GB written + 1.22 GB read over 5.41e9 cells; the one-pair "
                     "kernel it replaces on this workload: 17.9 instructions and 0.80 bytes per cell)"}
 
 
