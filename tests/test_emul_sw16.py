@@ -158,3 +158,38 @@ def test_n_padded_haplotypes_as_calculate_cigar_makes_them():
     for strategy in SC.STRATEGIES:
         took = _compare(pairs, SC.NEW_SW_PARAMETERS, strategy, force_k=16)
         assert took.all()
+
+
+def test_random_weights_up_to_the_eligibility_limits():
+    # the packed arithmetic keeps every 16-bit half inside [0, 65535] only for bounded weights (sw16_weights_ok: |w| <= 1000,
+    # open <= extend < 0): random parameter sets up to those limits, including the corners, against the oracle
+    rng = np.random.default_rng(1000)
+    sets = [[1000, -1000, -1000, -1], [1000, -1000, -1000, -1000], [1, -1, -1, -1], [1000, 1000, -1000, -500],
+            [-1000, -1000, -2, -1], [0, 0, -1000, -999], [7, -1000, -13, -13], [1000, -1, -1000, -1]]
+    for _ in range(10):
+        wo = -int(rng.integers(1, 1001))
+        sets.append([int(rng.integers(-50, 1001)), int(rng.integers(-1000, 51)), wo, -int(rng.integers(1, -wo + 1))])
+    pairs = equal_n_pairs(10, seed=31, min_len=20, max_len=120, max_indel=10)
+    for i, params in enumerate(sets):
+        assert E_weights_ok(params), params
+        strategy = SC.STRATEGIES[i % 4]
+        took = _compare(pairs, params, strategy, force_k=8)
+        assert took.any() or strategy in ("SoftClip", "Ignore")
+
+
+def test_long_gaps_and_repeats():
+    # long insertions / deletions (gap length recovered by walking the early-stored open flags) and low-complexity sequence
+    # (many ties between opening and extending, and between the three moves)
+    rng = np.random.default_rng(77)
+    pairs = []
+    for n in (150, 200):
+        ref = rng.choice(ACGT, n)
+        pairs.append((ref, np.concatenate([ref[:40], ref[100:]])))                      # 60-base deletion
+        pairs.append((ref.copy(), np.concatenate([ref[:70], rng.choice(ACGT, 45), ref[70:]])))  # 45-base insertion
+    rep = np.frombuffer(b"ACAC" * 40, np.uint8)
+    pairs += [(rep, np.frombuffer(b"AC" * 71, np.uint8)), (rep.copy(), np.frombuffer(b"ACAC" * 20 + b"AAAA" + b"ACAC" * 18, np.uint8))]
+    homo = np.frombuffer(b"A" * 140, np.uint8)
+    pairs += [(homo, np.frombuffer(b"A" * 100, np.uint8)), (homo.copy(), np.frombuffer(b"A" * 60 + b"C" + b"A" * 90, np.uint8))]
+    for strategy in SC.STRATEGIES:
+        for params in (SC.NEW_SW_PARAMETERS, SC.ORIGINAL_DEFAULT, [5, -4, -6, -6]):
+            _compare(pairs, params, strategy, max_ops=256, force_k=8)
