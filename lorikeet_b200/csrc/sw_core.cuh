@@ -383,10 +383,20 @@ LK_DEV void sw_dp_pair(Wp &w, const SwArgs &A, int pair, uint32_t *scratch, int3
     bool use_table;
     {
         bool other = false;
-        for (int j = lane; j < m; j += 32) {
-            const int cl = sw_byte_class(alt[j]);
-            other |= (cl == SW_N_CLASSES);
-            acls[j] = (uint8_t)(cl == SW_N_CLASSES ? 0 : cl);
+        for (int j0 = 0; j0 < m; j0 += 128) {  // four independent loads per lane and round trip
+            uint32_t by[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + q * 32 + lane;
+                by[q] = (j < m) ? (uint32_t)w.ldg(alt + j) : (uint32_t)'A';
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int j = j0 + q * 32 + lane;
+                const int cl = sw_byte_class(by[q]);
+                other |= (cl == SW_N_CLASSES);
+                if (j < m) acls[j] = (uint8_t)(cl == SW_N_CLASSES ? 0 : cl);
+            }
         }
         use_table = w.ballot(other) == 0u;
         w.sync();
