@@ -86,7 +86,7 @@ struct lk_resident {
     int64_t n_blocks = 0;   // (region, sample) blocks of the staged chunk
     bool sampled = false;   // several samples per region: block_region is in use
     // ---- Smith-Waterman ----
-    struct SwLaunch { int K; int32_t first; int32_t count; bool clamp; bool duo; };
+    struct SwLaunch { int K; int32_t first; int32_t count; bool clamp; int duo; };  // duo: 0 one pair per warp, 1 packed (equal reference lengths), 2 packed (any)
     std::vector<SwLaunch> sw_launches;
     int sw_blocks = 0;
     int64_t sw_scratch_words = 0;

@@ -46,6 +46,6 @@ cudaError_t launch_best_alleles(const double *values, const BestAlleleBlock *blo
                                 double informative_threshold, int32_t *best_allele, uint8_t *informative, cudaStream_t st);
 cudaError_t launch_sw(int K, bool clamp, const SwArgs &A, int n_blocks, cudaStream_t st);
 bool sw_duo_has_k(int K);
-cudaError_t launch_sw_duo(int K, const SwArgs &A, int n_sm, int64_t n_warps, cudaStream_t st);
+cudaError_t launch_sw_duo(int K, bool same_n, const SwArgs &A, int n_sm, int64_t n_warps, cudaStream_t st);
 
 }  // namespace lk

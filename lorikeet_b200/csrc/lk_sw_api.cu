@@ -26,11 +26,13 @@ namespace {
 const int kSwKs[] = { LK_SW_KS };
 constexpr int kNumSwKs = (int)(sizeof(kSwKs) / sizeof(kSwKs[0]));
 
-// LK_SW_DUO=0 in the environment keeps every pair on the one-pair-per-warp kernel (A/B measurements)
-bool sw_duo_enabled() {
-    static const bool on = [] { const char *e = getenv("LK_SW_DUO"); return !(e && e[0] == '0'); }();
-    return on;
+// A/B measurements: LK_SW_DUO=0 in the environment keeps every pair on the one-pair-per-warp kernel, LK_SW_DUO=2 sends every
+// packed launch to the any-lengths kernel
+int sw_duo_mode() {
+    static const int mode = [] { const char *e = getenv("LK_SW_DUO"); return (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1); }();
+    return mode;
 }
+bool sw_duo_enabled() { return sw_duo_mode() != 0; }
 
 int sw_choose_k(int n) {
     for (int i = 0; i < kNumSwKs; i++)
@@ -115,8 +117,30 @@ lk_status sw_stage_range(lk_ctx *ctx, lk_resident *R, int64_t p0, int64_t p1, co
         for (int ki = 0; ki < kNumSwKs; ki++) {
             if (count[ki] > 0) {
                 const bool clamp = !sw_clamp_inactive(nm_max[ki], params->match_value, params->mismatch_penalty, params->gap_open_penalty, params->gap_extend_penalty);
-                R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)count[ki], clamp, duo[ki] });
-                if (duo[ki]) max_words = std::max(max_words, sw16_scratch_words((int)m_max[ki], kSwKs[ki]));
+                if (!duo[ki]) {
+                    R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)count[ki], clamp, 0 });
+                } else {
+                    // The class is sorted by reference length.  Pairs that form duos of EQUAL length go first and run on the
+                    // kernel built for that (the faster one); what is left -- the odd one of every length, and the banded
+                    // references of the last class -- follows and runs on the any-lengths kernel.
+                    const int rows = 32 * kSwKs[ki];
+                    int32_t *run = order.data() + first;
+                    std::vector<int32_t> rest;
+                    int64_t w = 0;
+                    for (int64_t a = 0; a < count[ki];) {
+                        const int64_t pa = p0 + run[a], na = ref_off[pa + 1] - ref_off[pa];
+                        int64_t b = a + 1;
+                        while (b < count[ki] && ref_off[p0 + run[b] + 1] - ref_off[p0 + run[b]] == na) b++;
+                        const int64_t len = b - a, take = (na <= rows && sw_duo_mode() == 1) ? (len & ~(int64_t)1) : 0;
+                        for (int64_t q = 0; q < take; q++) run[w++] = run[a + q];  // w <= a: in place
+                        for (int64_t q = take; q < len; q++) rest.push_back(run[a + q]);
+                        a = b;
+                    }
+                    std::copy(rest.begin(), rest.end(), run + w);
+                    if (w > 0) R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)w, clamp, 1 });
+                    if (!rest.empty()) R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first + (int32_t)w, (int32_t)rest.size(), clamp, 2 });
+                    max_words = std::max(max_words, sw16_scratch_words((int)m_max[ki], kSwKs[ki]));
+                }
             }
             first += (int32_t)count[ki];
         }
@@ -196,7 +220,7 @@ lk_status sw_enqueue(lk_ctx *ctx, lk_resident *R, cudaStream_t st) {
         A.n_order = L.count;
         A.cursor = (int32_t *)R->counters.p + li++;
         // the packed kernel runs 12 warps per SM (its two weight tables per warp), the one-pair kernel 16
-        e = L.duo ? launch_sw_duo(L.K, A, ctx->n_sm, (int64_t)R->sw_blocks * (LK_SW_THREADS / 32), st) : launch_sw(L.K, L.clamp, A, R->sw_blocks, st);
+        e = L.duo ? launch_sw_duo(L.K, L.duo == 1, A, ctx->n_sm, (int64_t)R->sw_blocks * (LK_SW_THREADS / 32), st) : launch_sw(L.K, L.clamp, A, R->sw_blocks, st);
         if (e != cudaSuccess) return lk_cuda_fail(ctx, e, "sw_kernel");
         R->launch_count++;
     }

@@ -28,7 +28,8 @@
 //
 // Eligibility (sw16_weights_ok + the checks in sw16_align_duo; everything else takes sw_core.cuh): |weights| <= 1000,
 // open <= extend < 0, the -1e8 clamp proven inactive, both alternates made of A C G T N only (the classes of the weight
-// tables), both references of the same length n <= 32 K (one band).
+// tables), both references within one band of the launch's K class (n <= 32 K; K = 8 / 16 / 17, references of 129..544 rows;
+// the two lengths may differ).
 #pragma once
 #include "sw_core.cuh"
 
@@ -164,9 +165,12 @@ LK_HD int64_t sw16_scratch_words(int M, int K) {
     return (w + 3) & ~(int64_t)3;
 }
 
-// Aligns pairs pa and pb (same reference length n <= 32 K, prologue already done for both).  false: not eligible (an
+// Aligns pairs pa and pb (reference lengths <= 32 K, prologue already done for both).  false: not eligible (an
 // alternate holds a byte outside A C G T N) -- nothing has been written for either pair and the caller takes sw_dp_pair.
-template <class Wp, int K>
+// SAME_N: both references have the same length (one set of row indices; the case every haplotype of a region against that
+// region's reference is).  The general form costs ~6 % on cfg#4, and both forms inlined into ONE kernel cost the faster one
+// its register allocation, so each lives in a kernel of its own (sw_duo_kernel<K, SAME_N>) and the host gives each its pairs.
+template <class Wp, int K, bool SAME_N>
 LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scratch, int32_t *wtab_i) {
     typedef Sw16Table<K> T;
     constexpr int QA = T::quads_a, QB = T::quads_b;
@@ -177,7 +181,8 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
     const int pr[2] = { pa, pb };
     const uint8_t *ref[2] = { A.refs + A.ref_off[pa], A.refs + A.ref_off[pb] };
     const uint8_t *alt[2] = { A.alts + A.alt_off[pa], A.alts + A.alt_off[pb] };
-    const int n = (int)(A.ref_off[pa + 1] - A.ref_off[pa]);
+    const int n0 = (int)(A.ref_off[pa + 1] - A.ref_off[pa]), n1 = SAME_N ? n0 : (int)(A.ref_off[pb + 1] - A.ref_off[pb]);
+    const int N = n0 > n1 ? n0 : n1;
     const int mm[2] = { (int)(A.alt_off[pa + 1] - A.alt_off[pa]), (int)(A.alt_off[pb + 1] - A.alt_off[pb]) };
     const int M = mm[0] > mm[1] ? mm[0] : mm[1], m_min = mm[0] < mm[1] ? mm[0] : mm[1];
     const int strategy = A.strategy;
@@ -185,11 +190,12 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
     const bool edge_gaps = (strategy == SW_INDEL || strategy == SW_LEADING_INDEL);
     const bool need_bottom = !edge_gaps;
     constexpr int BAND = 32 * K;
-    // SoftClip / Ignore: the rows are shifted down so that the matrix's last row is register K-1 of lane 31 (see sw_core.cuh,
-    // bottom alignment); the pad_top rows above row 1 are virtual rows that reproduce the all-zero top row
-    const int pad_top = need_bottom ? BAND - n : 0;
-    const int lanes = need_bottom ? 32 : (n + K - 1) / K;
-
+    // SoftClip / Ignore: each pair's rows are shifted down so that its matrix's last row is register K-1 of lane 31 (see
+    // sw_core.cuh, bottom alignment); the pad_top rows above row 1 are virtual rows that reproduce the all-zero top row, as
+    // many as that pair's reference is short of 32 K.  The edge-gap strategies cannot have virtual rows (their top row
+    // carries gap penalties): both pairs start at row 1 and the shorter reference is followed by rows nobody reads.
+    const int pad0 = need_bottom ? BAND - n0 : 0, pad1 = SAME_N ? pad0 : (need_bottom ? BAND - n1 : 0);
+    const int lanes = need_bottom ? 32 : (N + K - 1) / K;
     LK_SW16_TICK_INIT;
     uint32_t *planes = scratch;                                               // [step][lane] x {pd, pr, vo, ho}
     uint8_t *nibs = reinterpret_cast<uint8_t *>(planes + ((int64_t)M + 32) * 128);  // [step][lane], row 16 of both pairs
@@ -233,25 +239,26 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
         int rcls0[RB], rcls1[RB];  // class of a row in either reference (SW_N_CLASSES: no base, never matches)
 #pragma unroll
         for (int kk = 0; kk < RB; kk++) {
-            const int i = lane * K + k0 + kk + 1 - pad_top;
-            const bool real = (k0 + kk < K) && (i >= 1 && i <= n);
-            rcls0[kk] = real ? (int)w.ldg(ref[0] + (real ? i - 1 : 0)) : 0;
-            rcls1[kk] = real ? (int)w.ldg(ref[1] + (real ? i - 1 : 0)) : 0;
+            const int i0 = lane * K + k0 + kk + 1 - pad0, i1 = SAME_N ? i0 : lane * K + k0 + kk + 1 - pad1;
+            const bool real0 = (k0 + kk < K) && (i0 >= 1 && i0 <= n0), real1 = SAME_N ? real0 : ((k0 + kk < K) && (i1 >= 1 && i1 <= n1));
+            rcls0[kk] = real0 ? (int)w.ldg(ref[0] + (real0 ? i0 - 1 : 0)) : 0;
+            rcls1[kk] = real1 ? (int)w.ldg(ref[1] + (real1 ? i1 - 1 : 0)) : 0;
         }
 #pragma unroll
         for (int kk = 0; kk < RB; kk++) {
             const int k = k0 + kk;
             if (k < K) {
-                const int i = lane * K + k + 1 - pad_top;  // 1-based matrix row; < 1: virtual row
-                const int32_t u0 = edge_gaps ? (i == 1 ? wo : we) : 0;  // sw[i][0] - sw[i-1][0] (:146-179)
+                // 1-based matrix row of either pair; < 1: virtual row (SoftClip / Ignore only)
+                const int i0 = lane * K + k + 1 - pad0, i1 = SAME_N ? i0 : lane * K + k + 1 - pad1;
+                const int32_t u0 = edge_gaps ? (i0 == 1 ? wo : we) : 0;  // sw[i][0] - sw[i-1][0] (:146-179); no padding when edge_gaps
                 u[k < K ? k : 0] = sw16_both(B + (uint32_t)u0);
                 ny[k < K ? k : 0] = Dp;                                  // best_gap_h starts at i32::MIN / 2: the first gap opens
                 const int cls0 = sw_byte_class((uint32_t)rcls0[kk]), cls1 = sw_byte_class((uint32_t)rcls1[kk]);
 #pragma unroll
                 for (int c = 0; c < SW_N_CLASSES; c++) {
                     // a virtual row scores 0 against every column
-                    const uint32_t s0 = (uint32_t)(((i < 1) ? 0 : ((cls0 == c) ? wm : wx)) + (int32_t)(2 * B));
-                    const uint32_t s1 = (uint32_t)(((i < 1) ? 0 : ((cls1 == c) ? wm : wx)) + (int32_t)(2 * B));
+                    const uint32_t s0 = (uint32_t)(((i0 < 1) ? 0 : ((cls0 == c) ? wm : wx)) + (int32_t)(2 * B));
+                    const uint32_t s1 = (uint32_t)(((i1 < 1) ? 0 : ((cls1 == c) ? wm : wx)) + (int32_t)(2 * B));
                     uint32_t *tb1 = wtab + T::a_words;
                     if (k < 16) {
                         if (!LK_SW16_COMPACT) wtab[((c * QA + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = s0;
@@ -339,12 +346,15 @@ LK_DEV bool sw16_align_duo(Wp &w, const SwArgs &A, int pa, int pb, uint32_t *scr
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     if (c == mm[h]) {  // this lane's rows of pair h's last column, top -> bottom with >= (:301-307)
+                        // (a second reference length is re-read here rather than kept in a register across the lean loop)
+                        const int n_h = SAME_N ? n0 : (int)(A.ref_off[pr[h] + 1] - A.ref_off[pr[h]]);
+                        const int pad_h = SAME_N ? pad0 : (need_bottom ? BAND - n_h : 0);
                         int32_t run = 0;
 #pragma unroll
                         for (int k = 0; k < K; k++) {
-                            const int i = lane * K + k + 1 - pad_top;
+                            const int i = lane * K + k + 1 - pad_h;
                             run += (int32_t)((u[k] >> (16 * h)) & 0xffffu) - (int32_t)B;
-                            if (i >= 1 && i <= n && run >= col_best[h]) { col_best[h] = run; col_row[h] = i; }
+                            if (i >= 1 && i <= n_h && run >= col_best[h]) { col_best[h] = run; col_row[h] = i; }
                         }
                         col_tot[h] = run;
                     }
@@ -373,7 +383,7 @@ LK_SW_PRAGMA(unroll LK_SW16_LEAN_UNROLL)
 
     // ---- per pair: absolute last column and bottom row, then start cell, traceback and output as in sw_core.cuh ---------
     for (int h = 0; h < 2; h++) {
-        const int m = mm[h];
+        const int m = mm[h], n = SAME_N ? n0 : (int)(A.ref_off[pr[h] + 1] - A.ref_off[pr[h]]), pad_h = SAME_N ? pad0 : (need_bottom ? BAND - n : 0);
         // last column: H(i, m) = H(0, m) + sum of u over the rows above and including i
         int32_t incl = col_tot[h];
         for (int d = 1; d < 32; d <<= 1) {
@@ -402,7 +412,7 @@ LK_SW_PRAGMA(unroll LK_SW16_LEAN_UNROLL)
         LK_SW16_TICK(3);
         // backtrack bits of matrix cell (i, j), 1-based, of pair h
         auto nibble = [&](int i, int j) -> uint32_t {
-            const int ii = i - 1 + pad_top;
+            const int ii = i - 1 + pad_h;
             const int ln = ii / K, k = ii % K;
             const int64_t el = (int64_t)(j + ln) * 32 + ln;  // the cell was written at step j + ln by lane ln
             // both loads unconditionally and without a branch, so that the loads of consecutive calls overlap

@@ -69,7 +69,7 @@ template <int K> struct SwDuoSmem { static constexpr int words = Sw16Table<K>::w
 #define LK_SW16_BLOCKS_PER_SM (LK_SW16_COMPACT ? 4 : 3)
 #endif
 
-template <int K>
+template <int K, bool SAME_N>
 __global__ void __launch_bounds__(LK_SW16_BLOCK_WARPS * 32, LK_SW16_BLOCKS_PER_SM) sw_duo_kernel(const SwArgs A) {
     extern __shared__ int4 lk_sw_smem[];
     int32_t *wtab = reinterpret_cast<int32_t *>(lk_sw_smem) + (threadIdx.x >> 5) * SwDuoSmem<K>::words;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(LK_SW16_BLOCK_WARPS * 32, LK_SW16_BLOCKS_PER_S
         LK_SW16_TICK(5);
         if (!done_a && !done_b) {
             const int64_t na = A.ref_off[pa + 1] - A.ref_off[pa], nb = A.ref_off[pb + 1] - A.ref_off[pb];
-            if (na == nb && na <= 32 * K && sw16_align_duo<SwDevWarp, K>(w, A, pa, pb, scratch, wtab)) {
+            if (na <= 32 * K && nb <= 32 * K && (!SAME_N || na == nb) && sw16_align_duo<SwDevWarp, K, SAME_N>(w, A, pa, pb, scratch, wtab)) {
                 if (w.lane() == 0) atomicAdd(A.packed_count, 2);
                 __syncwarp();
                 continue;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(LK_SW16_BLOCK_WARPS * 32, LK_SW16_BLOCKS_PER_S
     }
 }
 
-template <int K>
+template <int K, bool SAME_N>
 static cudaError_t launch_sw_duo_k(const SwArgs &A, int n_blocks, cudaStream_t st) {
     const int smem = LK_SW16_BLOCK_WARPS * SwDuoSmem<K>::words * (int)sizeof(int32_t);
     static bool configured_on[64] = { false };
@@ -106,24 +106,25 @@ static cudaError_t launch_sw_duo_k(const SwArgs &A, int n_blocks, cudaStream_t s
     cudaGetDevice(&dev);
     bool &configured = configured_on[dev & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sw_duo_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(sw_duo_kernel<K, SAME_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    sw_duo_kernel<K><<<n_blocks, LK_SW16_BLOCK_WARPS * 32, smem, st>>>(A);
+    sw_duo_kernel<K, SAME_N><<<n_blocks, LK_SW16_BLOCK_WARPS * 32, smem, st>>>(A);
     return cudaGetLastError();
 }
 
 // K classes the packed kernel is built for (references of 129..544 rows); the launcher falls back to launch_sw otherwise
 bool sw_duo_has_k(int K) { return K == 8 || K == 16 || K == 17; }
 // n_warps: per-warp scratch slices available; the grid is the device's fill of the packed kernel, or fewer
-cudaError_t launch_sw_duo(int K, const SwArgs &A, int n_sm, int64_t n_warps, cudaStream_t st) {
+// same_n: every two consecutive pairs of the order have references of the same length (the host arranges the order so)
+cudaError_t launch_sw_duo(int K, bool same_n, const SwArgs &A, int n_sm, int64_t n_warps, cudaStream_t st) {
     if (A.n_order == 0) return cudaSuccess;
     const int n_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm * LK_SW16_BLOCKS_PER_SM, n_warps / LK_SW16_BLOCK_WARPS));
     if (n_warps < LK_SW16_BLOCK_WARPS) return cudaErrorInvalidValue;
-    if (K == 8) return launch_sw_duo_k<8>(A, n_blocks, st);
-    if (K == 16) return launch_sw_duo_k<16>(A, n_blocks, st);
-    if (K == 17) return launch_sw_duo_k<17>(A, n_blocks, st);
+    if (K == 8) return same_n ? launch_sw_duo_k<8, true>(A, n_blocks, st) : launch_sw_duo_k<8, false>(A, n_blocks, st);
+    if (K == 16) return same_n ? launch_sw_duo_k<16, true>(A, n_blocks, st) : launch_sw_duo_k<16, false>(A, n_blocks, st);
+    if (K == 17) return same_n ? launch_sw_duo_k<17, true>(A, n_blocks, st) : launch_sw_duo_k<17, false>(A, n_blocks, st);
     return cudaErrorInvalidValue;
 }
 

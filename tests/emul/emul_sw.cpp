@@ -125,7 +125,9 @@ extern "C" int emul_sw_duo_batch(int64_t n_pairs, const int64_t *ref_off, const 
                     const bool done_a = sw_prologue(w, A, pa), done_b = (pb < 0) || sw_prologue(w, A, pb);
                     if (!done_a && !done_b) {
                         const int64_t na = ref_off[pa + 1] - ref_off[pa], nb = ref_off[pb + 1] - ref_off[pb];
-                        if (na == nb && na <= 32 * KV && sw16_align_duo<SwEmulWarp, KV>(w, A, pa, pb, scratch.data(), wtab.data())) { took[l] = 1; return; }
+                        if (na <= 32 * KV && nb <= 32 * KV &&
+                            (na == nb ? sw16_align_duo<SwEmulWarp, KV, true>(w, A, pa, pb, scratch.data(), wtab.data())
+                                      : sw16_align_duo<SwEmulWarp, KV, false>(w, A, pa, pb, scratch.data(), wtab.data()))) { took[l] = 1; return; }
                     }
                     if (!done_a) { sw_dp_pair<SwEmulWarp, KV, false>(w, A, pa, scratch.data(), wtab.data()); w.sync(); }
                     if (!done_b) { sw_dp_pair<SwEmulWarp, KV, false>(w, A, pb, scratch.data(), wtab.data()); w.sync(); }

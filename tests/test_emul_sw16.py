@@ -102,12 +102,32 @@ def test_haplotype_sized_duos(force_k):
     _compare(pairs, SC.ALIGNMENT_TO_BEST_HAPLOTYPE, "SoftClip", max_ops=512, force_k=force_k)
 
 
+@pytest.mark.parametrize("strategy", SC.STRATEGIES)
+def test_references_of_different_lengths_share_a_warp(strategy):
+    # each pair gets its own number of virtual rows (SoftClip / Ignore) or is followed by unread rows (InDel / LeadingInDel)
+    rng = np.random.default_rng(len(strategy) + 40)
+    pairs = []
+    for _ in range(12):
+        for n in (int(rng.integers(5, 200)), int(rng.integers(5, 200))):
+            ref = rng.choice(ACGT, n)
+            mode = int(rng.integers(0, 3))
+            alt = _mutate(rng, ref, int(rng.integers(0, 4)), 6) if mode else rng.choice(ACGT, int(rng.integers(3, 150)))
+            if mode == 2 and len(alt) > 10:
+                alt = alt[int(rng.integers(1, 5)):-int(rng.integers(1, 5))]
+            pairs.append((ref, alt))
+    pairs += [(rng.choice(ACGT, 256), rng.choice(ACGT, 40)), (rng.choice(ACGT, 1), rng.choice(ACGT, 90))]  # the extremes of the class
+    taken = 0
+    for params in SC.ALL_PARAMS:
+        taken += int(_compare(pairs, params, strategy, force_k=8).sum())
+    assert taken > 0
+
+
 def test_dispatch_falls_back_pair_by_pair():
     rng = np.random.default_rng(5)
     ref = rng.choice(ACGT, 60)
     a1, a2 = _mutate(rng, ref, 3, 5), _mutate(rng, ref, 3, 5)
     other = np.frombuffer(b"ACGTNRYacgt", np.uint8)
-    pairs = [(ref, a1), (rng.choice(ACGT, 61), a2),                     # different reference lengths
+    pairs = [(ref, a1), (rng.choice(ACGT, 700), a2),                    # a reference beyond the class's one band
              (ref, a1), (ref, np.concatenate([a2[:20], other, a2[20:]])),  # bytes outside A C G T N in one alternate
              (ref, ref[5:40]), (ref, a2),                                # exact substring: finished by the prologue
              (ref, a1)]                                                  # odd one out

@@ -168,10 +168,10 @@ def test_bytes_outside_acgtn_and_clamped_form(ctx):
 
 
 def test_packed_two_pairs_per_warp_kernel(ctx):
-    """References of equal length in the 257..544-row classes go two to a warp (sw16_core.cuh, 16-bit difference arithmetic):
-    same (offset, CIGAR) as the oracle for every strategy and parameter set, alternates of different lengths inside a duo,
-    N pads as calculate_cigar adds them, and pairs that do not qualify (other lengths, bytes outside ACGTN, exact-substring
-    hits) mixed in."""
+    """References of 129..544 rows go two to a warp (sw16_core.cuh, 16-bit difference arithmetic): same (offset, CIGAR) as the
+    oracle for every strategy and parameter set, references and alternates of different lengths inside a duo, N pads as
+    calculate_cigar adds them, and pairs that do not qualify (banded references, bytes outside ACGTN, exact-substring hits)
+    mixed in."""
     rng = np.random.default_rng(77)
     acgt = np.frombuffer(b"ACGT", np.uint8)
     pad = np.frombuffer(b"N" * 10, np.uint8)
@@ -190,8 +190,8 @@ def test_packed_two_pairs_per_warp_kernel(ctx):
         return alt
 
     pairs = []
-    for n in (260, 300, 411, 500, 512, 513, 520, 524, 544):
-        for _ in range(6):
+    for n in (140, 200, 256, 260, 300, 411, 500, 512, 513, 520, 524, 544):
+        for _ in range(5):
             ref = rng.choice(acgt, n - 20)
             mode = int(rng.integers(0, 4))
             alt = mutate(ref, int(rng.integers(1, 6)), 25)
@@ -209,7 +209,7 @@ def test_packed_two_pairs_per_warp_kernel(ctx):
     _compare(ctx, pairs, SC.STANDARD_NGS, "LeadingInDel", max_ops=512)
     _compare(ctx, pairs, SC.ALIGNMENT_TO_BEST_HAPLOTYPE, "SoftClip", max_ops=512)
     _compare(ctx, pairs, SC.ORIGINAL_DEFAULT, "InDel", max_ops=512)
-    # the packed kernel is what ran: all 54 equal-length pairs under InDel (no substring shortcut), minus odd leftovers
+    # the packed kernel is what ran: nearly all 60 pairs of the three classes under InDel (no substring shortcut)
     ro, refs, ao, alts = SC.pack(pairs)
     r = ctx.sw_upload(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, "InDel", max_ops=512)
     r.run()
