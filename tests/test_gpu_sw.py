@@ -221,3 +221,33 @@ def test_packed_two_pairs_per_warp_kernel(ctx):
     r2.run()
     assert r2.packed_pairs == 0
     r.free(); r2.free()
+
+
+def test_mixed_lengths_at_scale(ctx):
+    """2 400 pairs with reference lengths drawn from 100..600 and unrelated alternate lengths: the host order splits every class
+    into equal-length duos (equal-length packed kernel), the odd ones (any-lengths packed kernel), banded references and small
+    classes (one-pair kernels); every result against the oracle."""
+    rng = np.random.default_rng(2024)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    lens = rng.choice(np.arange(100, 601, 7), 2400)   # 72 distinct lengths: most of them occur an odd number of times somewhere
+    pairs = []
+    for n in lens:
+        ref = rng.choice(acgt, int(n))
+        alt = ref.copy()
+        for _ in range(int(rng.integers(0, 4))):
+            p = int(rng.integers(5, len(alt) - 5))
+            if rng.random() < 0.5:
+                alt = np.delete(alt, slice(p, p + int(rng.integers(1, 20))))
+            else:
+                alt = np.insert(alt, p, rng.choice(acgt, int(rng.integers(1, 20))))
+        if rng.random() < 0.3:
+            alt = alt[int(rng.integers(0, 30)):len(alt) - int(rng.integers(0, 30))]
+        pairs.append((ref, alt))
+    for strategy, params in (("SoftClip", SC.NEW_SW_PARAMETERS), ("LeadingInDel", SC.STANDARD_NGS), ("InDel", SC.ALIGNMENT_TO_BEST_HAPLOTYPE)):
+        _compare(ctx, pairs, params, strategy, max_ops=512)
+    ro, refs, ao, alts = SC.pack(pairs)
+    r = ctx.sw_upload(ro, refs, ao, alts, SC.NEW_SW_PARAMETERS, "InDel", max_ops=512)
+    r.run()
+    in_classes = int(((lens > 128) & (lens <= 544)).sum())
+    assert r.packed_pairs >= in_classes - 6, (r.packed_pairs, in_classes)  # all of them but the odd last one of each class
+    r.free()
