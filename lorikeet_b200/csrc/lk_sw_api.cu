@@ -85,7 +85,7 @@ lk_status sw_stage_range(lk_ctx *ctx, lk_resident *R, int64_t p0, int64_t p1, co
     }
     // order array: one contiguous run per K class, longest pairs first inside a class (better tail balance of the
     // persistent grid), by a counting sort: the order only has to be roughly descending.  A class the packed kernel serves
-    // (sw16_core.cuh: two consecutive pairs of the order per warp when their references have the same length) is ordered by
+    // (sw16_core.cuh: two consecutive pairs of the order per warp, best when their references have the same length) is ordered by
     // reference length first, then by alternate length in 16 steps, so that neighbours qualify; the others by cell count
     // in 256 steps.
     {
