@@ -22,7 +22,7 @@
 #define LK_FAST_K_TABLE(X) X(4, 4) X(6, 4) X(8, 4) X(10, 4) X(12, 3) X(14, 3) X(15, 3) X(16, 3) X(19, LK_K19_MINB) X(20, 3)
 #define LK_FAST_KS 4, 6, 8, 10, 12, 14, 15, 16, 19, 20
 // Smith-Waterman: rows per lane (K) variants; a pair with n reference rows uses the smallest K with 32*K >= n,
-// longer references are processed in bands of 32*17 rows.
+// longer references are processed in bands of 32*17 rows.  K >= 8 also exist as packed two-pairs-per-warp kernels.
 #define LK_SW_THREADS 128
-#define LK_SW_K_TABLE(X) X(2) X(4) X(8) X(16) X(17)
-#define LK_SW_KS 2, 4, 8, 16, 17
+#define LK_SW_K_TABLE(X) X(2) X(4) X(8) X(12) X(16) X(17)
+#define LK_SW_KS 2, 4, 8, 12, 16, 17

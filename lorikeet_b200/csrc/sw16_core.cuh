@@ -28,7 +28,7 @@
 //
 // Eligibility (sw16_weights_ok + the checks in sw16_align_duo; everything else takes sw_core.cuh): |weights| <= 1000,
 // open <= extend < 0, the -1e8 clamp proven inactive, both alternates made of A C G T N only (the classes of the weight
-// tables), both references within one band of the launch's K class (n <= 32 K; K = 8 / 16 / 17, references of 129..544 rows;
+// tables), both references within one band of the launch's K class (n <= 32 K; K = 8 / 12 / 16 / 17, references of 129..544 rows;
 // the two lengths may differ).
 #pragma once
 #include "sw_core.cuh"
@@ -148,9 +148,9 @@ LK_DEV uint32_t sw16_fsub(uint32_t a, uint32_t b, uint32_t mone) {
 // of a warp would not leave room for 12 warps per SM.  A cell's two weights are packed by one IMAD (even rows: w1 * 65536 + w0)
 // or one LOP3 (odd rows: (w1 & 0xffff0000) | w0).
 template <int K> struct Sw16Table {
-    static_assert(K == 17 || (K % 8 == 0 && K <= 16), "rows come in groups of eight, plus one odd row for K = 17");
+    static_assert(K == 17 || (K % 4 == 0 && K <= 16), "rows come in groups of four, plus one odd row for K = 17");
     static constexpr int rows16 = K < 16 ? K : 16;
-    static constexpr int quads_a = rows16 / 4, quads_b = rows16 / 8;
+    static constexpr int quads_a = rows16 / 4, quads_b = (rows16 + 7) / 8;  // K = 12: the second 16-bit quad is half used
     static constexpr int a_quad_words = SW_N_CLASSES * (LK_SW16_COMPACT ? quads_b : quads_a) * 128, b_quad_words = SW_N_CLASSES * quads_b * 128;
     static constexpr int a_words = a_quad_words + (K > 16 ? SW_N_CLASSES * 32 : 0);
     static constexpr int b_words = b_quad_words + (K > 16 ? SW_N_CLASSES * 32 : 0);

@@ -115,7 +115,7 @@ static cudaError_t launch_sw_duo_k(const SwArgs &A, int n_blocks, cudaStream_t s
 }
 
 // K classes the packed kernel is built for (references of 129..544 rows); the launcher falls back to launch_sw otherwise
-bool sw_duo_has_k(int K) { return K == 8 || K == 16 || K == 17; }
+bool sw_duo_has_k(int K) { return K == 8 || K == 12 || K == 16 || K == 17; }
 // n_warps: per-warp scratch slices available; the grid is the device's fill of the packed kernel, or fewer
 // same_n: every two consecutive pairs of the order have references of the same length (the host arranges the order so)
 cudaError_t launch_sw_duo(int K, bool same_n, const SwArgs &A, int n_sm, int64_t n_warps, cudaStream_t st) {
@@ -123,6 +123,7 @@ cudaError_t launch_sw_duo(int K, bool same_n, const SwArgs &A, int n_sm, int64_t
     const int n_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)n_sm * LK_SW16_BLOCKS_PER_SM, n_warps / LK_SW16_BLOCK_WARPS));
     if (n_warps < LK_SW16_BLOCK_WARPS) return cudaErrorInvalidValue;
     if (K == 8) return same_n ? launch_sw_duo_k<8, true>(A, n_blocks, st) : launch_sw_duo_k<8, false>(A, n_blocks, st);
+    if (K == 12) return same_n ? launch_sw_duo_k<12, true>(A, n_blocks, st) : launch_sw_duo_k<12, false>(A, n_blocks, st);
     if (K == 16) return same_n ? launch_sw_duo_k<16, true>(A, n_blocks, st) : launch_sw_duo_k<16, false>(A, n_blocks, st);
     if (K == 17) return same_n ? launch_sw_duo_k<17, true>(A, n_blocks, st) : launch_sw_duo_k<17, false>(A, n_blocks, st);
     return cudaErrorInvalidValue;

@@ -110,7 +110,7 @@ extern "C" int emul_sw_duo_batch(int64_t n_pairs, const int64_t *ref_off, const 
         int64_t nmax = 0, mmax = 0;
         for (int q : { pa, pb })
             if (q >= 0) { nmax = std::max(nmax, ref_off[q + 1] - ref_off[q]); mmax = std::max(mmax, alt_off[q + 1] - alt_off[q]); }
-        const int K = force_k > 0 ? force_k : (nmax <= 256 ? 8 : (nmax <= 512 ? 16 : 17));
+        const int K = force_k > 0 ? force_k : (nmax <= 256 ? 8 : (nmax <= 384 ? 12 : (nmax <= 512 ? 16 : 17)));
         if (!sw_clamp_inactive(nmax + mmax, params[0], params[1], params[2], params[3])) return -2;
         std::vector<int32_t> wtab((size_t)std::max(SwTable<17>::words, Sw16Table<17>::words));
         std::vector<uint32_t> scratch((size_t)std::max<int64_t>(64, std::max(nmax > 0 && mmax > 0 ? sw_scratch_words((int)nmax, (int)mmax, K) : 64,
@@ -133,6 +133,7 @@ extern "C" int emul_sw_duo_batch(int64_t n_pairs, const int64_t *ref_off, const 
                     if (!done_b) { sw_dp_pair<SwEmulWarp, KV, false>(w, A, pb, scratch.data(), wtab.data()); w.sync(); }
                 };
                 if (K == 8) run(std::integral_constant<int, 8>());
+                else if (K == 12) run(std::integral_constant<int, 12>());
                 else if (K == 16) run(std::integral_constant<int, 16>());
                 else run(std::integral_constant<int, 17>());
             });

@@ -32,7 +32,7 @@ def test_random_pairs_all_params(strategy):
         _compare(pairs, params, strategy)
 
 
-@pytest.mark.parametrize("force_k", [2, 4])
+@pytest.mark.parametrize("force_k", [2, 4, 12])
 def test_multi_band_small_k(force_k):
     # forcing a small K makes references of 70..200 rows span several row bands
     pairs = SC.random_pairs(16, seed=3, min_len=70, max_len=200)

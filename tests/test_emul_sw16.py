@@ -83,6 +83,19 @@ def test_k8_class_sizes():
         _compare(pairs, SC.NEW_SW_PARAMETERS, strategy, max_ops=512, force_k=8)
 
 
+def test_k12_class_sizes():
+    # K = 12 (references of 257..384 rows): the second quad of 16-bit table rows is half used, six row pairs per plane byte
+    pairs = equal_n_pairs(4, seed=12, min_len=257, max_len=384, max_indel=15)
+    pairs += [(pairs[0][0][:300], pairs[1][1]), (pairs[2][0], pairs[3][1][:200])]  # and a duo of different lengths
+    for strategy in SC.STRATEGIES:
+        took = _compare(pairs, SC.NEW_SW_PARAMETERS, strategy, max_ops=512, force_k=12)
+        assert took.any()
+    small = equal_n_pairs(12, seed=13, min_len=3, max_len=120)
+    for params in SC.ALL_PARAMS:
+        _compare(small, params, "SoftClip", force_k=12)
+        _compare(small, params, "LeadingInDel", force_k=12)
+
+
 @pytest.mark.parametrize("force_k", [16, 17])
 def test_haplotype_sized_duos(force_k):
     # references of 300..544 rows, alternates of different lengths within a duo: lean middle steps, the tail that runs to the

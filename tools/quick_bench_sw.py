@@ -11,7 +11,8 @@ import lorikeet_b200 as lk
 from lorikeet_b200 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-ro, refs, ao, alts = synth.sw_pairs(n)
+ref_len = int(sys.argv[2]) if len(sys.argv) > 2 else 500  # + 2 x 10 N pads
+ro, refs, ao, alts = synth.sw_pairs(n, ref_len=ref_len)
 with lk.Context(0) as ctx:
     for strategy in ("SoftClip", "InDel"):
         res = ctx.sw_upload(ro, refs, ao, alts, [200, -150, -260, -11], strategy, max_ops=64)
