@@ -137,8 +137,16 @@ lk_status sw_stage_range(lk_ctx *ctx, lk_resident *R, int64_t p0, int64_t p1, co
                         a = b;
                     }
                     std::copy(rest.begin(), rest.end(), run + w);
-                    if (w > 0) R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)w, clamp, 1 });
-                    if (!rest.empty()) R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first + (int32_t)w, (int32_t)rest.size(), clamp, 2 });
+                    // A short tail is not worth a launch of its own (it would start after the main one has drained and run on a
+                    // handful of warps): up to eight left-over pairs ride along in the equal-lengths launch, where unequal neighbours
+                    // take the one-pair routine; a few equal-length duos ride along in the any-lengths launch.
+                    const int64_t few = std::max<int64_t>(64, count[ki] / 50);
+                    if ((int64_t)rest.size() <= 8 && w > 0) R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)count[ki], clamp, 1 });
+                    else if (w <= few) R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)count[ki], clamp, 2 });
+                    else {
+                        R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first, (int32_t)w, clamp, 1 });
+                        R->sw_launches.push_back(lk_resident::SwLaunch{ kSwKs[ki], first + (int32_t)w, (int32_t)rest.size(), clamp, 2 });
+                    }
                     max_words = std::max(max_words, sw16_scratch_words((int)m_max[ki], kSwKs[ki]));
                 }
             }
