@@ -16,6 +16,15 @@
 // (:253-260).  Absolute scores are needed only along the last column and the bottom row (:301-329); they are rebuilt from
 // u and v by prefix sums after the fill.
 //
+// Ranges (S = max|substitution weight|, G = max|gap weight|, both <= 1000 here).  u, v >= open >= -G because a cell is at
+// least the gap opened from its upper / left neighbour.  u <= S + G: if the cell took the diagonal, u = s - v(i-1,j) <= S + G;
+// if it took the vertical gap, u = extend - nx <= 0; if it took a horizontal gap of length k, the same gap is available to
+// row i-1 (E(i-1,j) >= H(i-1,j-k) + open + (k-1) extend), so u(i,j) <= u(i,j-k), which ends at one of the first two cases or
+// in column 0 (u in {0, open, extend}); v by symmetry.  Hence z = u + v(i-1,j) in [-2G, 2S + 2G], a, b in [-3G, z],
+// nf = H - F <= u - open <= S + 2G, and with the biases below every half stays inside [1048, 8096] (values) or below
+// 0x7fff + 5000 (flag words): no carry ever leaves a half.  The same holds for the cells nobody reads (rows past a reference,
+// columns past an alternate): they are ordinary cells of a larger problem.
+//
 // Representation: every half is an UNSIGNED biased value and every sum below ends in [0, 65535] per half, so plain 32-bit
 // adds and subtracts never carry between the halves and can issue on either integer pipe (IADD3 on the ALU pipe, IMAD on
 // the FMA pipe): u, v carry bias B; s, a, b, z carry 2 B; nf, ne, nx, ny are plain.  A flag is the top bit of a half of
