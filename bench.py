@@ -159,6 +159,20 @@ def run_extras(ctx, args, peak_fp32):
             best = min(best, time.perf_counter() - t0)
         out["cfg4_smith_waterman"]["e2e"] = {"ms": best * 1e3, "gcups": n_cells / best / 1e9,
                                              "api": "lk_sw_batch_host (the gkl::smithwaterman::align seam, batched), pinned host buffers"}
+        if not args.no_cpu_baseline:
+            # the reference's scalar SW (C restatement, the checker of the parity tests) on the first 4 000 pairs, all host cores
+            from oracle import lk_oracle as O
+            ns = 4000
+            r_, a_ = ro[:ns + 1], ao[:ns + 1]
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            O.sw_batch(r_, refs[:r_[-1]], a_, alts[:a_[-1]], [200, -150, -260, -11], "SoftClip", max_ops=64, n_threads=cores)
+            dt = time.perf_counter() - t0
+            sc = float((np.diff(r_) * np.diff(a_)).sum())
+            out["cfg4_smith_waterman"]["cpu_baseline"] = {
+                "value": sc / dt / 1e9, "unit": "GCUPS", "cores": cores, "kind": "port",
+                "sample": "first %d pairs of the same generator (%.3e cells, %.2f s)" % (ns, sc, dt),
+                "note": "C restatement of the reference's in-tree scalar path (smith_waterman_aligner.rs:124-442); gkl's AVX path is not vendored"}
     except Exception as e:  # side measurements must never break the bench line
         out["cfg4_error"] = str(e)
     try:
